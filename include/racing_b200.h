@@ -1,0 +1,177 @@
+/*
+ * racing_b200.h -- C ABI of the B200-native batched racing backend.
+ *
+ * The reference (LucasHJin/self-play-racing) is pure Python and has no FFI; the
+ * boundary its hot path sits behind is the Gymnasium surface.
+ * Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure and never
+ *    throws; rk_last_error() describes the last failure on that handle (or the
+ *    last create failure when the handle is NULL);
+ *  - "dev" pointers are DEVICE pointers owned by the caller (e.g. torch
+ *    tensors); "host" pointers are ordinary host memory;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *    stream); all step/reset/gae/policy calls are asynchronous on it;
+ *  - one handle per GPU; a handle is not thread-safe, distinct handles are;
+ *  - E = num_envs, A = num_agents, R = num_sensors,
+ *    D = obs_dim = R + 4 (single) or R + 4 + 4*(A-1) (multi).
+ */
+#ifndef RACING_B200_H
+#define RACING_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RK_API __attribute__((visibility("default")))
+#else
+#define RK_API
+#endif
+
+#define RK_ABI_VERSION 1
+#define RK_MAX_AGENTS 8
+#define RK_MAX_SENSORS 64
+
+typedef struct rk_env_s* rk_handle;
+
+/* env_kind: which reference class' rules apply */
+enum { RK_ENV_SINGLE = 0,   /* environment/racing_env.py  RacingEnv          */
+       RK_ENV_MULTI = 1 };  /* environment/multi_racing_env.py MultiRacingEnv */
+/* autoreset_mode: gymnasium 1.x SyncVectorEnv semantics (agent/ppo.py:70,114) */
+enum { RK_AUTORESET_NEXT_STEP = 0, RK_AUTORESET_SAME_STEP = 1, RK_AUTORESET_DISABLED = 2 };
+/* query_mode: how waypoint-argmin and raycast candidates are found.  Both give
+ * the reference's float64 result; CULLED finds candidates in fp32 over
+ * bounding-circle chunks and re-evaluates the winners in float64. */
+enum { RK_QUERY_EXACT_F64 = 0, RK_QUERY_CULLED = 1 };
+
+typedef struct rk_config {
+    int32_t struct_size;        /* sizeof(rk_config), for ABI checking                */
+    int32_t device;             /* CUDA device ordinal                                 */
+    int32_t num_envs;           /* E                                                   */
+    int32_t num_agents;         /* A (must be 1 for RK_ENV_SINGLE)                     */
+    int32_t num_sensors;        /* R, rays per car (racing_env.py:9, multi:9)          */
+    int32_t env_kind;           /* RK_ENV_*                                            */
+    int32_t autoreset_mode;     /* RK_AUTORESET_*                                      */
+    int32_t query_mode;         /* RK_QUERY_*                                          */
+    int32_t max_episode_steps;  /* <=0 -> 3000 (racing_env.py:162)                     */
+    int32_t reserved0;
+    double speed_weight;        /* single env speed bonus weight (racing_env.py:9,140) */
+    uint64_t seed;              /* Philox key for start-slot shuffles, random opponent */
+} rk_config;
+
+/* ---- lifetime ------------------------------------------------------------ */
+RK_API int rk_create(const rk_config* cfg, rk_handle* out);
+RK_API int rk_destroy(rk_handle h);
+RK_API const char* rk_last_error(rk_handle h);
+RK_API int rk_abi_version(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+RK_API uint64_t rk_launch_count(void);
+
+/* ---- tracks: replaces Track.__init__ (environment/track.py:61-148) ------- */
+/* Build the pool on the device from control points: periodic cubic spline
+ * (the algorithm of scipy CubicSpline(bc_type='periodic'), track.py:100-115),
+ * normals (:117-124), boundaries (:93-94), segment table (:126-148), bbox
+ * diagonal (:82-91), start pose (:154-157).  host_ctrl_xy holds the tracks'
+ * control points back to back as (x, y) pairs; waypoints per track =
+ * n_ctrl[t] * factor (the reference uses factor 30).  host_env_to_track may be
+ * NULL (env e uses track e % n_tracks). */
+RK_API int rk_set_tracks_from_control_points(rk_handle h, const double* host_ctrl_xy, const int32_t* host_n_ctrl,
+                                      const double* host_widths, int32_t n_tracks, int32_t factor,
+                                      const int32_t* host_env_to_track);
+/* Same, but from ready-made waypoints (float64, e.g. taken from the reference's
+ * Track.waypoints) so that discrete events are bit-comparable with the
+ * reference: only IEEE-exact operations separate waypoints from the tables. */
+RK_API int rk_set_tracks_from_waypoints(rk_handle h, const double* host_wp_xy, const int32_t* host_n_wp,
+                                 const double* host_widths, int32_t n_tracks,
+                                 const int32_t* host_env_to_track);
+/* Procedural pool generated on the device with the distributions of
+ * gen_tracks/gen_random_track (track.py:4-56) from a Philox stream; widths are
+ * width_lo + (t % width_mod).  For synthetic benchmark configurations. */
+RK_API int rk_generate_tracks(rk_handle h, uint64_t seed, int32_t n_tracks, int32_t factor,
+                       double width_lo, int32_t width_mod, const int32_t* host_env_to_track);
+RK_API int rk_num_tracks(rk_handle h);
+/* Export one track (what utils/visualization.py reads from env.track).  Any
+ * pointer may be NULL; host_meta receives {n_wp, width, max_track_distance,
+ * start_x, start_y, start_angle}.  Arrays are (x, y) pairs, n_wp entries. */
+RK_API int rk_get_track(rk_handle h, int32_t track_id, double* host_meta6, double* host_waypoints,
+                 double* host_normals, double* host_left, double* host_right, double* host_ctrl,
+                 int32_t* n_ctrl_out);
+
+/* ---- env: replaces RacingEnv/MultiRacingEnv.reset/step + SyncVectorEnv ---- */
+/* reset (racing_env.py:86-102, multi_racing_env.py:118-153).  dev_mask: uint8
+ * [E] or NULL (all).  dev_start_slot: int32 [E,A] slot of each car on the grid
+ * (multi_racing_env.py:127-138) or NULL (Philox shuffle).  dev_obs: float32
+ * [E,A,D] or NULL. */
+RK_API int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs, void* stream);
+
+typedef struct rk_step_io {
+    int32_t struct_size;
+    int32_t reserved0;
+    const float* actions;        /* in  [E,A,2] steer, throttle (racing_env.py:104-107)        */
+    const int32_t* start_slot;   /* in  [E,A] or NULL: slots used by auto-resets this step     */
+    float* obs;                  /* out [E,A,D]                                                 */
+    float* reward_f32;           /* out [E,A] or NULL                                           */
+    double* reward_f64;          /* out [E,A] or NULL (SyncVectorEnv returns float64)           */
+    uint8_t* terminated;         /* out [E]  crashed|finished / any finished|all crashed        */
+    uint8_t* truncated;          /* out [E]  steps >= max_episode_steps                         */
+    uint8_t* done;               /* out [E] or NULL: terminated|truncated (dones["__all__"])    */
+    float* done_f32;             /* out [E] or NULL: same as float (PPO next_done)              */
+    /* RecordEpisodeStatistics (agent/ppo.py:88,123-130): valid where ep_mask != 0 */
+    uint8_t* ep_mask;            /* out [E] or NULL */
+    double* ep_return;           /* out [E] or NULL */
+    int32_t* ep_length;          /* out [E] or NULL */
+    /* per-car info of this step (racing_env.py:77-84,156-159): may be NULL     */
+    double* info_f64;            /* out [E,A,5]: x, y, speed, progress (1.0 if finished), progress_delta */
+    int32_t* info_i32;           /* out [E,A,4]: crashed, finished, placement (0 unless ended), progress_idx */
+} rk_step_io;
+RK_API int rk_step(rk_handle h, const rk_step_io* io, void* stream);
+
+/* RacingEnv.speed_weight (racing_env.py:26; annealed by agent/ppo.py:256-258) */
+RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
+
+/* parity harness: raw state.  host_car_f64 [E,A,6] = x, y, angle, vx, vy,
+ * last_steering; host_car_i32 [E,A,4] = progress_idx, last_progress_idx, flags
+ * (bit0 crashed, 1 finished, 2..4 checkpoints, 5 has_crashed), finished_step;
+ * host_env_i32 [E,3] = steps, needs_reset, ep_length; host_env_f64 [E] =
+ * ep_return. */
+RK_API int rk_get_state(rk_handle h, double* host_car_f64, int32_t* host_car_i32, int32_t* host_env_i32, double* host_env_f64);
+RK_API int rk_set_state(rk_handle h, const double* host_car_f64, const int32_t* host_car_i32, const int32_t* host_env_i32, const double* host_env_f64);
+/* recompute observations from the current state (racing_env.py:55-75) */
+RK_API int rk_observe(rk_handle h, float* dev_obs, void* stream);
+
+/* ---- rollout-side kernels -------------------------------------------------- */
+/* GAE backward scan: PPO.compute_advantages (agent/ppo.py:134-154).  All
+ * pointers device float32; rewards/values/dones/adv/ret are [T,E]; next_value,
+ * next_done_f32 are [E]. */
+RK_API int rk_gae(const float* rewards, const float* values, const float* dones, const float* next_value,
+           const float* next_done_f32, float gamma, float lam, int32_t T, int32_t E,
+           float* adv, float* ret, void* stream);
+
+/* Fused policy inference: Agent.get_action_and_value with action=None
+ * (agent/ppo.py:43-56) for a batch of B observations of width obs_dim.
+ * params: the Agent state_dict flattened in registration order
+ *   actor_mu.{0,2,4}.{weight,bias}, log_std, critic.{0,2,4}.{weight,bias}
+ * (float32, row-major [out,in] weights as torch stores them).  obs rows are
+ * obs_stride floats apart, action rows act_stride floats apart (so a car's
+ * slice of an [E,A,*] tensor can be read/written in place).  Normal samples
+ * come from Philox(seed, counter).  logprob [B], value [B] and mean [B,2] (the
+ * pre-noise tanh output) may each be NULL (opponent inference,
+ * environment/wrappers.py:35-39, needs only the action).  If params is NULL,
+ * actions are uniform in Box([-1,0],[1,1]) -- the pool-empty opponent
+ * (wrappers.py:30-32). */
+RK_API int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
+                  uint64_t seed, uint64_t counter, float* action, int64_t act_stride,
+                  float* logprob, float* value, float* mean, void* stream);
+/* number of float32 values in the flattened Agent for a given obs_dim/action_dim=2 */
+RK_API int rk_policy_param_count(int32_t obs_dim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACING_B200_H */

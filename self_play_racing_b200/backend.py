@@ -1,0 +1,246 @@
+"""Device-resident batched racing simulator: a thin object over the C ABI.
+
+PyTorch is used only for device memory and streams; every computation on the
+step path is a kernel of librk_b200.so.  Host-side mirror of the reference's
+vectorised execution: E x (RacingEnv | MultiRacingEnv) stepped in one launch
+(reference call site: SyncVectorEnv.step in agent/ppo.py:114).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RacingBackend:
+    """E environments of one kind on one GPU.
+
+    kind='single' -> RacingEnv rules (A=1, 120 deg cone, obs R+4);
+    kind='multi'  -> MultiRacingEnv rules (A cars, 180 deg cone, obs R+4+4(A-1)).
+    Output tensors are allocated once and overwritten by every step.
+    """
+
+    def __init__(self, num_envs, kind='single', num_agents=1, num_sensors=11, device=None,
+                 autoreset='next_step', query='exact', speed_weight=8.0, seed=0,
+                 max_episode_steps=3000, want_info=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError('self_play_racing_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.kind = kind
+        self.E = int(num_envs)
+        self.A = 1 if kind == 'single' else int(num_agents)
+        self.R = int(num_sensors)
+        self.D = self.R + 4 if kind == 'single' else self.R + 4 + 4 * (self.A - 1)
+        cfg = _lib.RkConfig(struct_size=C.sizeof(_lib.RkConfig), device=self.device.index, num_envs=self.E,
+                            num_agents=self.A, num_sensors=self.R,
+                            env_kind=_lib.RK_ENV_SINGLE if kind == 'single' else _lib.RK_ENV_MULTI,
+                            autoreset_mode=_lib.AUTORESET[autoreset], query_mode=_lib.QUERY[query],
+                            max_episode_steps=int(max_episode_steps), reserved0=0,
+                            speed_weight=float(speed_weight), seed=int(seed))
+        h = C.c_void_p()
+        _lib.check(self.lib.rk_create(C.byref(cfg), C.byref(h)), None, 'rk_create')
+        self.h = h
+        E, A, D, dev = self.E, self.A, self.D, self.device
+        f32, f64, u8, i32 = torch.float32, torch.float64, torch.uint8, torch.int32
+        self.actions = torch.zeros(E, A, 2, dtype=f32, device=dev)
+        self.obs = torch.zeros(E, A, D, dtype=f32, device=dev)
+        self.reward = torch.zeros(E, A, dtype=f32, device=dev)
+        self.reward64 = torch.zeros(E, A, dtype=f64, device=dev)
+        self.terminated = torch.zeros(E, dtype=u8, device=dev)
+        self.truncated = torch.zeros(E, dtype=u8, device=dev)
+        self.done = torch.zeros(E, dtype=u8, device=dev)
+        self.done_f32 = torch.zeros(E, dtype=f32, device=dev)
+        self.ep_mask = torch.zeros(E, dtype=u8, device=dev)
+        self.ep_return = torch.zeros(E, dtype=f64, device=dev)
+        self.ep_length = torch.zeros(E, dtype=i32, device=dev)
+        self.info_f64 = torch.zeros(E, A, 5, dtype=f64, device=dev) if want_info else None
+        self.info_i32 = torch.zeros(E, A, 4, dtype=i32, device=dev) if want_info else None
+        self._io = _lib.RkStepIO(struct_size=C.sizeof(_lib.RkStepIO))
+        self._bind_io()
+
+    def _bind_io(self):
+        io = self._io
+        io.actions = self.actions.data_ptr()
+        io.start_slot = None
+        io.obs = self.obs.data_ptr()
+        io.reward_f32 = self.reward.data_ptr()
+        io.reward_f64 = self.reward64.data_ptr()
+        io.terminated = self.terminated.data_ptr()
+        io.truncated = self.truncated.data_ptr()
+        io.done = self.done.data_ptr()
+        io.done_f32 = self.done_f32.data_ptr()
+        io.ep_mask = self.ep_mask.data_ptr()
+        io.ep_return = self.ep_return.data_ptr()
+        io.ep_length = self.ep_length.data_ptr()
+        io.info_f64 = self.info_f64.data_ptr() if self.info_f64 is not None else None
+        io.info_i32 = self.info_i32.data_ptr() if self.info_i32 is not None else None
+
+    # ---- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, 'h', None):
+            torch.cuda.synchronize(self.device)
+            self.lib.rk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- tracks -----------------------------------------------------------
+    def _e2t(self, env_to_track):
+        if env_to_track is None:
+            return None
+        a = np.ascontiguousarray(env_to_track, dtype=np.int32)
+        assert a.shape == (self.E,)
+        return a
+
+    def set_tracks_from_control_points(self, control_points, widths, env_to_track=None, factor=30):
+        """Device-side Track.__init__ (track.py:61-148) for a pool of control-point arrays."""
+        n = np.array([len(c) for c in control_points], dtype=np.int32)
+        xy = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64) for c in control_points]))
+        w = np.ascontiguousarray(np.broadcast_to(np.asarray(widths, dtype=np.float64), (len(n),)))
+        e2t = self._e2t(env_to_track)
+        _lib.check(self.lib.rk_set_tracks_from_control_points(self.h, _np_ptr(xy), _np_ptr(n), _np_ptr(w), len(n),
+                                                              int(factor), _np_ptr(e2t)), self.h, 'set_tracks')
+
+    def set_tracks_from_waypoints(self, waypoints, widths, env_to_track=None):
+        n = np.array([len(c) for c in waypoints], dtype=np.int32)
+        xy = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64) for c in waypoints]))
+        w = np.ascontiguousarray(np.broadcast_to(np.asarray(widths, dtype=np.float64), (len(n),)))
+        e2t = self._e2t(env_to_track)
+        _lib.check(self.lib.rk_set_tracks_from_waypoints(self.h, _np_ptr(xy), _np_ptr(n), _np_ptr(w), len(n),
+                                                         _np_ptr(e2t)), self.h, 'set_tracks')
+
+    def generate_tracks(self, seed, n_tracks, factor=30, width_lo=6.0, width_mod=4, env_to_track=None):
+        e2t = self._e2t(env_to_track)
+        _lib.check(self.lib.rk_generate_tracks(self.h, int(seed), int(n_tracks), int(factor), float(width_lo),
+                                               int(width_mod), _np_ptr(e2t)), self.h, 'generate_tracks')
+
+    @property
+    def num_tracks(self):
+        return int(self.lib.rk_num_tracks(self.h))
+
+    def get_track(self, track_id):
+        """dict with waypoints, normals, left/right boundary, width, ... (float64, host)."""
+        meta = np.zeros(6)
+        _lib.check(self.lib.rk_get_track(self.h, int(track_id), _np_ptr(meta), None, None, None, None, None, None),
+                   self.h, 'get_track')
+        n = int(meta[0])
+        wp, nrm, left, right = (np.zeros((n, 2)) for _ in range(4))
+        ctrl = np.zeros((256, 2))
+        nc = C.c_int32(0)
+        _lib.check(self.lib.rk_get_track(self.h, int(track_id), _np_ptr(meta), _np_ptr(wp), _np_ptr(nrm),
+                                         _np_ptr(left), _np_ptr(right), _np_ptr(ctrl), C.byref(nc)),
+                   self.h, 'get_track')
+        return dict(waypoints=wp, normals=nrm, left_boundary=left, right_boundary=right,
+                    control_points=ctrl[:nc.value].copy(), track_width=meta[1], max_track_distance=meta[2],
+                    start_pos=(meta[3], meta[4], meta[5]))
+
+    # ---- env --------------------------------------------------------------
+    def reset(self, mask=None, start_slot=None):
+        """Reset all (or masked) environments; returns the obs tensor [E,A,D]."""
+        _lib.check(self.lib.rk_reset(self.h, _ptr(mask), _ptr(start_slot), _ptr(self.obs), self._stream()),
+                   self.h, 'rk_reset')
+        return self.obs
+
+    def step(self, start_slot=None):
+        """One step of all environments on self.actions; outputs land in the
+        pre-allocated tensors (obs, reward, terminated, truncated, done, ep_*)."""
+        self._io.start_slot = start_slot.data_ptr() if start_slot is not None else None
+        _lib.check(self.lib.rk_step(self.h, C.byref(self._io), self._stream()), self.h, 'rk_step')
+
+    def observe(self):
+        _lib.check(self.lib.rk_observe(self.h, _ptr(self.obs), self._stream()), self.h, 'rk_observe')
+        return self.obs
+
+    def set_speed_weight(self, w):
+        _lib.check(self.lib.rk_set_speed_weight(self.h, float(w)), self.h, 'set_speed_weight')
+
+    def get_state(self):
+        E, A = self.E, self.A
+        car_f = np.zeros((E, A, 6))
+        car_i = np.zeros((E, A, 4), dtype=np.int32)
+        env_i = np.zeros((E, 3), dtype=np.int32)
+        env_f = np.zeros(E)
+        _lib.check(self.lib.rk_get_state(self.h, _np_ptr(car_f), _np_ptr(car_i), _np_ptr(env_i), _np_ptr(env_f)),
+                   self.h, 'get_state')
+        return dict(car_f64=car_f, car_i32=car_i, env_i32=env_i, env_f64=env_f)
+
+    def set_state(self, car_f64=None, car_i32=None, env_i32=None, env_f64=None):
+        cf = None if car_f64 is None else np.ascontiguousarray(car_f64, dtype=np.float64)
+        ci = None if car_i32 is None else np.ascontiguousarray(car_i32, dtype=np.int32)
+        ei = None if env_i32 is None else np.ascontiguousarray(env_i32, dtype=np.int32)
+        ef = None if env_f64 is None else np.ascontiguousarray(env_f64, dtype=np.float64)
+        _lib.check(self.lib.rk_set_state(self.h, _np_ptr(cf), _np_ptr(ci), _np_ptr(ei), _np_ptr(ef)),
+                   self.h, 'set_state')
+
+
+# ---- rollout-side kernels ---------------------------------------------------
+def gae(rewards, values, dones, next_value, next_done, gamma, lam, adv=None, ret=None):
+    """PPO.compute_advantages (agent/ppo.py:134-154) as one kernel.  All [T,E]
+    float32 CUDA tensors; next_value [E]; next_done [E] (bool or float)."""
+    lib = _lib.load()
+    T, E = rewards.shape
+    nd = next_done.to(torch.float32)
+    rewards, values, dones, next_value = (t.contiguous() for t in (rewards, values, dones, next_value))
+    adv = torch.empty_like(rewards) if adv is None else adv
+    ret = torch.empty_like(rewards) if ret is None else ret
+    stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    _lib.check(lib.rk_gae(_ptr(rewards), _ptr(values), _ptr(dones), _ptr(next_value), _ptr(nd), float(gamma),
+                          float(lam), T, E, _ptr(adv), _ptr(ret), stream), None, 'rk_gae')
+    return adv, ret
+
+
+PARAM_ORDER = ['actor_mu.0.weight', 'actor_mu.0.bias', 'actor_mu.2.weight', 'actor_mu.2.bias',
+               'actor_mu.4.weight', 'actor_mu.4.bias', 'log_std',
+               'critic.0.weight', 'critic.0.bias', 'critic.2.weight', 'critic.2.bias',
+               'critic.4.weight', 'critic.4.bias']
+
+
+def flatten_agent(state_dict, out=None):
+    """Agent state_dict (agent/ppo.py:11-37) -> one float32 vector in PARAM_ORDER."""
+    flat = torch.cat([state_dict[k].detach().reshape(-1).to(torch.float32) for k in PARAM_ORDER])
+    if out is not None:
+        out.copy_(flat)
+        return out
+    return flat.contiguous()
+
+
+def policy_act(params, obs, action_out, seed, counter, logprob=None, value=None, mean=None):
+    """Fused Agent.get_action_and_value(obs) (action=None).  obs: [B, D] view of
+    a CUDA float32 tensor whose rows are obs.stride(0) apart (last dim
+    contiguous); action_out: [B, 2] view likewise.  params=None -> uniform
+    Box([-1,0],[1,1]) actions (SelfPlayWrapper with an empty pool)."""
+    lib = _lib.load()
+    B = action_out.shape[0]
+    assert action_out.stride(-1) == 1
+    if params is not None:
+        assert obs.stride(-1) == 1 and obs.dtype == torch.float32
+        obs_ptr, obs_stride, obs_dim = _ptr(obs), obs.stride(0), obs.shape[-1]
+    else:
+        obs_ptr, obs_stride, obs_dim = None, 0, 0
+    stream = C.c_void_p(torch.cuda.current_stream(action_out.device).cuda_stream)
+    _lib.check(lib.rk_policy_act(_ptr(params), obs_dim, obs_ptr, obs_stride, B, int(seed), int(counter),
+                                 _ptr(action_out), action_out.stride(0), _ptr(logprob), _ptr(value), _ptr(mean),
+                                 stream), None, 'rk_policy_act')

@@ -1,0 +1,432 @@
+// C ABI of librk_b200.so (declared in include/racing_b200.h).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "rk_types.cuh"
+
+namespace rk {
+
+struct PoolBuffers;  // rk_track.cu
+int build_pool(PoolBuffers& pb, int n_tracks, const int32_t* n_ctrl, const int32_t* ctrl_off, size_t total_ctrl,
+               const double* host_ctrl, const int32_t* n_wp, const double* host_wp, const double* widths,
+               const int32_t* host_env_to_track, int E, char* err, size_t errlen);
+int generate_control_points(uint64_t seed, int n_tracks, std::vector<double>& ctrl, std::vector<int32_t>& n_ctrl,
+                            char* err, size_t errlen);
+PoolBuffers* pool_new();
+void pool_delete(PoolBuffers* p);
+TrackPool pool_view(const PoolBuffers* p);
+int pool_num_tracks(const PoolBuffers* p);
+const TrackMeta* pool_host_meta(const PoolBuffers* p, int t);
+const double* pool_ctrl(const PoolBuffers* p);
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace rk
+
+using namespace rk;
+
+struct rk_env_s {
+    rk_config cfg;
+    int D = 0;
+    PoolBuffers* pool = nullptr;
+    EnvState st{};
+    double* sensor_angles = nullptr;
+    std::vector<void*> owned;
+    char err[512] = {0};
+};
+
+static char g_create_err[512] = {0};
+
+#define H_CUDA(h, call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            snprintf((h)->err, sizeof((h)->err), "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(rk_env_s* h, T** p, size_t n) {
+    H_CUDA(h, cudaMalloc((void**)p, n * sizeof(T)));
+    H_CUDA(h, cudaMemset(*p, 0, n * sizeof(T)));
+    h->owned.push_back(*p);
+    return 0;
+}
+
+extern "C" {
+
+int rk_abi_version(void) { return RK_ABI_VERSION; }
+uint64_t rk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* rk_last_error(rk_handle h) { return h ? h->err : g_create_err; }
+
+int rk_create(const rk_config* cfg, rk_handle* out) {
+    if (!cfg || !out) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_create: null argument");
+        return 1;
+    }
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(rk_config)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_create: struct_size %d != %zu (ABI mismatch)",
+                 cfg->struct_size, sizeof(rk_config));
+        return 1;
+    }
+    const bool single = cfg->env_kind == RK_ENV_SINGLE;
+    if (cfg->num_envs <= 0 || cfg->num_agents <= 0 || cfg->num_agents > RK_MAX_AGENTS || cfg->num_sensors <= 0 ||
+        cfg->num_sensors > RK_MAX_SENSORS || (single && cfg->num_agents != 1) ||
+        (cfg->env_kind != RK_ENV_SINGLE && cfg->env_kind != RK_ENV_MULTI) || cfg->autoreset_mode < 0 ||
+        cfg->autoreset_mode > RK_AUTORESET_DISABLED || cfg->query_mode < 0 || cfg->query_mode > RK_QUERY_CULLED) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "rk_create: invalid config (E=%d A=%d R=%d kind=%d autoreset=%d query=%d)", cfg->num_envs,
+                 cfg->num_agents, cfg->num_sensors, cfg->env_kind, cfg->autoreset_mode, cfg->query_mode);
+        return 1;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_create: no usable CUDA device %d (%s); there is no CPU path",
+                 cfg->device, ce != cudaSuccess ? cudaGetErrorString(ce) : "ordinal out of range");
+        return 1;
+    }
+    rk_env_s* h = new rk_env_s();
+    h->cfg = *cfg;
+    if (h->cfg.max_episode_steps <= 0) h->cfg.max_episode_steps = 3000;
+    const int E = cfg->num_envs, A = cfg->num_agents, R = cfg->num_sensors;
+    h->D = single ? R + 4 : R + 4 + 4 * (A - 1);
+    h->pool = pool_new();
+    int rc = 0;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) rc = 1;
+    const size_t C = (size_t)E * A;
+    rc = rc || dev_alloc(h, &h->st.x, C) || dev_alloc(h, &h->st.y, C) || dev_alloc(h, &h->st.ang, C) ||
+         dev_alloc(h, &h->st.vx, C) || dev_alloc(h, &h->st.vy, C) || dev_alloc(h, &h->st.last_steer, C) ||
+         dev_alloc(h, &h->st.pidx, C) || dev_alloc(h, &h->st.lpidx, C) || dev_alloc(h, &h->st.flags, C) ||
+         dev_alloc(h, &h->st.fstep, C) || dev_alloc(h, &h->st.steps, (size_t)E) ||
+         dev_alloc(h, &h->st.needs_reset, (size_t)E) || dev_alloc(h, &h->st.ep_return, (size_t)E) ||
+         dev_alloc(h, &h->st.ep_length, (size_t)E) || dev_alloc(h, &h->st.reset_count, (size_t)E) ||
+         dev_alloc(h, &h->sensor_angles, (size_t)R);
+    if (rc) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_create: %s", h->err[0] ? h->err : "cudaSetDevice failed");
+        rk_destroy(h);
+        return 1;
+    }
+    // np.linspace(-half, half, R): racing_env.py:45 (120 deg) / multi_racing_env.py:50 (180 deg)
+    std::vector<double> ang(R);
+    const double half = single ? M_PI / 3 : M_PI / 2;
+    const double start = -half, stop = half;
+    if (R == 1) {
+        ang[0] = start;
+    } else {
+        volatile double step = (stop - start) / (double)(R - 1);
+        for (int k = 0; k < R; ++k) {
+            volatile double prod = (double)k * step;  // numpy: arange(R) * step + start, no fused multiply-add
+            ang[k] = prod + start;
+        }
+        ang[R - 1] = stop;
+    }
+    cudaMemcpy(h->sensor_angles, ang.data(), R * sizeof(double), cudaMemcpyHostToDevice);
+    *out = h;
+    return 0;
+}
+
+int rk_destroy(rk_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->pool) pool_delete(h->pool);
+    delete h;
+    return 0;
+}
+
+static int set_tracks_common(rk_handle h, const double* ctrl, const int32_t* n_ctrl, const double* wp,
+                             const int32_t* n_wp_in, const double* widths, int n_tracks, int factor,
+                             const int32_t* e2t) {
+    if (!h) return 1;
+    if (n_tracks <= 0 || !widths || (!ctrl && !wp)) {
+        snprintf(h->err, sizeof(h->err), "set_tracks: invalid arguments");
+        return 1;
+    }
+    cudaSetDevice(h->cfg.device);
+    std::vector<int32_t> n_wp(n_tracks), off(n_tracks);
+    size_t total_ctrl = 0;
+    for (int t = 0; t < n_tracks; ++t) {
+        if (ctrl) {
+            if (factor <= 0) {
+                snprintf(h->err, sizeof(h->err), "set_tracks: factor must be positive");
+                return 1;
+            }
+            off[t] = (int32_t)total_ctrl;
+            total_ctrl += n_ctrl[t];
+            n_wp[t] = n_ctrl[t] * factor;
+        } else {
+            n_wp[t] = n_wp_in[t];
+        }
+    }
+    return build_pool(*h->pool, n_tracks, ctrl ? n_ctrl : nullptr, ctrl ? off.data() : nullptr, total_ctrl, ctrl,
+                      n_wp.data(), wp, widths, e2t, h->cfg.num_envs, h->err, sizeof(h->err));
+}
+
+int rk_set_tracks_from_control_points(rk_handle h, const double* host_ctrl_xy, const int32_t* host_n_ctrl,
+                                      const double* host_widths, int32_t n_tracks, int32_t factor,
+                                      const int32_t* host_env_to_track) {
+    if (h && (!host_ctrl_xy || !host_n_ctrl)) {
+        snprintf(h->err, sizeof(h->err), "set_tracks_from_control_points: null argument");
+        return 1;
+    }
+    return set_tracks_common(h, host_ctrl_xy, host_n_ctrl, nullptr, nullptr, host_widths, n_tracks, factor,
+                             host_env_to_track);
+}
+
+int rk_set_tracks_from_waypoints(rk_handle h, const double* host_wp_xy, const int32_t* host_n_wp,
+                                 const double* host_widths, int32_t n_tracks, const int32_t* host_env_to_track) {
+    if (h && (!host_wp_xy || !host_n_wp)) {
+        snprintf(h->err, sizeof(h->err), "set_tracks_from_waypoints: null argument");
+        return 1;
+    }
+    return set_tracks_common(h, nullptr, nullptr, host_wp_xy, host_n_wp, host_widths, n_tracks, 0, host_env_to_track);
+}
+
+int rk_generate_tracks(rk_handle h, uint64_t seed, int32_t n_tracks, int32_t factor, double width_lo,
+                       int32_t width_mod, const int32_t* host_env_to_track) {
+    if (!h) return 1;
+    if (n_tracks <= 0 || factor <= 0) {
+        snprintf(h->err, sizeof(h->err), "generate_tracks: invalid arguments");
+        return 1;
+    }
+    cudaSetDevice(h->cfg.device);
+    std::vector<double> ctrl;
+    std::vector<int32_t> n_ctrl;
+    if (generate_control_points(seed, n_tracks, ctrl, n_ctrl, h->err, sizeof(h->err))) return 1;
+    std::vector<double> widths(n_tracks);
+    for (int t = 0; t < n_tracks; ++t) widths[t] = width_lo + (width_mod > 0 ? t % width_mod : 0);
+    return set_tracks_common(h, ctrl.data(), n_ctrl.data(), nullptr, nullptr, widths.data(), n_tracks, factor,
+                             host_env_to_track);
+}
+
+int rk_num_tracks(rk_handle h) { return h ? pool_num_tracks(h->pool) : 0; }
+
+int rk_get_track(rk_handle h, int32_t track_id, double* meta6, double* wp, double* nrm, double* left, double* right,
+                 double* ctrl, int32_t* n_ctrl_out) {
+    if (!h) return 1;
+    if (track_id < 0 || track_id >= pool_num_tracks(h->pool)) {
+        snprintf(h->err, sizeof(h->err), "get_track: id %d out of range", track_id);
+        return 1;
+    }
+    cudaSetDevice(h->cfg.device);
+    const TrackMeta& m = *pool_host_meta(h->pool, track_id);
+    const TrackPool v = pool_view(h->pool);
+    const int N = m.n_wp;
+    if (meta6) {
+        meta6[0] = N; meta6[1] = m.width; meta6[2] = m.max_track_distance;
+        meta6[3] = m.start_x; meta6[4] = m.start_y; meta6[5] = m.start_angle;
+    }
+    std::vector<double> a(N), b(N);
+    auto fetch = [&](const double* dx, const double* dy, size_t off, double* out) -> int {
+        if (!out) return 0;
+        H_CUDA(h, cudaMemcpy(a.data(), dx + off, N * sizeof(double), cudaMemcpyDeviceToHost));
+        H_CUDA(h, cudaMemcpy(b.data(), dy + off, N * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < N; ++i) {
+            out[2 * i] = a[i];
+            out[2 * i + 1] = b[i];
+        }
+        return 0;
+    };
+    if (fetch(v.wx, v.wy, m.wp_off, wp) || fetch(v.nx, v.ny, m.wp_off, nrm) ||
+        fetch(v.sx, v.sy, 2 * (size_t)m.wp_off, left) || fetch(v.sx, v.sy, 2 * (size_t)m.wp_off + N, right))
+        return 1;
+    if (n_ctrl_out) *n_ctrl_out = m.n_ctrl;
+    if (ctrl && m.n_ctrl > 0 && pool_ctrl(h->pool))
+        H_CUDA(h, cudaMemcpy(ctrl, pool_ctrl(h->pool) + 2 * (size_t)m.ctrl_off, 2 * (size_t)m.n_ctrl * sizeof(double),
+                             cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int fill_params(rk_handle h, StepParams& p, const char* who) {
+    if (pool_num_tracks(h->pool) == 0) {
+        snprintf(h->err, sizeof(h->err), "%s: no tracks set (call rk_set_tracks_* or rk_generate_tracks first)", who);
+        return 1;
+    }
+    memset(&p, 0, sizeof(p));
+    p.trk = pool_view(h->pool);
+    p.st = h->st;
+    p.sensor_angles = h->sensor_angles;
+    p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
+    p.autoreset = h->cfg.autoreset_mode;
+    p.max_steps = h->cfg.max_episode_steps;
+    p.speed_weight = h->cfg.speed_weight;
+    p.seed = h->cfg.seed;
+    return 0;
+}
+
+int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs, void* stream) {
+    if (!h) return 1;
+    StepParams p;
+    if (fill_params(h, p, "rk_reset")) return 1;
+    p.mode = 1;
+    p.reset_mask = dev_mask;
+    p.io.start_slot = dev_start_slot;
+    p.io.obs = dev_obs;
+    if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
+        snprintf(h->err, sizeof(h->err), "rk_reset: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
+int rk_step(rk_handle h, const rk_step_io* io, void* stream) {
+    if (!h) return 1;
+    if (!io || io->struct_size != (int32_t)sizeof(rk_step_io)) {
+        snprintf(h->err, sizeof(h->err), "rk_step: bad rk_step_io (struct_size mismatch)");
+        return 1;
+    }
+    if (!io->actions || !io->terminated || !io->truncated) {
+        snprintf(h->err, sizeof(h->err), "rk_step: actions, terminated and truncated are required");
+        return 1;
+    }
+    StepParams p;
+    if (fill_params(h, p, "rk_step")) return 1;
+    p.mode = 0;
+    p.io = *io;
+    if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
+        snprintf(h->err, sizeof(h->err), "rk_step: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
+int rk_observe(rk_handle h, float* dev_obs, void* stream) {
+    if (!h) return 1;
+    if (!dev_obs) {
+        snprintf(h->err, sizeof(h->err), "rk_observe: null obs");
+        return 1;
+    }
+    StepParams p;
+    if (fill_params(h, p, "rk_observe")) return 1;
+    p.mode = 2;
+    p.io.obs = dev_obs;
+    if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
+        snprintf(h->err, sizeof(h->err), "rk_observe: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
+int rk_set_speed_weight(rk_handle h, double w) {
+    if (!h) return 1;
+    h->cfg.speed_weight = w;
+    return 0;
+}
+
+int rk_get_state(rk_handle h, double* car_f64, int32_t* car_i32, int32_t* env_i32, double* env_f64) {
+    if (!h) return 1;
+    cudaSetDevice(h->cfg.device);
+    H_CUDA(h, cudaDeviceSynchronize());
+    const size_t E = h->cfg.num_envs, C = E * h->cfg.num_agents;
+    if (car_f64) {
+        std::vector<double> t(C);
+        std::vector<float> f(C);
+        const double* src[5] = {h->st.x, h->st.y, h->st.ang, h->st.vx, h->st.vy};
+        for (int k = 0; k < 5; ++k) {
+            H_CUDA(h, cudaMemcpy(t.data(), src[k], C * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < C; ++i) car_f64[6 * i + k] = t[i];
+        }
+        H_CUDA(h, cudaMemcpy(f.data(), h->st.last_steer, C * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < C; ++i) car_f64[6 * i + 5] = f[i];
+    }
+    if (car_i32) {
+        std::vector<int32_t> t(C);
+        const int32_t* src[4] = {h->st.pidx, h->st.lpidx, h->st.flags, h->st.fstep};
+        for (int k = 0; k < 4; ++k) {
+            H_CUDA(h, cudaMemcpy(t.data(), src[k], C * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < C; ++i) car_i32[4 * i + k] = t[i];
+        }
+    }
+    if (env_i32) {
+        std::vector<int32_t> t(E);
+        std::vector<uint8_t> u(E);
+        H_CUDA(h, cudaMemcpy(t.data(), h->st.steps, E * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < E; ++i) env_i32[3 * i] = t[i];
+        H_CUDA(h, cudaMemcpy(u.data(), h->st.needs_reset, E, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < E; ++i) env_i32[3 * i + 1] = u[i];
+        H_CUDA(h, cudaMemcpy(t.data(), h->st.ep_length, E * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < E; ++i) env_i32[3 * i + 2] = t[i];
+    }
+    if (env_f64) H_CUDA(h, cudaMemcpy(env_f64, h->st.ep_return, E * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rk_set_state(rk_handle h, const double* car_f64, const int32_t* car_i32, const int32_t* env_i32,
+                 const double* env_f64) {
+    if (!h) return 1;
+    cudaSetDevice(h->cfg.device);
+    H_CUDA(h, cudaDeviceSynchronize());
+    const size_t E = h->cfg.num_envs, C = E * h->cfg.num_agents;
+    if (car_f64) {
+        std::vector<double> t(C);
+        std::vector<float> f(C);
+        double* dst[5] = {h->st.x, h->st.y, h->st.ang, h->st.vx, h->st.vy};
+        for (int k = 0; k < 5; ++k) {
+            for (size_t i = 0; i < C; ++i) t[i] = car_f64[6 * i + k];
+            H_CUDA(h, cudaMemcpy(dst[k], t.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        for (size_t i = 0; i < C; ++i) f[i] = (float)car_f64[6 * i + 5];
+        H_CUDA(h, cudaMemcpy(h->st.last_steer, f.data(), C * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (car_i32) {
+        std::vector<int32_t> t(C);
+        int32_t* dst[4] = {h->st.pidx, h->st.lpidx, h->st.flags, h->st.fstep};
+        for (int k = 0; k < 4; ++k) {
+            for (size_t i = 0; i < C; ++i) t[i] = car_i32[4 * i + k];
+            H_CUDA(h, cudaMemcpy(dst[k], t.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+    }
+    if (env_i32) {
+        std::vector<int32_t> t(E);
+        std::vector<uint8_t> u(E);
+        for (size_t i = 0; i < E; ++i) t[i] = env_i32[3 * i];
+        H_CUDA(h, cudaMemcpy(h->st.steps, t.data(), E * sizeof(int32_t), cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < E; ++i) u[i] = (uint8_t)(env_i32[3 * i + 1] != 0);
+        H_CUDA(h, cudaMemcpy(h->st.needs_reset, u.data(), E, cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < E; ++i) t[i] = env_i32[3 * i + 2];
+        H_CUDA(h, cudaMemcpy(h->st.ep_length, t.data(), E * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (env_f64) H_CUDA(h, cudaMemcpy(h->st.ep_return, env_f64, E * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int rk_gae(const float* rewards, const float* values, const float* dones, const float* next_value,
+           const float* next_done_f32, float gamma, float lam, int32_t T, int32_t E, float* adv, float* ret,
+           void* stream) {
+    if (!rewards || !values || !dones || !next_value || !next_done_f32 || !adv || !ret || T <= 0 || E <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_gae: invalid arguments");
+        return 1;
+    }
+    return launch_gae(rewards, values, dones, next_value, next_done_f32, gamma, lam, T, E, adv, ret,
+                      (cudaStream_t)stream);
+}
+
+int rk_policy_param_count(int32_t obs_dim) { return policy_param_count(obs_dim); }
+
+int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
+                  uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
+                  float* mean, void* stream) {
+    if (!action || B < 0 || (params && (!obs || obs_dim <= 0 || obs_dim > 256))) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_policy_act: invalid arguments");
+        return 1;
+    }
+    if (launch_policy_act(params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value,
+                          mean, (cudaStream_t)stream)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_policy_act: launch failed: %s",
+                 cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
+}  // extern "C"

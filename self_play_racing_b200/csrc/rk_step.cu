@@ -1,0 +1,571 @@
+// The fused environment step: one warp per environment.
+//
+// Replaces, in one launch for E environments (reference paths relative to its
+// root): Car.update (environment/car.py:45-80), Track.closest_waypoint_idx /
+// check_collision / raycast (environment/track.py:150-198),
+// MultiTrack.raycast_with_cars (environment/multi_track.py:5-44),
+// MultiCar.rectangles_intersect (environment/multi_car.py:16-43),
+// RacingEnv.step/_get_obs (environment/racing_env.py:44-166),
+// MultiRacingEnv.step/calc_reward/place/_get_obs
+// (environment/multi_racing_env.py:48-268) and gymnasium's NEXT_STEP auto-reset
+// plus RecordEpisodeStatistics (call sites agent/ppo.py:70,88,114-130).
+//
+// Arithmetic contract: the car state and everything that decides a discrete
+// event (waypoint argmin, wall test, SAT, checkpoints, finish, placement) is
+// float64 in the reference's operation order with round-to-nearest intrinsics
+// (no FMA contraction), so those events are bit-comparable with the reference.
+// Lane a < A owns car a's scalars; the whole warp cooperates on the argmin and
+// the raycast, reducing with warp shuffles.
+#include <math.h>
+#include <stdio.h>
+
+#include "rk_types.cuh"
+
+namespace rk {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kDt = 0.05;            // car.py:45
+constexpr double kMaxSpeed = 30.0;      // car.py:4
+constexpr double kTwoPi = 6.283185307179586;
+constexpr double kMaxRange = 50.0;      // racing_env.py:15
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
+    return v;
+}
+
+// per-warp scratch in dynamic shared memory
+struct Scratch {
+    double x[RK_MAX_AGENTS], y[RK_MAX_AGENTS], c[RK_MAX_AGENTS], s[RK_MAX_AGENTS];
+    double ang[RK_MAX_AGENTS], vx[RK_MAX_AGENTS], vy[RK_MAX_AGENTS];
+    double cx[RK_MAX_AGENTS][4], cy[RK_MAX_AGENTS][4];
+};
+
+// car.py:26-43: corners FL, FR, RR, RL = R(angle) * (+-2, +-1) + position
+__device__ __forceinline__ void corners(double x, double y, double c, double s, double* cx, double* cy) {
+    const double lx[4] = {2.0, 2.0, -2.0, -2.0}, ly[4] = {1.0, -1.0, -1.0, 1.0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cx[k] = dadd(dadd(dmul(c, lx[k]), dmul(-s, ly[k])), x);
+        cy[k] = dadd(dadd(dmul(s, lx[k]), dmul(c, ly[k])), y);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Waypoint argmin for NQ query points (track.py:150-152), exact float64 brute
+// force: every lane scans waypoints lane, lane+32, ...; ties resolve to the
+// lowest index, as numpy's argmin does.
+// ---------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMeta& tm, const double* qx,
+                                             const double* qy, int lane, int* out_idx) {
+    double best[NQ];
+    int bi[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        best[q] = INFINITY;
+        bi[q] = 0x7fffffff;
+    }
+    const double* wx = tp.wx + tm.wp_off;
+    const double* wy = tp.wy + tm.wp_off;
+    for (int i = lane; i < tm.n_wp; i += 32) {
+        const double px = wx[i], py = wy[i];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const double dx = dsub(px, qx[q]), dy = dsub(py, qy[q]);
+            const double d = dadd(dmul(dx, dx), dmul(dy, dy));
+            if (d < best[q]) {
+                best[q] = d;
+                bi[q] = i;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double od = shfl_xor_d(best[q], m);
+            const int oi = __shfl_xor_sync(kFull, bi[q], m);
+            if (od < best[q] || (od == best[q] && oi < bi[q])) {
+                best[q] = od;
+                bi[q] = oi;
+            }
+        }
+        out_idx[q] = bi[q];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// One ray against one segment, the reference's formula (track.py:176-195 /
+// multi_track.py:28-44).  Returns t if hit, +inf otherwise.  The divisions are
+// only evaluated when the sign/magnitude pre-test (which can not reject a true
+// hit) passes.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ray_segment(double v1x, double v1y, double v2x, double v2y, double cross,
+                                              double v3x, double v3y) {
+    const double dotp = dadd(dmul(v2x, v3x), dmul(v2y, v3y));
+    const double dv = dadd(dmul(v1x, v3x), dmul(v1y, v3y));
+    const double adot = fabs(dotp);
+    if (adot > 1e-10 && fabs(dv) <= adot * (1.0 + 1e-12)) {
+        const double t = ddiv(cross, dotp), s = ddiv(dv, dotp);
+        if (t >= 0.0 && s >= 0.0 && s <= 1.0) return t;
+    }
+    return INFINITY;
+}
+
+constexpr int kRayBlock = 8;  // rays whose running minima are kept in registers at once
+
+// All R rays of one car against all walls of its track, exact float64 brute
+// force; lanes stride over the 2N segments, then shuffle-min.  ray_out[r] for
+// r in [r0, r0 + kRayBlock) is valid on every lane on return.
+__device__ __forceinline__ void raycast_walls_exact(const TrackPool& tp, const TrackMeta& tm, double ox, double oy,
+                                                    const double* v3x, const double* v3y, int nr, int lane,
+                                                    double* best) {
+    const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
+    const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
+    const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
+    const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
+    const int S = 2 * tm.n_wp;
+    for (int i = lane; i < S; i += 32) {
+        const double ax = v2x[i], ay = v2y[i];
+        const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
+        const double cross = dsub(dmul(ax, v1y), dmul(ay, v1x));
+#pragma unroll
+        for (int k = 0; k < kRayBlock; ++k)
+            if (k < nr) best[k] = fmin(best[k], ray_segment(v1x, v1y, ax, ay, cross, v3x[k], v3y[k]));
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * kWarpsPerCta + warp;
+    if (e >= p.E) return;
+    Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[warp];
+    const int A = p.A, R = p.R;
+    const TrackPool& tp = p.trk;
+    const TrackMeta tm = tp.meta[tp.env_to_track[e]];
+    const double Nd = (double)tm.n_wp;
+    const bool is_car = lane < A;
+    const int c = e * A + (is_car ? lane : 0);
+
+    // ---- which of {step, reset, observe} applies to this environment -------
+    bool stepping = (p.mode == 0);
+    bool resetting = false;
+    if (p.mode == 0 && p.autoreset == RK_AUTORESET_NEXT_STEP && p.st.needs_reset[e]) {
+        stepping = false;  // the action is ignored (gymnasium NEXT_STEP)
+        resetting = true;
+    }
+    if (p.mode == 1) resetting = (p.reset_mask == nullptr) || (p.reset_mask[e] != 0);
+
+    // ---- load car state ------------------------------------------------------
+    double x = 0, y = 0, ang = 0, vx = 0, vy = 0;
+    float last_steer = 0.f;
+    int pidx = 0, lpidx = 0, flags = 0, fstep = 0;
+    if (is_car) {
+        x = p.st.x[c]; y = p.st.y[c]; ang = p.st.ang[c]; vx = p.st.vx[c]; vy = p.st.vy[c];
+        last_steer = p.st.last_steer[c];
+        pidx = p.st.pidx[c]; lpidx = p.st.lpidx[c]; flags = p.st.flags[c]; fstep = p.st.fstep[c];
+    }
+    int steps = p.st.steps[e];
+    double reward = 0.0, delta = 0.0;
+    int placement = 0;
+    bool terminated = false, truncated = false;
+
+    if (stepping) {
+        // ---- D: vehicle dynamics (car.py:45-80), one lane per car -------------
+        const bool moving = is_car && !(flags & F_CRASHED);  // car.py:51-52
+        double cs = 1.0, sn = 0.0;
+        if (is_car) {
+            const float a0 = p.io.actions[2 * c], a1 = p.io.actions[2 * c + 1];
+            const float steer_f = fminf(fmaxf(a0, -1.f), 1.f);  // racing_env.py:106
+            float thr_f;
+            if (KIND == RK_ENV_SINGLE)
+                thr_f = fminf(fmaxf(a1, 0.f), 1.f);  // racing_env.py:107
+            else  // multi_racing_env.py:217, evaluated in float32 for float32 actions
+                thr_f = fminf(fmaxf(__fdiv_rn(__fadd_rn(a1, 1.f), 2.f), 0.f), 1.f);
+            last_steer = steer_f;
+            if (moving) {
+                const double steer = (double)steer_f, thr = (double)thr_f;
+                double na = dadd(ang, dmul(dmul(steer, 3.0), kDt));  // car.py:54-55
+                na = fmod(na, kTwoPi);                                // car.py:56 (python modulo)
+                if (na != 0.0) { if (na < 0.0) na = dadd(na, kTwoPi); } else na = 0.0;
+                ang = na;
+                sincos(ang, &sn, &cs);
+                double vf = dadd(dmul(vx, cs), dmul(vy, sn));          // car.py:59
+                double vl = dadd(dmul(vx, -sn), dmul(vy, cs));         // car.py:60
+                vf = dmul(dadd(vf, dmul(dmul(thr, 10.0), kDt)), 0.985);  // car.py:61-62
+                vl = dmul(dmul(vl, 0.85), 0.9);                        // car.py:63
+                vx = dsub(dmul(vf, cs), dmul(vl, sn));                 // car.py:66-67
+                vy = dadd(dmul(vf, sn), dmul(vl, cs));
+                const double speed = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));  // car.py:70
+                if (speed > kMaxSpeed) {
+                    const double scale = ddiv(kMaxSpeed, speed);
+                    vx = dmul(vx, scale);
+                    vy = dmul(vy, scale);
+                }
+                x = dadd(x, dmul(vx, kDt));  // car.py:77-78
+                y = dadd(y, dmul(vy, kDt));
+            } else {
+                sincos(ang, &sn, &cs);
+            }
+            S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn;
+            corners(x, y, cs, sn, S.cx[lane], S.cy[lane]);
+        }
+        __syncwarp();
+
+        // ---- W + C: progress index and wall test for every moving car ---------
+        unsigned todo = __ballot_sync(kFull, moving);
+        while (todo) {
+            const int a = __ffs(todo) - 1;
+            todo &= todo - 1;
+            double qx[5], qy[5];
+            qx[0] = S.x[a]; qy[0] = S.y[a];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[a][k]; qy[k + 1] = S.cy[a][k]; }
+            int idx[5];
+            argmin_exact<5>(tp, tm, qx, qy, lane, idx);
+            if (lane == a) {
+                pidx = idx[0];  // car.py:79
+                bool crashed = false;  // track.py:163-171
+#pragma unroll
+                for (int k = 1; k < 5; ++k) {
+                    const int i = tm.wp_off + idx[k];
+                    const double dist = fabs(dadd(dmul(dsub(qx[k], tp.wx[i]), tp.nx[i]),
+                                                  dmul(dsub(qy[k], tp.wy[i]), tp.ny[i])));
+                    crashed |= dist > tm.width;
+                }
+                if (crashed) flags |= F_CRASHED;
+            }
+        }
+
+        // ---- X: car-car collisions (multi_racing_env.py:222-231) --------------
+        double touching = 0.0;
+        if (KIND == RK_ENV_MULTI && A > 1) {
+            // lane pr < A*(A-1)/2 tests pair pr; every lane then applies its own hits
+            int pi = 0, pj = 0;
+            {
+                int k = lane, i = 0;
+                while (i < A - 1 && k >= A - 1 - i) { k -= A - 1 - i; ++i; }
+                pi = i; pj = i + 1 + k;
+            }
+            bool hit = false;
+            if (pi < A - 1 && pj < A) {
+                hit = true;  // multi_car.py:16-43: 4 axes, strict separation test
+#pragma unroll
+                for (int ax = 0; ax < 4; ++ax) {
+                    const int o = (ax < 2) ? pi : pj, k0 = ax & 1;
+                    const double ex = dsub(S.cx[o][k0 + 1], S.cx[o][k0]), ey = dsub(S.cy[o][k0 + 1], S.cy[o][k0]);
+                    const double nx = -ey, ny = ex;
+                    double amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double pa = dadd(dmul(S.cx[pi][k], nx), dmul(S.cy[pi][k], ny));
+                        const double pb = dadd(dmul(S.cx[pj][k], nx), dmul(S.cy[pj][k], ny));
+                        amin = fmin(amin, pa); amax = fmax(amax, pa);
+                        bmin = fmin(bmin, pb); bmax = fmax(bmax, pb);
+                    }
+                    if (amax < bmin || bmax < amin) hit = false;
+                }
+            }
+            const unsigned hits = __ballot_sync(kFull, hit);
+            if (is_car && hits) {  // pairs in (i, j) order, as the reference's nested loops
+                int pr = 0;
+                for (int i = 0; i < A - 1; ++i)
+                    for (int j = i + 1; j < A; ++j, ++pr)
+                        if (((hits >> pr) & 1u) && (i == lane || j == lane)) {
+                            vx = dmul(vx, 0.92);
+                            vy = dmul(vy, 0.92);
+                            touching = dadd(touching, -5.0);
+                        }
+            }
+        }
+        steps += 1;  // racing_env.py:110 / multi_racing_env.py:233
+
+        // ---- reward and episode logic, one lane per car ------------------------
+        if (is_car) {
+            const double prog = ddiv((double)pidx, Nd), lprog = ddiv((double)lpidx, Nd);  // track.py:161
+            delta = dsub(prog, lprog);  // racing_env.py:112-116 / multi:159-163
+            if (lprog > 0.9 && prog < 0.1) delta = dadd(dsub(1.0, lprog), prog);
+            else if (lprog < 0.1 && prog > 0.9) delta = -dadd(dsub(1.0, prog), lprog);
+            const bool crashed = flags & F_CRASHED;
+            const double speed = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+            const double ratio = clipd(ddiv(speed, kMaxSpeed), 0.0, 1.0);
+            reward = dmul(delta, 200.0);
+            const double cp_bonus = (KIND == RK_ENV_SINGLE) ? 20.0 : 25.0;
+            if (KIND == RK_ENV_MULTI && !crashed && delta > 0.0) reward = dadd(reward, dmul(ratio, 18.0));  // multi:169-172
+            if (!(flags & F_CP25) && 0.25 <= prog && prog < 0.35) { flags |= F_CP25; reward = dadd(reward, cp_bonus); }
+            if ((flags & F_CP25) && !(flags & F_CP50) && 0.50 <= prog && prog < 0.60) { flags |= F_CP50; reward = dadd(reward, cp_bonus); }
+            if ((flags & F_CP50) && !(flags & F_CP75) && 0.75 <= prog && prog < 0.85) { flags |= F_CP75; reward = dadd(reward, cp_bonus); }
+            const bool all_cp = (flags & (F_CP25 | F_CP50 | F_CP75)) == (F_CP25 | F_CP50 | F_CP75);
+            const bool fin = all_cp && lprog > 0.9 && prog < 0.1 && delta > 0.0;
+            if (KIND == RK_ENV_SINGLE) {
+                if (!crashed && delta > 0.0) reward = dadd(reward, dmul(ratio, p.speed_weight));  // racing_env.py:137-140
+                if (crashed) reward = dsub(reward, 60.0);                                        // :142-143
+                if (fin) {                                                                       // :145-150
+                    flags |= F_FINISHED;
+                    reward = dadd(reward, 100.0);
+                    reward = dadd(reward, fmax(0.0, dsub(200.0, ddiv((double)steps, 10.0))));
+                }
+            } else {
+                if (fin) {  // multi:186-190
+                    flags |= F_FINISHED;
+                    fstep = steps;
+                    reward = dadd(reward, dadd(100.0, fmax(0.0, dsub(300.0, ddiv((double)steps, 15.0)))));
+                }
+                if (crashed && !(flags & F_HAS_CRASHED)) {  // multi:192-194
+                    reward = dsub(reward, 160.0);
+                    flags |= F_HAS_CRASHED;
+                }
+                reward = dadd(reward, touching);  // multi:240
+            }
+        }
+        const unsigned car_mask = (A >= 32) ? kFull : ((1u << A) - 1u);
+        const unsigned fin_b = __ballot_sync(kFull, is_car && (flags & F_FINISHED));
+        const unsigned crash_b = __ballot_sync(kFull, is_car && (flags & F_CRASHED));
+        if (KIND == RK_ENV_SINGLE)
+            terminated = (fin_b | crash_b) & 1u;  // racing_env.py:161
+        else
+            terminated = (fin_b != 0u) || ((crash_b & car_mask) == car_mask);  // multi:247-249
+        truncated = steps >= p.max_steps;
+        if (KIND == RK_ENV_MULTI && (terminated || truncated)) {
+            // place() multi:198-211: descending (score, idx); ties go to the higher index
+            double score = 0.0;
+            if (is_car) {
+                const double prog = ddiv((double)pidx, Nd);
+                score = dadd(dadd(dadd((flags & F_FINISHED) ? 10000.0 : 0.0, dmul(prog, 100.0)),
+                                  (flags & F_CRASHED) ? 0.0 : 10.0),
+                             ddiv(1.0, (double)(fstep ? fstep : 10000)));
+            }
+            int ahead = 0;
+            for (int o = 0; o < A; ++o) {
+                const double so = __shfl_sync(kFull, score, o);
+                if (is_car && o != lane && (so > score || (so == score && o > lane))) ++ahead;
+            }
+            placement = ahead + 1;
+            if (is_car && placement == 1) reward = dadd(reward, 250.0);  // multi:256-257
+        }
+        if (is_car) lpidx = pidx;  // racing_env.py:165 / multi:266-267
+    }
+
+    // ---- episode statistics (RecordEpisodeStatistics) -------------------------
+    const bool ended = terminated || truncated;
+    if (stepping) {
+        const double r0 = __shfl_sync(kFull, reward, 0);
+        if (lane == 0) {
+            const double er = dadd(p.st.ep_return[e], r0);
+            const int el = p.st.ep_length[e] + 1;
+            p.st.ep_return[e] = er;
+            p.st.ep_length[e] = el;
+            if (p.io.ep_mask) p.io.ep_mask[e] = ended;
+            if (p.io.ep_return) p.io.ep_return[e] = ended ? er : 0.0;
+            if (p.io.ep_length) p.io.ep_length[e] = ended ? el : 0;
+        }
+    } else if (p.mode == 0 && lane == 0) {
+        if (p.io.ep_mask) p.io.ep_mask[e] = 0;
+        if (p.io.ep_return) p.io.ep_return[e] = 0.0;
+        if (p.io.ep_length) p.io.ep_length[e] = 0;
+    }
+    // per-car info of the step itself (before any same-step reset)
+    if (p.mode == 0 && is_car) {
+        if (p.io.info_f64) {
+            double* o = p.io.info_f64 + 5 * (size_t)c;
+            o[0] = x; o[1] = y;
+            o[2] = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
+            o[3] = (flags & F_FINISHED) ? 1.0 : ddiv((double)pidx, Nd);
+            o[4] = delta;
+        }
+        if (p.io.info_i32) {
+            int32_t* o = p.io.info_i32 + 4 * (size_t)c;
+            o[0] = (flags & F_CRASHED) != 0; o[1] = (flags & F_FINISHED) != 0;
+            o[2] = placement; o[3] = pidx;
+        }
+    }
+
+    // ---- reset (racing_env.py:86-102 / multi_racing_env.py:118-153) ------------
+    if (p.mode == 0 && p.autoreset == RK_AUTORESET_SAME_STEP && ended) resetting = true;
+    if (resetting) {
+        int slot = lane;
+        if (KIND == RK_ENV_MULTI) {
+            const int32_t* ss = (p.mode == 1) ? p.io.start_slot : p.io.start_slot;
+            if (ss) {
+                slot = is_car ? ss[c] : 0;
+            } else {
+                // Fisher-Yates over car ids from Philox(seed; env, reset_count); slot = position of this car
+                const uint32_t rc = p.st.reset_count[e];
+                int perm = lane;  // perm[lane] = car id at grid position `lane`
+                for (int i = A - 1; i > 0; --i) {
+                    uint32_t ctr[4] = {(uint32_t)e, rc, (uint32_t)i, 0x736c6f74u};
+                    philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                    const int j = (int)(((uint64_t)ctr[0] * (uint64_t)(i + 1)) >> 32);
+                    const int vi = __shfl_sync(kFull, perm, i), vj = __shfl_sync(kFull, perm, j);
+                    if (lane == i) perm = vj;
+                    else if (lane == j) perm = vi;
+                }
+                slot = 0;
+                for (int k = 0; k < A; ++k)
+                    if (__shfl_sync(kFull, perm, k) == lane) slot = k;
+            }
+        }
+        if (is_car) {
+            x = tm.start_x; y = tm.start_y; ang = tm.start_angle;  // car.py:17-24
+            if (KIND == RK_ENV_MULTI) {  // multi:124-138
+                const double center = ddiv((double)(A - 1), 2.0);
+                const double off = dmul(dsub((double)slot, center), 3.5);
+                x = dadd(tm.start_x, dmul(tm.start_nx, off));
+                y = dadd(tm.start_y, dmul(tm.start_ny, off));
+            }
+            vx = 0.0; vy = 0.0; last_steer = 0.f;
+            pidx = 0; lpidx = 0; flags = 0; fstep = 0;
+        }
+        steps = 0;
+        if (lane == 0) {
+            p.st.ep_return[e] = 0.0;
+            p.st.ep_length[e] = 0;
+            p.st.reset_count[e] += 1;
+        }
+    }
+
+    // ---- write state back ------------------------------------------------------
+    if (p.mode != 2) {
+        if (is_car) {
+            p.st.x[c] = x; p.st.y[c] = y; p.st.ang[c] = ang; p.st.vx[c] = vx; p.st.vy[c] = vy;
+            p.st.last_steer[c] = last_steer;
+            p.st.pidx[c] = pidx; p.st.lpidx[c] = lpidx; p.st.flags[c] = flags; p.st.fstep[c] = fstep;
+        }
+        if (lane == 0) {
+            p.st.steps[e] = steps;
+            if (p.mode == 0)
+                p.st.needs_reset[e] = (p.autoreset == RK_AUTORESET_NEXT_STEP) ? (stepping && ended) : 0;
+            else if (resetting)
+                p.st.needs_reset[e] = 0;
+        }
+    }
+    if (p.mode == 0) {
+        if (is_car) {
+            const double r = stepping ? reward : 0.0;
+            if (p.io.reward_f32) p.io.reward_f32[c] = (float)r;
+            if (p.io.reward_f64) p.io.reward_f64[c] = r;
+        }
+        if (lane == 0) {
+            p.io.terminated[e] = terminated;
+            p.io.truncated[e] = truncated;
+            if (p.io.done) p.io.done[e] = ended;
+            if (p.io.done_f32) p.io.done_f32[e] = ended ? 1.f : 0.f;
+        }
+    }
+    float* obs = (p.mode == 1) ? p.io.obs : p.io.obs;
+    if (obs == nullptr || (p.mode == 1 && !resetting)) return;
+
+    // ---- observations (racing_env.py:44-75 / multi_racing_env.py:48-105) --------
+    // publish the final pose of every car
+    double cs, sn;
+    sincos(ang, &sn, &cs);
+    __syncwarp();
+    if (is_car) {
+        S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn; S.ang[lane] = ang;
+        S.vx[lane] = vx; S.vy[lane] = vy;
+        corners(x, y, cs, sn, S.cx[lane], S.cy[lane]);
+    }
+    __syncwarp();
+    const int D = p.D;
+    for (int a = 0; a < A; ++a) {
+        const double ox = S.x[a], oy = S.y[a], oang = S.ang[a];
+        float* orow = obs + ((size_t)e * A + a) * D;
+        for (int r0 = 0; r0 < R; r0 += kRayBlock) {
+            const int nr = min(kRayBlock, R - r0);
+            double v3x[kRayBlock], v3y[kRayBlock], best[kRayBlock];
+#pragma unroll
+            for (int k = 0; k < kRayBlock; ++k) {
+                // lane k computes ray r0+k's direction, then it is broadcast
+                double dsn = 0.0, dcs = 1.0;
+                if (lane == k && k < nr) sincos(dadd(oang, p.sensor_angles[r0 + k]), &dsn, &dcs);
+                v3x[k] = -__shfl_sync(kFull, dsn, k);  // track.py:178 v3 = (-dir_y, dir_x)
+                v3y[k] = __shfl_sync(kFull, dcs, k);
+                best[k] = INFINITY;
+            }
+            raycast_walls_exact(tp, tm, ox, oy, v3x, v3y, nr, lane, best);
+            if (KIND == RK_ENV_MULTI) {
+                // multi_track.py:10-24: lane k < 4A tests edge k%4 of car k/4
+                const int oc = lane >> 2, ed = lane & 3;
+                if (oc < A) {
+                    const double ddx = dsub(S.x[oc], ox), ddy = dsub(S.y[oc], oy);
+                    const bool skip = sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5;  // multi_track.py:13
+                    if (!skip) {
+                        const double ex0 = S.cx[oc][ed], ey0 = S.cy[oc][ed];
+                        const double ex1 = S.cx[oc][(ed + 1) & 3], ey1 = S.cy[oc][(ed + 1) & 3];
+                        const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
+                        const double ax = dsub(ex1, ex0), ay = dsub(ey1, ey0);
+                        const double cross = dsub(dmul(ax, v1y), dmul(ay, v1x));
+#pragma unroll
+                        for (int k = 0; k < kRayBlock; ++k)
+                            if (k < nr) {
+                                const double dotp = dadd(dmul(ax, v3x[k]), dmul(ay, v3y[k]));
+                                if (!(fabs(dotp) < 1e-10)) {  // multi_track.py:35
+                                    const double t = ddiv(cross, dotp);
+                                    const double s = ddiv(dadd(dmul(v1x, v3x[k]), dmul(v1y, v3y[k])), dotp);
+                                    if (t >= 0.0 && s >= 0.0 && s <= 1.0) best[k] = fmin(best[k], t);
+                                }
+                            }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kRayBlock; ++k) {
+                double t = warp_min_d(best[k]);
+                if (KIND == RK_ENV_MULTI) t = fmin(t, kMaxRange);       // multi_track.py:8,26
+                else if (t == INFINITY) t = kMaxRange;                  // track.py:196-197
+                if (lane == k && k < nr) orow[r0 + k] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+            }
+        }
+    }
+    if (is_car) {
+        float* orow = obs + (size_t)c * D + R;
+        const double vf = clipd(ddiv(dadd(dmul(vx, cs), dmul(vy, sn)), kMaxSpeed), -1.0, 1.0);
+        const double vl = clipd(ddiv(dadd(dmul(-vx, sn), dmul(vy, cs)), kMaxSpeed), -1.0, 1.0);
+        orow[0] = (float)vf;
+        orow[1] = (float)vl;
+        orow[2] = 0.f;  // Car.angular_velocity is never updated
+        orow[3] = last_steer;
+        if (KIND == RK_ENV_MULTI) {
+            int w = 4;
+            for (int o = 0; o < A; ++o) {
+                if (o == lane) continue;
+                const double rx = dsub(S.x[o], x), ry = dsub(S.y[o], y);
+                const double rvx = dsub(S.vx[o], vx), rvy = dsub(S.vy[o], vy);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(rx, cs), dmul(ry, sn)), tm.max_track_distance), -1.0, 1.0);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rx, sn), dmul(ry, cs)), tm.max_track_distance), -1.0, 1.0);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(rvx, cs), dmul(rvy, sn)), kMaxSpeed), -1.0, 1.0);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rvx, sn), dmul(rvy, cs)), kMaxSpeed), -1.0, 1.0);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
+    (void)query_mode;
+    const int grid = (p.E + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t smem = kWarpsPerCta * sizeof(Scratch);
+    if (env_kind == RK_ENV_SINGLE)
+        step_kernel<RK_ENV_SINGLE><<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
+    else
+        step_kernel<RK_ENV_MULTI><<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace rk

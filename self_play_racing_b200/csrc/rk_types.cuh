@@ -1,0 +1,108 @@
+// Internal device-side types shared by the kernels of librk_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/racing_b200.h"
+
+namespace rk {
+
+constexpr int kChunk = 16;          // boundary points / waypoints per bounding-circle chunk
+constexpr int kMaxKnots = 130;      // n_ctrl + 1 <= kMaxKnots
+constexpr int kWarpsPerCta = 8;
+
+// flags word of a car
+enum : int { F_CRASHED = 1, F_FINISHED = 2, F_CP25 = 4, F_CP50 = 8, F_CP75 = 16, F_HAS_CRASHED = 32 };
+
+// One record per track.  Everything float64 is what the reference keeps in
+// Track (environment/track.py:61-98); org/chunk fields serve the culled query
+// path only.
+struct TrackMeta {
+    int32_t n_wp;        // N = n_ctrl * factor            (track.py:110)
+    int32_t wp_off;      // offset into per-waypoint arrays; segment arrays start at 2*wp_off
+    int32_t n_wchunk;    // ceil(N / kChunk) waypoint chunks
+    int32_t wchunk_off;
+    int32_t n_bchunk;    // 2 * ceil(N / kChunk) boundary chunks (left side first)
+    int32_t bchunk_off;
+    int32_t n_ctrl;
+    int32_t ctrl_off;
+    double width;               // track.py:77-80
+    double max_track_distance;  // track.py:82-91
+    double start_x, start_y, start_angle;  // track.py:154-157
+    double start_nx, start_ny;  // normals[0] (multi_racing_env.py:123)
+    double org_x, org_y;        // bbox centre: origin of the fp32 tables
+};
+
+struct TrackPool {
+    const TrackMeta* meta;
+    const int32_t* env_to_track;  // [E]
+    // float64 tables, the reference's arithmetic
+    const double *wx, *wy, *nx, *ny;      // [sum N]   waypoints, unit normals
+    const double *sx, *sy, *v2x, *v2y;    // [sum 2N]  segment starts and vectors (track.py:134-148)
+    // fp32 tables relative to (org_x, org_y): candidate search only
+    const float2* wpt;     // [sum N]  waypoints
+    const float2* bpt;     // [sum 2N] boundary points (left then right)
+    const float4* wchunk;  // (cx, cy, r, -) bounding circle of kChunk waypoints
+    const float4* bchunk;  // (cx, cy, r, -) bounding circle of kChunk boundary segments
+};
+
+struct EnvState {
+    // per car, index e*A + a
+    double *x, *y, *ang, *vx, *vy;
+    float* last_steer;
+    int32_t *pidx, *lpidx, *flags, *fstep;
+    // per env
+    int32_t* steps;
+    uint8_t* needs_reset;
+    double* ep_return;
+    int32_t* ep_length;
+    uint32_t* reset_count;
+};
+
+struct StepParams {
+    TrackPool trk;
+    EnvState st;
+    rk_step_io io;
+    const double* sensor_angles;  // [R] np.linspace(-half, half, R)
+    int32_t E, A, R, D;
+    int32_t autoreset, max_steps;
+    double speed_weight;
+    uint64_t seed;
+    // reset-only
+    const uint8_t* reset_mask;
+    int32_t mode;  // 0 = step, 1 = reset(mask), 2 = observe only
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG ----------------
+__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__host__ __device__ inline float u01(uint32_t r) { return ((r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__host__ __device__ inline double u01d(uint32_t hi, uint32_t lo) {
+    return ((((uint64_t)hi << 21) ^ (uint64_t)(lo >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// launch bookkeeping (rk_launch_count)
+void count_launch(int n = 1);
+
+// host-side launchers implemented in the .cu files
+int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream);
+int launch_gae(const float* rewards, const float* values, const float* dones, const float* next_value,
+               const float* next_done, float gamma, float lam, int T, int E, float* adv, float* ret,
+               cudaStream_t stream);
+int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B,
+                      uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob,
+                      float* value, float* mean, cudaStream_t stream);
+int policy_param_count(int obs_dim);
+
+}  // namespace rk
