@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the batched racing step path (BASELINE.json metric: agent
+env-steps/s, 65,536 envs per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one pass of the hot path over all E environments of a rank: the
+opponent-snapshot MLP inference kernel + the fused environment step kernel
+(2-car workload), or the step kernel alone (single-car workload).  Rank 0 prints
+ONE JSON line.  See DESIGN.md "Measurement" for the definitions used here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE configs[2]: the configuration the metric and the 1e9 target are quoted on
+    'multi2_selfplay_65536': dict(kind='multi', A=2, R=11, E=65536, tracks=16, factor=30, selfplay=True),
+    # BASELINE configs[1]
+    'single_65536': dict(kind='single', A=1, R=11, E=65536, tracks=16, factor=30, selfplay=False),
+    # BASELINE configs[4] (one point of the sweep; the rest via --envs/--agents/--rays/--factor)
+    'sweep_4car_64ray': dict(kind='multi', A=4, R=64, E=262144, tracks=16, factor=30, selfplay=False, width_lo=9.0),
+}
+
+
+def alg_bytes_per_agent_step(D):
+    """state r/w (fp64 here) + action + obs + reward + flags, shared tracks."""
+    return 2 * (5 * 8 + 4 + 16) + 8 + 4 * D + 4 + 8 + 3
+
+
+def alg_flops_per_agent_step(R, S, A, N):
+    """F = 13 R (S + 4(A-1)) + 25 N + 200 (reference formulation, brute force)."""
+    return 13 * R * (S + 4 * (A - 1)) + 25 * N + 200
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.p.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self.p.terminate()
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for k, n in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith('active'):
+                    reasons.add(n)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx[0] if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------ CPU legs
+def _oracle_shard(args):
+    """Time `steps` oracle steps of `E` envs in this process (after 1 warm-up step)."""
+    kind, A, R, E, steps, seed = args
+    from oracle import racing_oracle as O
+    rs = np.random.RandomState(seed)
+    cps = [O.gen_random_track(rs.randint(10, 15), rs.randint(50, 80), rs.randint(10, 20), rs.uniform(0.2, 0.7),
+                              rs.uniform(0.2, 0.7), rng=rs) for _ in range(4)]
+    tracks = O.make_pool(cps, [8.0, 7.0, 9.0, 8.0])
+    env = O.OracleVecEnv(tracks, np.arange(E) % 4, kind=kind, num_agents=A, num_sensors=R, seed=seed)
+    env.reset()
+
+    def act():
+        a = rs.uniform(-1, 1, size=(E, env.A, 2)).astype(np.float32)
+        a[..., 1] = np.abs(a[..., 1])
+        return a
+    env.step(act())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.step(act())
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, budget_envs=64, steps=12):
+    """Single-process oracle port on a bounded sample of the same workload."""
+    dt = _oracle_shard((wl['kind'], wl['A'], wl['R'], budget_envs, steps, 0))
+    return {'value': budget_envs * wl['A'] * steps / dt, 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
+            'sample': f'{budget_envs} envs x {steps} steps of the {wl["kind"]} workload, oracle/racing_oracle.py '
+                      f'(batched numpy restatement; the unmodified per-env reference ran 617 steps/s single / '
+                      f'240 agent-steps/s 2-car on one core at survey time)'}
+
+
+def run_reference_arm(args, wl, rank, world):
+    """--impl reference: the oracle port on all host cores (the reference itself
+    is Python under /root/reference and does not exist on the GPU box)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    E_proc, inner = 32, 3
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        jobs = [(wl['kind'], wl['A'], wl['R'], E_proc, inner, 100 + i) for i in range(cores)]
+        for _ in range(max(args.warmup, 1) - 1):
+            pool.map(_oracle_shard, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_oracle_shard, jobs)
+        wall = time.perf_counter() - t0
+    units = cores * E_proc * wl['A'] * inner * args.steps
+    val = units / wall
+    line = {'impl': 'reference', 'metric': 'agent_env_steps_per_sec', 'value': val, 'unit': 'agent-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'sample': f'each step = {cores} processes x {E_proc} envs x {inner} env-steps'},
+            'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{cores} processes x {E_proc} envs x {inner} env-steps per bench step'},
+            'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def fp_peaks(torch, dev):
+    """Live FMA-throughput micro-benchmarks: torch has no such kernel, so this
+    uses a tiny dependent-chain FMA kernel compiled into librk_b200.so."""
+    from self_play_racing_b200 import _lib
+    lib = _lib.load()
+    if not hasattr(lib, 'rk_fma_peak'):
+        return None
+    import ctypes as C
+    lib.rk_fma_peak.restype = C.c_double
+    lib.rk_fma_peak.argtypes = [C.c_int32, C.c_int32]
+    return {'fp32_tflops': lib.rk_fma_peak(0, 4096), 'fp64_tflops': lib.rk_fma_peak(1, 2048)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--workload', default='multi2_selfplay_65536', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--envs', type=int, default=None)
+    ap.add_argument('--query', default='culled', choices=['culled', 'exact'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl['E'] = args.envs
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from self_play_racing_b200 import _lib
+    from self_play_racing_b200.backend import flatten_agent
+    from self_play_racing_b200.environment.vec_env import BatchedRacingVecEnv
+    from self_play_racing_b200.agent.ppo import Agent
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device; there is no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    E, A, R = wl['E'], wl['A'], wl['R']
+    vec = BatchedRacingVecEnv.synthetic(wl['kind'], E, n_tracks=wl['tracks'], num_agents=A, num_sensors=R,
+                                        selfplay=wl['selfplay'], device=dev, query=args.query, seed=1000 + rank,
+                                        copy=False, factor=wl['factor'], width_lo=wl.get('width_lo', 6.0))
+    be = vec.be
+    D = be.D
+    if wl['selfplay']:
+        # opponent snapshot: orthogonal-init Agent, manual_seed(1), log_std -0.3
+        torch.manual_seed(1)
+        opp = Agent(vec.single_observation_space, vec.single_action_space)
+        opp.log_std.data.fill_(-0.3)
+        vec.set_opponent(flatten_agent(opp.state_dict()).to(dev))
+    # learner / all-car actions resident in HBM: 8 pre-drawn uniform tensors cycled through
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    n_act = 8
+    if wl['selfplay']:
+        act_pool = torch.rand(n_act, E, 2, device=dev, generator=g) * 2 - 1
+    else:
+        act_pool = torch.rand(n_act, *be.actions.shape, device=dev, generator=g) * 2 - 1
+    act_pool[..., 1] = act_pool[..., 1].abs()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(k):
+        if wl['selfplay']:
+            vec.step_device(act_pool[k % n_act])
+        else:
+            be.actions.copy_(act_pool[k % n_act])
+            be.step()
+
+    vec.reset_device()
+    for k in range(args.warmup):
+        one_step(k)
+    torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput: K steps, each bracketed by CUDA events, L2 flushed between
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        one_step(k)
+        ev[k][1].record()
+    torch.cuda.synchronize(dev)
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(ms.sum())
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+
+    # ---- the step kernel alone (the dominant kernel), for the roofline line
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        if wl['selfplay']:
+            be.actions[0].copy_(act_pool[k % n_act])
+            vec._opponent_act()
+        else:
+            be.actions.copy_(act_pool[k % n_act])
+        flush.zero_()
+        kev[k][0].record()
+        be.step()
+        kev[k][1].record()
+    torch.cuda.synchronize(dev)
+    kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    clocks = sampler.stop()
+
+    # ---- end to end through the Gymnasium face: host numpy in, host numpy out
+    rs = np.random.RandomState(3 + rank)
+    host_actions = [rs.uniform(-1, 1, size=(E, 2)).astype(np.float32) for _ in range(4)]
+    for a in host_actions:
+        a[:, 1] = np.abs(a[:, 1])
+    e2e = None
+    if wl['kind'] == 'single' or wl['selfplay']:
+        vec.reset()
+        for k in range(min(args.warmup, 10)):
+            vec.step(host_actions[k % 4])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            obs, rew, term, trunc, infos = vec.step(host_actions[k % 4])
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e = {'value': E * A * args.steps * world / float(tw.item()), 'unit': 'agent-steps/s',
+               'h2d_bytes_per_step': int(vec.h2d_bytes_per_step), 'd2h_bytes_per_step': int(vec.d2h_bytes_per_step),
+               'ms_per_step': 1e3 * float(tw.item()) / args.steps}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        else:
+            hbm_peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        agent_steps = E * A
+        bytes_step = alg_bytes_per_agent_step(D) * agent_steps
+        n_mean = 12 * wl['factor']  # n_ctrl in [10, 15) -> mean 12 control points
+        flops_step = alg_flops_per_agent_step(R, 2 * n_mean, A, n_mean) * agent_steps
+        ach = bytes_step / (kms * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                'traffic': None, 'peak_source': peak_src, 'kernel': 'rk::step_kernel', 'kernel_ms': kms,
+                'algorithmic_bytes_per_agent_step': alg_bytes_per_agent_step(D),
+                'note': 'the step kernel is FP32/FP64-pipe bound, not HBM bound (SURVEY 8d); see fp_pipe'}
+        fp = fp_peaks(torch, dev)
+        roof['fp_pipe'] = {'brute_force_flop_per_agent_step': alg_flops_per_agent_step(R, 2 * n_mean, A, n_mean),
+                           'effective_tflops': flops_step / (kms * 1e-3) / 1e12, 'measured_peaks': fp}
+        if fp and fp.get('fp32_tflops'):
+            roof['fp_pipe']['frac_of_fp32_peak'] = roof['fp_pipe']['effective_tflops'] / fp['fp32_tflops']
+        line = {'metric': 'agent_env_steps_per_sec', 'value': agent_steps * args.steps * world / (total_ms_max * 1e-3),
+                'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64 state + f32 candidate search', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'envs_per_gpu': E, 'cars_per_env': A, 'rays': R,
+                           'tracks': wl['tracks'], 'waypoints_per_track': '300-420', 'query': args.query,
+                           'autoreset': 'next_step', 'actions': 'uniform random, resident in HBM',
+                           'opponent': 'frozen MLP snapshot (fused inference kernel)' if wl['selfplay'] else None,
+                           'l2': 'flushed between timed steps (256 MiB memset outside the event pair)'},
+                'roofline': roof, 'clocks': clocks, 'gpu_launches': int(launches), 'e2e': e2e}
+        if not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(wl)
+        print(json.dumps(line))
+    vec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

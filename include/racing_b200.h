@@ -107,12 +107,18 @@ RK_API int rk_get_track(rk_handle h, int32_t track_id, double* host_meta6, doubl
 /* reset (racing_env.py:86-102, multi_racing_env.py:118-153).  dev_mask: uint8
  * [E] or NULL (all).  dev_start_slot: int32 [E,A] slot of each car on the grid
  * (multi_racing_env.py:127-138) or NULL (Philox shuffle).  dev_obs: float32
- * [E,A,D] or NULL. */
-RK_API int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs, void* stream);
+ * [E,A,D] ([A,E,D] if layout is RK_LAYOUT_AGENT_MAJOR) or NULL. */
+RK_API int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs,
+                    int32_t layout, void* stream);
+
+/* layout of the per-car arrays (actions, obs, reward_*, info_*) */
+enum { RK_LAYOUT_ENV_MAJOR = 0,     /* [E,A,...]: one row per environment              */
+       RK_LAYOUT_AGENT_MAJOR = 1 }; /* [A,E,...]: car a of every env is one contiguous
+                                       block (the SelfPlayWrapper view of car 0 / car 1) */
 
 typedef struct rk_step_io {
     int32_t struct_size;
-    int32_t reserved0;
+    int32_t layout;              /* RK_LAYOUT_*                                                 */
     const float* actions;        /* in  [E,A,2] steer, throttle (racing_env.py:104-107)        */
     const int32_t* start_slot;   /* in  [E,A] or NULL: slots used by auto-resets this step     */
     float* obs;                  /* out [E,A,D]                                                 */
@@ -129,6 +135,9 @@ typedef struct rk_step_io {
     /* per-car info of this step (racing_env.py:77-84,156-159): may be NULL     */
     double* info_f64;            /* out [E,A,5]: x, y, speed, progress (1.0 if finished), progress_delta */
     int32_t* info_i32;           /* out [E,A,4]: crashed, finished, placement (0 unless ended), progress_idx */
+    /* running totals over finished episodes, accumulated atomically: {sum of
+     * returns, sum of lengths, count} -- what PPO.train averages (agent/ppo.py:272-276) */
+    double* ep_stats;            /* inout [3] or NULL */
 } rk_step_io;
 RK_API int rk_step(rk_handle h, const rk_step_io* io, void* stream);
 
@@ -143,7 +152,7 @@ RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
 RK_API int rk_get_state(rk_handle h, double* host_car_f64, int32_t* host_car_i32, int32_t* host_env_i32, double* host_env_f64);
 RK_API int rk_set_state(rk_handle h, const double* host_car_f64, const int32_t* host_car_i32, const int32_t* host_env_i32, const double* host_env_f64);
 /* recompute observations from the current state (racing_env.py:55-75) */
-RK_API int rk_observe(rk_handle h, float* dev_obs, void* stream);
+RK_API int rk_observe(rk_handle h, float* dev_obs, int32_t layout, void* stream);
 
 /* ---- rollout-side kernels -------------------------------------------------- */
 /* GAE backward scan: PPO.compute_advantages (agent/ppo.py:134-154).  All
@@ -170,6 +179,12 @@ RK_API int rk_policy_act(const float* params, int32_t obs_dim, const float* obs,
                   float* logprob, float* value, float* mean, void* stream);
 /* number of float32 values in the flattened Agent for a given obs_dim/action_dim=2 */
 RK_API int rk_policy_param_count(int32_t obs_dim);
+
+/* ---- measurement aid --------------------------------------------------------- */
+/* Sustained FMA throughput of the current device in TFLOP/s (fp32, or fp64 when
+ * use_fp64 != 0): the non-tensor roofline denominator bench.py reports the step
+ * kernel against (SURVEY.md 8d asks the builder to measure it). */
+RK_API double rk_fma_peak(int32_t use_fp64, int32_t iters);
 
 #ifdef __cplusplus
 }

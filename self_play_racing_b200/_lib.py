@@ -15,6 +15,7 @@ RK_ENV_SINGLE, RK_ENV_MULTI = 0, 1
 RK_AUTORESET_NEXT_STEP, RK_AUTORESET_SAME_STEP, RK_AUTORESET_DISABLED = 0, 1, 2
 RK_QUERY_EXACT_F64, RK_QUERY_CULLED = 0, 1
 RK_MAX_AGENTS, RK_MAX_SENSORS = 8, 64
+RK_LAYOUT_ENV_MAJOR, RK_LAYOUT_AGENT_MAJOR = 0, 1
 
 AUTORESET = {'next_step': RK_AUTORESET_NEXT_STEP, 'same_step': RK_AUTORESET_SAME_STEP,
              'disabled': RK_AUTORESET_DISABLED}
@@ -30,12 +31,13 @@ class RkConfig(C.Structure):
 
 
 class RkStepIO(C.Structure):
-    _fields_ = [('struct_size', C.c_int32), ('reserved0', C.c_int32),
+    _fields_ = [('struct_size', C.c_int32), ('layout', C.c_int32),
                 ('actions', C.c_void_p), ('start_slot', C.c_void_p), ('obs', C.c_void_p),
                 ('reward_f32', C.c_void_p), ('reward_f64', C.c_void_p),
                 ('terminated', C.c_void_p), ('truncated', C.c_void_p), ('done', C.c_void_p),
                 ('done_f32', C.c_void_p), ('ep_mask', C.c_void_p), ('ep_return', C.c_void_p),
-                ('ep_length', C.c_void_p), ('info_f64', C.c_void_p), ('info_i32', C.c_void_p)]
+                ('ep_length', C.c_void_p), ('info_f64', C.c_void_p), ('info_i32', C.c_void_p),
+                ('ep_stats', C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/racing_b200.h declares
@@ -53,17 +55,18 @@ SIGNATURES = {
                                      C.c_void_p]),
     'rk_num_tracks': (C.c_int, [C.c_void_p]),
     'rk_get_track': (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
-    'rk_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'rk_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'rk_step': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.c_void_p]),
     'rk_set_speed_weight': (C.c_int, [C.c_void_p, C.c_double]),
     'rk_get_state': (C.c_int, [C.c_void_p] * 5),
     'rk_set_state': (C.c_int, [C.c_void_p] * 5),
-    'rk_observe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'rk_observe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'rk_gae': (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     'rk_policy_act': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'rk_policy_param_count': (C.c_int, [C.c_int32]),
+    'rk_fma_peak': (C.c_double, [C.c_int32, C.c_int32]),
 }
 
 _lib = None

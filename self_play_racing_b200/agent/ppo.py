@@ -1,0 +1,263 @@
+"""`Agent` and `PPO` with the reference's constructor and method surface
+(agent/ppo.py:11-293), re-designed so that the rollout never leaves the device:
+
+  * the vector env is ONE `BatchedRacingVecEnv` (one fused kernel per step);
+  * the per-step policy forward + sampling + log-prob + value is one fused
+    kernel (`rk_policy_act`) reading the observation the step kernel just wrote;
+  * the step kernel writes observation, reward and done straight into the
+    [T, ...] rollout buffers (no per-step copies, no host synchronisation);
+  * GAE is one backward-scan kernel (`rk_gae`);
+  * the clipped-surrogate update stays PyTorch autograd on the device, with an
+    optional NCCL all-reduce of the flat gradient and of the three global
+    minibatch statistics when torch.distributed is initialised (environments
+    shard across GPUs; nothing else is communicated).
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from ..backend import flatten_agent, gae as gae_kernel, policy_act
+from ..environment.vec_env import BatchedRacingVecEnv
+
+
+def _ortho(layer, std=np.sqrt(2), bias=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias)
+    return layer
+
+
+class Agent(nn.Module):
+    """Two separate 64-64 tanh MLPs and a state-independent log_std *buffer*;
+    state_dict keys match the reference (agent/ppo.py:11-37) so its checkpoints
+    load here and vice versa."""
+
+    def __init__(self, obs_space, action_space):
+        super().__init__()
+        obs_dim = int(np.array(obs_space.shape).prod())
+        action_dim = action_space.shape[0]
+        self.actor_mu = nn.Sequential(
+            _ortho(nn.Linear(obs_dim, 64)), nn.Tanh(),
+            _ortho(nn.Linear(64, 64)), nn.Tanh(),
+            _ortho(nn.Linear(64, action_dim), std=0.01), nn.Tanh())
+        self.register_buffer('log_std', torch.zeros(action_dim))
+        self.critic = nn.Sequential(
+            _ortho(nn.Linear(obs_dim, 64)), nn.Tanh(),
+            _ortho(nn.Linear(64, 64)), nn.Tanh(),
+            _ortho(nn.Linear(64, 1), std=1.0))
+
+    def get_value(self, obs):
+        return self.critic(obs)
+
+    def get_action_and_value(self, obs, action=None):
+        mu = self.actor_mu(obs)
+        dist = torch.distributions.Normal(mu, torch.exp(self.log_std).expand_as(mu))
+        if action is None:
+            action = torch.clamp(dist.sample(), -1.0, 1.0)
+        return action, dist.log_prob(action).sum(-1), dist.entropy().sum(-1), self.critic(obs)
+
+
+def _dist_ready():
+    return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+
+class PPO:
+    LOG_STD_RANGE = (-0.5, -1.6)  # agent/ppo.py:250-253
+
+    def __init__(self, env_fn, config, device='cuda', query='culled'):
+        self.config = config
+        self.device = torch.device(device)
+        self.query = query
+        self.world = torch.distributed.get_world_size() if _dist_ready() else 1
+        self.rank = torch.distributed.get_rank() if _dist_ready() else 0
+        self.envs = self._make_vec_env(env_fn)
+        random.seed(config['seed'])
+        np.random.seed(config['seed'])
+        torch.manual_seed(config['seed'])
+        self.agent = Agent(self.envs.single_observation_space, self.envs.single_action_space).to(self.device)
+        self.optimizer = optim.Adam(self.agent.parameters(), lr=config['learning_rate'], eps=1e-5)
+        self._act_counter = 0
+        self._perm_gen = None
+
+    # ---- env construction (agent/ppo.py:70,85-95) ------------------------------
+    def _make_env(self, env_fn, seed, env_idx):
+        return lambda: env_fn(env_idx)
+
+    def _make_vec_env(self, env_fn):
+        c = self.config
+        if isinstance(env_fn, BatchedRacingVecEnv):
+            return env_fn
+        return BatchedRacingVecEnv([self._make_env(env_fn, c['seed'] + i, i) for i in range(c['num_envs'])],
+                                   device=self.device if self.device.type == 'cuda' else None, query=self.query,
+                                   seed=c['seed'] + 7919 * self.rank)
+
+    # ---- rollout (agent/ppo.py:97-132), device resident ---------------------------
+    def alloc_buffers(self):
+        """[T+1] observation/done slots so the step kernel can write step t's
+        successor in place; `obs[:T]`, `dones[:T]` are the reference's buffers."""
+        c, be = self.config, self.envs.be
+        T, E, A, D, dev = c['num_steps'], c['num_envs'], be.A, be.D, be.device
+        return dict(obs=torch.zeros(T + 1, A, E, D, device=dev), actions=torch.zeros(T, A, E, 2, device=dev),
+                    logprobs=torch.zeros(T, E, device=dev), dones=torch.zeros(T + 1, E, device=dev),
+                    rewards=torch.zeros(T, A, E, device=dev), values=torch.zeros(T, E, device=dev))
+
+    def collect_rollout(self, buf):
+        """Fills buf in place; slot 0 of obs/dones must hold next_obs/next_done
+        of the previous rollout.  Returns (episodes, mean_return, mean_length)."""
+        c, envs = self.config, self.envs
+        be = envs.be
+        T = c['num_steps']
+        params = flatten_agent(self.agent.state_dict()).to(be.device)
+        be.ep_stats.zero_()
+        with torch.no_grad():
+            for t in range(T):
+                self._act_counter += 1
+                policy_act(params, buf['obs'][t, 0], buf['actions'][t, 0], seed=c['seed'] * 2654435761 + self.rank,
+                           counter=self._act_counter, logprob=buf['logprobs'][t], value=buf['values'][t])
+                envs.step_into(buf['actions'][t], buf['obs'][t + 1], buf['rewards'][t], buf['dones'][t + 1])
+        n, ret, length = (float(v) for v in (be.ep_stats[2], be.ep_stats[0], be.ep_stats[1]))  # one sync per rollout
+        return int(n), (ret / n if n else 0.0), (length / n if n else 0.0)
+
+    # ---- GAE (agent/ppo.py:134-154) ---------------------------------------------------
+    def compute_advantages(self, rewards, dones, values, next_value, next_done):
+        c = self.config
+        if rewards.is_cuda:
+            return gae_kernel(rewards, values, dones, next_value, next_done, c['gamma'], c['gae_lambda'])
+        raise RuntimeError('compute_advantages runs on the device only (rk_gae); there is no CPU path')
+
+    # ---- update (agent/ppo.py:156-209) ------------------------------------------------
+    def _all_reduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t)
+        return t
+
+    def _permutation(self, n, device):
+        """Shared-seed device permutation (the reference shuffles on the host
+        with np.random, agent/ppo.py:168); identical on every rank by construction."""
+        if self._perm_gen is None or self._perm_gen.device != device:
+            self._perm_gen = torch.Generator(device=device)
+            self._perm_gen.manual_seed(self.config['seed'] + 12345)
+        return torch.randperm(n, device=device, generator=self._perm_gen)
+
+    def ppo_update(self, advantages, returns, values, logprobs, actions, obs, permutation=None):
+        """Flat [B, ...] tensors of THIS rank's share of the batch.  Returns the
+        number of optimizer steps taken (the KL early stop aborts the update)."""
+        c = self.config
+        b_obs = obs.reshape(-1, obs.shape[-1])
+        b_actions = actions.reshape(-1, actions.shape[-1])
+        b_logprobs, b_adv = logprobs.reshape(-1), advantages.reshape(-1)
+        b_returns, b_values = returns.reshape(-1), values.reshape(-1)
+        n_local = b_obs.shape[0]
+        mb_local = max(n_local // c['num_minibatches'], 1)
+        params = [p for p in self.agent.parameters()]
+        n_steps = 0
+        for epoch in range(c['update_epochs']):
+            perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
+            for start in range(0, n_local - mb_local + 1, mb_local):
+                idx = perm[start:start + mb_local]
+                mb_obs, mb_act = b_obs[idx], b_actions[idx]
+                _, new_logp, entropy, new_v = self.agent.get_action_and_value(mb_obs, mb_act)
+                old_logp = b_logprobs[idx]
+                logratio = new_logp - old_logp
+                ratio = logratio.exp()
+                mb_adv = b_adv[idx]
+                with torch.no_grad():
+                    # global-minibatch statistics: KL stop (ppo.py:178-182) and advantage
+                    # normalisation with the unbiased std (ppo.py:187) over all ranks' samples
+                    stats = torch.stack([(-logratio).sum(), mb_adv.sum(), (mb_adv * mb_adv).sum(),
+                                         torch.tensor(float(mb_local), device=mb_adv.device)]).double()
+                    self._all_reduce(stats)
+                    n = stats[3]
+                    approx_kl = stats[0] / n
+                    mean = stats[1] / n
+                    std = ((stats[2] - n * mean * mean) / (n - 1)).clamp_min(0).sqrt()
+                    if approx_kl > c['kl_target']:
+                        if self.rank == 0:
+                            print(f'  Early stopping at epoch {epoch + 1} due to KL divergence: {float(approx_kl):.4f}')
+                        return n_steps
+                adv = (mb_adv - mean.float()) / (std.float() + 1e-8)
+                pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - c['clip_coef'], 1 + c['clip_coef'])).mean()
+                new_v = new_v.flatten()
+                v_old, ret = b_values[idx], b_returns[idx]
+                v_clip = v_old + torch.clamp(new_v - v_old, -c['clip_coef'], c['clip_coef'])
+                v_loss = 0.5 * torch.max((new_v - ret) ** 2, (v_clip - ret) ** 2).mean()
+                loss = pg_loss + c['ent_coef'] * (-entropy.mean()) + c['vf_coef'] * v_loss
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                if self.world > 1:  # one flat all-reduce of the 11,075-float gradient
+                    flat = torch.cat([p.grad.reshape(-1) for p in params])
+                    self._all_reduce(flat).div_(self.world)
+                    off = 0
+                    for p in params:
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                        off += p.numel()
+                nn.utils.clip_grad_norm_(params, c['max_grad_norm'])
+                self.optimizer.step()
+                n_steps += 1
+        return n_steps
+
+    # ---- training loop (agent/ppo.py:211-287) ---------------------------------------------
+    def _anneal(self, update, num_updates):
+        c = self.config
+        frac = max(0.0, 1.0 - update / num_updates)
+        self.optimizer.param_groups[0]['lr'] = frac * c['learning_rate']
+        lo, hi = self.LOG_STD_RANGE
+        self.agent.log_std.data.fill_(frac * lo + (1 - frac) * hi)
+        return frac
+
+    def _learn_from(self, buf):
+        """GAE + update from a filled rollout buffer; returns optimizer steps taken."""
+        c = self.config
+        T = c['num_steps']
+        obs, dones = buf['obs'][:T, 0], buf['dones'][:T]
+        next_obs, next_done = buf['obs'][T, 0], buf['dones'][T]
+        rewards, actions = buf['rewards'][:, 0], buf['actions'][:, 0]
+        with torch.no_grad():
+            next_value = self.agent.get_value(next_obs).flatten()
+        adv, ret = self.compute_advantages(rewards.contiguous(), dones.contiguous(), buf['values'], next_value, next_done)
+        steps = self.ppo_update(adv, ret, buf['values'], buf['logprobs'], actions, obs)
+        # carry next_obs / next_done into slot 0 of the next rollout (ppo.py:104-106)
+        buf['obs'][0].copy_(buf['obs'][T])
+        buf['dones'][0].copy_(buf['dones'][T])
+        return steps
+
+    def train(self, log=print):
+        c = self.config
+        buf = self.alloc_buffers()
+        buf['obs'][0].copy_(self._reset_all())
+        num_updates = c['total_timesteps'] // (c['batch_size'] * self.world)
+        global_step = 0
+        training_info = {'steps': [], 'rewards': []}
+        for update in range(num_updates):
+            frac = self._anneal(update, num_updates)
+            if c.get('anneal_speed_weight', False):
+                # ppo.py:256-258 writes speed_weight 8 -> 14 onto the outermost gymnasium
+                # wrapper, which gymnasium >= 1.0 does not forward to RacingEnv (SURVEY quirk
+                # 11): off by default to match the pinned dependency's behaviour.
+                self.envs.set_speed_weight(8.0 + (1 - frac) * 6.0)
+            n_ep, mean_r, mean_l = self.collect_rollout(buf)
+            self._learn_from(buf)
+            global_step += c['batch_size'] * self.world
+            if n_ep:
+                training_info['steps'].append(global_step)
+                training_info['rewards'].append(float(mean_r))
+                log(f'Update {update + 1}/{num_updates} | Step {global_step} | Episodes: {n_ep} | '
+                    f'Mean Reward: {mean_r:.2f} | Mean Length: {mean_l:.2f}')
+            else:
+                log(f'Update {update + 1}/{num_updates} | Step {global_step} | No episodes completed this rollout')
+        self.training_info = training_info
+        return training_info
+
+    def _reset_all(self):
+        self.envs.reset_device()
+        return self.envs.be.obs
+
+    def save(self, path):
+        torch.save(self.agent.state_dict(), path)
+
+    def load(self, path):
+        self.agent.load_state_dict(torch.load(path, map_location=self.device))

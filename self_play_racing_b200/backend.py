@@ -35,7 +35,7 @@ class RacingBackend:
 
     def __init__(self, num_envs, kind='single', num_agents=1, num_sensors=11, device=None,
                  autoreset='next_step', query='exact', speed_weight=8.0, seed=0,
-                 max_episode_steps=3000, want_info=True):
+                 max_episode_steps=3000, want_info=True, agent_major=False):
         if not torch.cuda.is_available():
             raise RuntimeError('self_play_racing_b200 needs a CUDA device (sm_100a); there is no CPU path')
         self.lib = _lib.load()
@@ -58,24 +58,43 @@ class RacingBackend:
         self.h = h
         E, A, D, dev = self.E, self.A, self.D, self.device
         f32, f64, u8, i32 = torch.float32, torch.float64, torch.uint8, torch.int32
-        self.actions = torch.zeros(E, A, 2, dtype=f32, device=dev)
-        self.obs = torch.zeros(E, A, D, dtype=f32, device=dev)
-        self.reward = torch.zeros(E, A, dtype=f32, device=dev)
-        self.reward64 = torch.zeros(E, A, dtype=f64, device=dev)
-        self.terminated = torch.zeros(E, dtype=u8, device=dev)
-        self.truncated = torch.zeros(E, dtype=u8, device=dev)
+        # per-car arrays are [E,A,...], or [A,E,...] when agent_major (car a of
+        # every env contiguous: the SelfPlayWrapper view needs no gather)
+        self.agent_major = bool(agent_major)
+        self.layout = _lib.RK_LAYOUT_AGENT_MAJOR if agent_major else _lib.RK_LAYOUT_ENV_MAJOR
+        lead = (A, E) if agent_major else (E, A)
+        self.actions = torch.zeros(*lead, 2, dtype=f32, device=dev)
+        self.obs = torch.zeros(*lead, D, dtype=f32, device=dev)
+        self.reward = torch.zeros(*lead, dtype=f32, device=dev)
         self.done = torch.zeros(E, dtype=u8, device=dev)
         self.done_f32 = torch.zeros(E, dtype=f32, device=dev)
-        self.ep_mask = torch.zeros(E, dtype=u8, device=dev)
-        self.ep_return = torch.zeros(E, dtype=f64, device=dev)
-        self.ep_length = torch.zeros(E, dtype=i32, device=dev)
-        self.info_f64 = torch.zeros(E, A, 5, dtype=f64, device=dev) if want_info else None
-        self.info_i32 = torch.zeros(E, A, 4, dtype=i32, device=dev) if want_info else None
+        # Host-visible results of car 0 live back to back in one arena so the
+        # Gymnasium-facing step can fetch them with a single device->host copy:
+        # [ep_return f64 | ep_length i32 | terminated | truncated | ep_mask | pad | reward64 (all cars)]
+        sizes = [8 * E, 4 * E, E, E, E]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        r64_off = int((offs[-1] + 7) // 8 * 8)
+        self.arena = torch.zeros(r64_off + 8 * A * E, dtype=u8, device=dev)
+        cut = lambda o, n, dt: self.arena[int(o):int(o) + n].view(dt)
+        self.ep_return = cut(offs[0], 8 * E, f64)
+        self.ep_length = cut(offs[1], 4 * E, i32)
+        self.terminated = cut(offs[2], E, u8)
+        self.truncated = cut(offs[3], E, u8)
+        self.ep_mask = cut(offs[4], E, u8)
+        self.reward64 = cut(r64_off, 8 * A * E, f64).view(*lead)
+        self.arena_host_bytes = r64_off + 8 * E if agent_major or A == 1 else r64_off + 8 * A * E
+        self.arena_offsets = dict(ep_return=0, ep_length=int(offs[1]), terminated=int(offs[2]),
+                                  truncated=int(offs[3]), ep_mask=int(offs[4]), reward64=r64_off)
+        self.ep_stats = torch.zeros(3, dtype=f64, device=dev)  # sum return, sum length, episodes
+        self.info_f64 = torch.zeros(*lead, 5, dtype=f64, device=dev) if want_info else None
+        self.info_i32 = torch.zeros(*lead, 4, dtype=i32, device=dev) if want_info else None
         self._io = _lib.RkStepIO(struct_size=C.sizeof(_lib.RkStepIO))
         self._bind_io()
 
     def _bind_io(self):
         io = self._io
+        io.layout = self.layout
+        io.ep_stats = self.ep_stats.data_ptr()
         io.actions = self.actions.data_ptr()
         io.start_slot = None
         io.obs = self.obs.data_ptr()
@@ -160,8 +179,8 @@ class RacingBackend:
     # ---- env --------------------------------------------------------------
     def reset(self, mask=None, start_slot=None):
         """Reset all (or masked) environments; returns the obs tensor [E,A,D]."""
-        _lib.check(self.lib.rk_reset(self.h, _ptr(mask), _ptr(start_slot), _ptr(self.obs), self._stream()),
-                   self.h, 'rk_reset')
+        _lib.check(self.lib.rk_reset(self.h, _ptr(mask), _ptr(start_slot), _ptr(self.obs), self.layout,
+                                     self._stream()), self.h, 'rk_reset')
         return self.obs
 
     def step(self, start_slot=None):
@@ -171,7 +190,7 @@ class RacingBackend:
         _lib.check(self.lib.rk_step(self.h, C.byref(self._io), self._stream()), self.h, 'rk_step')
 
     def observe(self):
-        _lib.check(self.lib.rk_observe(self.h, _ptr(self.obs), self._stream()), self.h, 'rk_observe')
+        _lib.check(self.lib.rk_observe(self.h, _ptr(self.obs), self.layout, self._stream()), self.h, 'rk_observe')
         return self.obs
 
     def set_speed_weight(self, w):

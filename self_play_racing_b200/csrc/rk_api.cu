@@ -264,7 +264,8 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
     return 0;
 }
 
-int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs, void* stream) {
+int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot, float* dev_obs, int32_t layout,
+             void* stream) {
     if (!h) return 1;
     StepParams p;
     if (fill_params(h, p, "rk_reset")) return 1;
@@ -272,6 +273,7 @@ int rk_reset(rk_handle h, const uint8_t* dev_mask, const int32_t* dev_start_slot
     p.reset_mask = dev_mask;
     p.io.start_slot = dev_start_slot;
     p.io.obs = dev_obs;
+    p.io.layout = layout;
     if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
         snprintf(h->err, sizeof(h->err), "rk_reset: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
@@ -300,7 +302,7 @@ int rk_step(rk_handle h, const rk_step_io* io, void* stream) {
     return 0;
 }
 
-int rk_observe(rk_handle h, float* dev_obs, void* stream) {
+int rk_observe(rk_handle h, float* dev_obs, int32_t layout, void* stream) {
     if (!h) return 1;
     if (!dev_obs) {
         snprintf(h->err, sizeof(h->err), "rk_observe: null obs");
@@ -310,6 +312,7 @@ int rk_observe(rk_handle h, float* dev_obs, void* stream) {
     if (fill_params(h, p, "rk_observe")) return 1;
     p.mode = 2;
     p.io.obs = dev_obs;
+    p.io.layout = layout;
     if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
         snprintf(h->err, sizeof(h->err), "rk_observe: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;

@@ -1,0 +1,60 @@
+// FMA-pipe peak micro-benchmark: the FP32 / FP64 roofline denominators of the
+// step kernel are not in MEASURED_PEAKS.json, so bench.py
+// measures them live with this kernel: 8 independent dependent-FMA chains per
+// thread, every SM saturated, timed with CUDA events.
+#include "rk_types.cuh"
+
+namespace rk {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) fma_chain_kernel(T* out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3;
+    T x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    const T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456789) out[0] = s;  // never true; keeps the chains alive
+}
+
+template <typename T>
+double measure(int iters) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    T* out = nullptr;
+    if (cudaMalloc(&out, sizeof(T)) != cudaSuccess) return -1.0;
+    const int grid = sms * 8, block = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        fma_chain_kernel<T><<<grid, block>>>(out, iters, (T)1.0000001, (T)1e-7);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        count_launch();
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * block;
+        if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
+
+}  // namespace
+}  // namespace rk
+
+extern "C" RK_API double rk_fma_peak(int32_t use_fp64, int32_t iters) {
+    if (iters <= 0) iters = 1024;
+    return use_fp64 ? rk::measure<double>(iters) : rk::measure<float>(iters);
+}

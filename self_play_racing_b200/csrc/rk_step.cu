@@ -159,7 +159,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
     const TrackMeta tm = tp.meta[tp.env_to_track[e]];
     const double Nd = (double)tm.n_wp;
     const bool is_car = lane < A;
-    const int c = e * A + (is_car ? lane : 0);
+    const int c = e * A + (is_car ? lane : 0);  // state index
+    // index of car (e, a) in the caller's per-car arrays
+    const bool agent_major = p.io.layout == RK_LAYOUT_AGENT_MAJOR;
+    auto io_index = [&](int a) -> size_t { return agent_major ? (size_t)a * p.E + e : (size_t)e * A + a; };
+    const size_t ci = io_index(is_car ? lane : 0);
 
     // ---- which of {step, reset, observe} applies to this environment -------
     bool stepping = (p.mode == 0);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
         const bool moving = is_car && !(flags & F_CRASHED);  // car.py:51-52
         double cs = 1.0, sn = 0.0;
         if (is_car) {
-            const float a0 = p.io.actions[2 * c], a1 = p.io.actions[2 * c + 1];
+            const float a0 = p.io.actions[2 * ci], a1 = p.io.actions[2 * ci + 1];
             const float steer_f = fminf(fmaxf(a0, -1.f), 1.f);  // racing_env.py:106
             float thr_f;
             if (KIND == RK_ENV_SINGLE)
@@ -372,6 +376,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
             if (p.io.ep_mask) p.io.ep_mask[e] = ended;
             if (p.io.ep_return) p.io.ep_return[e] = ended ? er : 0.0;
             if (p.io.ep_length) p.io.ep_length[e] = ended ? el : 0;
+            if (p.io.ep_stats && ended) {
+                atomicAdd(p.io.ep_stats + 0, er);
+                atomicAdd(p.io.ep_stats + 1, (double)el);
+                atomicAdd(p.io.ep_stats + 2, 1.0);
+            }
         }
     } else if (p.mode == 0 && lane == 0) {
         if (p.io.ep_mask) p.io.ep_mask[e] = 0;
@@ -381,14 +390,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
     // per-car info of the step itself (before any same-step reset)
     if (p.mode == 0 && is_car) {
         if (p.io.info_f64) {
-            double* o = p.io.info_f64 + 5 * (size_t)c;
+            double* o = p.io.info_f64 + 5 * ci;
             o[0] = x; o[1] = y;
             o[2] = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));
             o[3] = (flags & F_FINISHED) ? 1.0 : ddiv((double)pidx, Nd);
             o[4] = delta;
         }
         if (p.io.info_i32) {
-            int32_t* o = p.io.info_i32 + 4 * (size_t)c;
+            int32_t* o = p.io.info_i32 + 4 * ci;
             o[0] = (flags & F_CRASHED) != 0; o[1] = (flags & F_FINISHED) != 0;
             o[2] = placement; o[3] = pidx;
         }
@@ -456,8 +465,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
     if (p.mode == 0) {
         if (is_car) {
             const double r = stepping ? reward : 0.0;
-            if (p.io.reward_f32) p.io.reward_f32[c] = (float)r;
-            if (p.io.reward_f64) p.io.reward_f64[c] = r;
+            if (p.io.reward_f32) p.io.reward_f32[ci] = (float)r;
+            if (p.io.reward_f64) p.io.reward_f64[ci] = r;
         }
         if (lane == 0) {
             p.io.terminated[e] = terminated;
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
     const int D = p.D;
     for (int a = 0; a < A; ++a) {
         const double ox = S.x[a], oy = S.y[a], oang = S.ang[a];
-        float* orow = obs + ((size_t)e * A + a) * D;
+        float* orow = obs + io_index(a) * D;
         for (int r0 = 0; r0 < R; r0 += kRayBlock) {
             const int nr = min(kRayBlock, R - r0);
             double v3x[kRayBlock], v3y[kRayBlock], best[kRayBlock];
@@ -532,7 +541,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
         }
     }
     if (is_car) {
-        float* orow = obs + (size_t)c * D + R;
+        float* orow = obs + ci * D + R;
         const double vf = clipd(ddiv(dadd(dmul(vx, cs), dmul(vy, sn)), kMaxSpeed), -1.0, 1.0);
         const double vl = clipd(ddiv(dadd(dmul(-vx, sn), dmul(vy, cs)), kMaxSpeed), -1.0, 1.0);
         orow[0] = (float)vf;

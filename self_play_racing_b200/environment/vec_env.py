@@ -1,0 +1,272 @@
+"""`BatchedRacingVecEnv`: the vector-env surface the reference's PPO drives
+(`gym.vector.SyncVectorEnv` of `RecordEpisodeStatistics`-wrapped envs; call
+sites agent/ppo.py:70,88,114-130,230 and agent/self_play_ppo.py:19-29,49-50),
+backed by ONE device-resident batch and one fused kernel per step.
+
+Two faces:
+  * Gymnasium face -- `reset()` / `step(actions)` with HOST numpy arrays, the
+    exact return convention of SyncVectorEnv (obs float32 (E,D), reward float64
+    (E,), terminated/truncated bool (E,), infos with "episode"/"_episode" only
+    on steps where an episode ended; NEXT_STEP auto-reset).
+  * device face -- `reset_device()` / `step_device(actions)` on CUDA tensors
+    with no host synchronisation, used by the device-resident rollout.
+
+Environments that are `SelfPlayWrapper(MultiRacingEnv)` get the wrapper's
+semantics (environment/wrappers.py:29-55): car 0 is the learner, car 1 is driven
+by the frozen opponent snapshot (or uniform random actions when none is set),
+whose inference is one fused kernel over all environments.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import spaces
+from ..backend import RacingBackend, flatten_agent, policy_act
+from .multi_racing_env import MultiRacingEnv
+from .racing_env import RacingEnv
+from .track import Track
+from .wrappers import SelfPlayWrapper
+
+
+class _EnvProxy:
+    """Element of `vec.envs`: attribute writes such as the speed_weight
+    annealing of agent/ppo.py:256-258 reach the batch."""
+
+    def __init__(self, vec, idx, spec):
+        object.__setattr__(self, '_vec', vec)
+        object.__setattr__(self, '_idx', idx)
+        object.__setattr__(self, '_spec', spec)
+
+    def __setattr__(self, name, value):
+        if name == 'speed_weight':
+            self._vec.set_speed_weight(value)
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getattr__(self, name):
+        if name == 'speed_weight':
+            return self._vec.speed_weight
+        if name == 'track':
+            return self._vec.track_of(self._idx)
+        return getattr(self._spec, name)
+
+
+class BatchedRacingVecEnv:
+    def __init__(self, env_fns, device=None, query='culled', autoreset='next_step', seed=0, copy=True,
+                 want_info=False):
+        envs = [fn() if callable(fn) else fn for fn in env_fns]
+        if not envs:
+            raise ValueError('need at least one environment')
+        self.selfplay = isinstance(envs[0], SelfPlayWrapper)
+        base = [e.env if isinstance(e, SelfPlayWrapper) else e for e in envs]
+        first = base[0]
+        if not isinstance(first, (RacingEnv, MultiRacingEnv)):
+            raise TypeError(f'unsupported environment type {type(first).__name__}')
+        for b in base:
+            if type(b) is not type(first) or b.num_sensors != first.num_sensors or b.num_agents != first.num_agents:
+                raise ValueError('all environments of a batch must share class, num_sensors and num_agents')
+        if self.selfplay and first.num_agents != 2:
+            raise ValueError('SelfPlayWrapper drives exactly one opponent (num_agents must be 2)')
+        self._specs = envs
+        self.kind = first.KIND
+        self.num_envs = len(envs)
+        self.num_agents = first.num_agents
+        self.copy = copy
+        # de-duplicate tracks: one device table per distinct (control points, width)
+        keys, cps, widths, e2t = {}, [], [], np.zeros(self.num_envs, dtype=np.int32)
+        for i, b in enumerate(base):
+            k = (b.control_points.tobytes(), b.track_width)
+            if k not in keys:
+                keys[k] = len(cps)
+                cps.append(b.control_points)
+                widths.append(b.track_width)
+            e2t[i] = keys[k]
+        self.env_to_track = e2t
+        sw = first.speed_weight if self.kind == 'single' else 8.0
+        self.be = RacingBackend(self.num_envs, kind=self.kind, num_agents=self.num_agents,
+                                num_sensors=first.num_sensors, device=device, autoreset=autoreset, query=query,
+                                speed_weight=sw, seed=seed, want_info=want_info, agent_major=True)
+        self.be.set_tracks_from_control_points(cps, widths, env_to_track=e2t)
+        self._finish_init(first, seed)
+
+    # -- alternative constructors for large synthetic batches -------------------
+    @classmethod
+    def synthetic(cls, kind, num_envs, n_tracks=16, num_agents=2, num_sensors=11, selfplay=True, device=None,
+                  query='culled', autoreset='next_step', seed=0, copy=True, factor=30, width_lo=6.0, width_mod=4,
+                  want_info=False):
+        """E environments over a device-generated procedural pool (BASELINE
+        configs 2-5): env e runs on track e % n_tracks, widths width_lo + (t % width_mod)."""
+        self = cls.__new__(cls)
+        self.kind = kind
+        self.num_envs = int(num_envs)
+        self.num_agents = 1 if kind == 'single' else int(num_agents)
+        self.selfplay = bool(selfplay) and kind == 'multi' and self.num_agents == 2
+        self.copy = copy
+        self._specs = None
+        self.env_to_track = (np.arange(self.num_envs) % n_tracks).astype(np.int32)
+        self.be = RacingBackend(self.num_envs, kind=kind, num_agents=self.num_agents, num_sensors=num_sensors,
+                                device=device, autoreset=autoreset, query=query, seed=seed, want_info=want_info,
+                                agent_major=True)
+        self.be.generate_tracks(seed, n_tracks, factor=factor, width_lo=width_lo, width_mod=width_mod,
+                                env_to_track=self.env_to_track)
+        proto = RacingEnv(num_sensors=num_sensors) if kind == 'single' else \
+            MultiRacingEnv(num_agents=self.num_agents, num_sensors=num_sensors)
+        self._finish_init(proto, seed)
+        return self
+
+    def _finish_init(self, proto, seed):
+        be = self.be
+        if self.kind == 'single':
+            self.single_observation_space = proto.observation_space
+            self.single_action_space = proto.action_space
+        else:
+            self.single_observation_space = proto.observation_space['0']
+            self.single_action_space = proto.action_space['0']
+        self.observation_space = self.single_observation_space
+        self.action_space = self.single_action_space
+        E, D = self.num_envs, be.D
+        self.seed = int(seed)
+        self._opp_params = None     # flattened frozen opponent (device float32) or None -> random
+        self._opp_counter = 0
+        self._obs_cur = be.obs
+        self._tracks = {}
+        # pinned host staging for the Gymnasium face
+        self._h_actions = torch.zeros(E, 2, dtype=torch.float32).pin_memory()
+        self._h_obs = torch.zeros(E, D, dtype=torch.float32).pin_memory()
+        self._h_arena = torch.zeros(be.arena_host_bytes, dtype=torch.uint8).pin_memory()
+        a, o = self._h_arena.numpy(), be.arena_offsets
+        self._np_ep_return = a[o['ep_return']:o['ep_return'] + 8 * E].view(np.float64)
+        self._np_ep_length = a[o['ep_length']:o['ep_length'] + 4 * E].view(np.int32)
+        self._np_terminated = a[o['terminated']:o['terminated'] + E].view(np.bool_)
+        self._np_truncated = a[o['truncated']:o['truncated'] + E].view(np.bool_)
+        self._np_ep_mask = a[o['ep_mask']:o['ep_mask'] + E].view(np.bool_)
+        self._np_reward = a[o['reward64']:o['reward64'] + 8 * E].view(np.float64)
+        self.h2d_bytes_per_step = self._h_actions.numel() * 4
+        self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
+
+    # ---- reference-facing attributes ------------------------------------------
+    @property
+    def envs(self):
+        specs = self._specs or [None] * self.num_envs
+        return [_EnvProxy(self, i, s) for i, s in enumerate(specs)]
+
+    @property
+    def speed_weight(self):
+        return getattr(self, '_speed_weight', 8.0)
+
+    def set_speed_weight(self, value):
+        self._speed_weight = float(value)
+        self.be.set_speed_weight(value)
+
+    def track_of(self, env_idx):
+        t = int(self.env_to_track[env_idx])
+        if t not in self._tracks:
+            self._tracks[t] = Track(self.be.get_track(t))
+        return self._tracks[t]
+
+    def set_opponent(self, opponent_policy):
+        """SelfPlayWrapper.set_opponent for every environment at once.  Accepts
+        an Agent module, a state_dict, an already flattened parameter vector, or
+        None (uniform random opponent, wrappers.py:30-32)."""
+        if opponent_policy is None:
+            self._opp_params = None
+            return
+        if isinstance(opponent_policy, torch.Tensor):
+            flat = opponent_policy
+        else:
+            sd = opponent_policy.state_dict() if hasattr(opponent_policy, 'state_dict') else opponent_policy
+            flat = flatten_agent(sd)
+        self._opp_params = flat.to(self.be.device, torch.float32).contiguous()
+
+    # ---- device face -------------------------------------------------------------
+    @property
+    def obs_device(self):
+        """Learner observation [E, D] (car 0), a view of the kernel's output."""
+        return self.be.obs[0]
+
+    def reset_device(self, start_slot=None):
+        self.be.reset(start_slot=start_slot)
+        self._obs_cur = self.be.obs
+        return self.be.obs[0]
+
+    def _opponent_act(self, obs=None, actions=None):
+        """SelfPlayWrapper.step's opponent half (wrappers.py:30-39) for every env:
+        car 1's action from the frozen snapshot on car 1's latest observation."""
+        be = self.be
+        obs = be.obs if obs is None else obs
+        actions = be.actions if actions is None else actions
+        self._opp_counter += 1
+        policy_act(self._opp_params, obs[1] if self._opp_params is not None else None, actions[1],
+                   seed=self.seed ^ 0x5eed0bb, counter=self._opp_counter)
+
+    def step_into(self, actions, obs_out, reward_out, done_out, start_slot=None):
+        """Zero-copy rollout step: `actions` [A,E,2] already holds the learner's
+        action in actions[0]; the kernel writes the successor observation
+        [A,E,D], reward [A,E] and done [E] (float32) straight into the caller's
+        rollout-buffer slots.  No host synchronisation."""
+        be, io = self.be, self.be._io
+        if self.selfplay:
+            self._opponent_act(self._obs_cur, actions)
+        io.actions, io.obs = actions.data_ptr(), obs_out.data_ptr()
+        io.reward_f32, io.done_f32 = reward_out.data_ptr(), done_out.data_ptr()
+        try:
+            be.step(start_slot=start_slot)
+        finally:
+            be._bind_io()
+        self._obs_cur = obs_out
+
+    def step_device(self, actions, start_slot=None):
+        """actions: CUDA float32 [E, 2] (learner).  Returns views (obs [E,D],
+        reward float32 [E], done float32 [E]) valid until the next step; no
+        host synchronisation.  `done` = terminated | truncated, which is what
+        SelfPlayWrapper reports as `terminated` and PPO uses as next_done."""
+        be = self.be
+        if actions.data_ptr() != be.actions[0].data_ptr():
+            be.actions[0].copy_(actions)
+        if self.selfplay:
+            self._opponent_act()
+        be.step(start_slot=start_slot)
+        self._obs_cur = be.obs
+        return be.obs[0], be.reward[0], be.done_f32
+
+    # ---- Gymnasium face ------------------------------------------------------------
+    def reset(self, seed=None, options=None):
+        obs = self.reset_device()
+        self._h_obs.copy_(obs, non_blocking=True)
+        torch.cuda.current_stream(self.be.device).synchronize()
+        out = self._h_obs.numpy()
+        return (out.copy() if self.copy else out), {}
+
+    def step(self, actions, start_slot=None):
+        """SyncVectorEnv.step.  `start_slot` (int [E,A], optional, not part of the
+        gymnasium signature) injects the grid slots used by auto-resets this
+        step; by default they come from the backend's Philox stream."""
+        be = self.be
+        self._h_actions.numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
+        be.actions[0].copy_(self._h_actions, non_blocking=True)
+        if self.selfplay:
+            self._opponent_act()
+        if start_slot is not None:
+            start_slot = torch.as_tensor(np.ascontiguousarray(start_slot, dtype=np.int32)).to(be.device)
+        be.step(start_slot=start_slot)
+        self._obs_cur = be.obs
+        self._h_obs.copy_(be.obs[0], non_blocking=True)
+        self._h_arena.copy_(be.arena[:be.arena_host_bytes], non_blocking=True)
+        torch.cuda.current_stream(be.device).synchronize()
+        obs, rew = self._h_obs.numpy(), self._np_reward
+        term, trunc = self._np_terminated, self._np_truncated
+        if self.selfplay:  # wrappers.py:52: the wrapper reports dones["__all__"] as `terminated`
+            term = term | trunc
+        infos = {}
+        if self._np_ep_mask.any():
+            infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy()}
+            infos['_episode'] = self._np_ep_mask.copy()
+        if self.copy:
+            return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
+        return obs, rew, term, trunc, infos
+
+    def close(self):
+        if getattr(self, 'be', None) is not None:
+            self.be.close()
+            self.be = None

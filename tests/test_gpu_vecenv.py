@@ -1,0 +1,201 @@
+"""GPU tests of the reference-facing host layer: the Gymnasium faces
+(RacingEnv / MultiRacingEnv / SelfPlayWrapper / BatchedRacingVecEnv) and the
+device-resident PPO loop."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import racing_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    import self_play_racing_b200.environment as env
+    import self_play_racing_b200.agent as agent
+    import self_play_racing_b200.configs as configs
+    return env, agent, configs
+
+
+def test_single_env_object_matches_reference_golden(pkg, golden):
+    """RacingEnv(num_sensors=11) used the way evaluate.py uses it (reset/step/info)."""
+    env_mod, _, _ = pkg
+    g = golden('single_default_10k')
+    env = env_mod.RacingEnv(num_sensors=11)
+    assert env.observation_space.shape == (15,) and env.action_space.shape == (2,)
+    obs, info = env.reset()
+    np.testing.assert_allclose(obs, g['obs0'], atol=1e-6)
+    assert info['progress'] == 0.0 and not info['crashed']
+    for k in range(120):
+        obs, r, te, tr, info = env.step(g['actions'][k])
+        np.testing.assert_allclose(obs, g['obs'][k], atol=1e-6)
+        assert abs(r - g['reward'][k]) < 1e-9 and te == g['terminated'][k] and tr == g['truncated'][k]
+        assert set(info) >= {'position', 'speed', 'progress', 'crashed', 'finished', 'reward', 'progress_delta'}
+        np.testing.assert_allclose(info['position'], g['state'][k, :2], atol=1e-9)
+        if te:
+            break
+    assert te and info['crashed']
+    trk = env.track
+    np.testing.assert_allclose(trk.waypoints, g['waypoints'], atol=1e-11)
+    assert trk.left_boundary.shape == trk.right_boundary.shape == trk.waypoints.shape
+    np.testing.assert_allclose(env.car.get_corners().mean(0), [env.car.x, env.car.y], atol=1e-9)
+    env.close()
+
+
+def test_multi_env_object_and_selfplay_wrapper(pkg, golden):
+    env_mod, agent_mod, _ = pkg
+    g = golden('multi2_default')
+    env = env_mod.MultiRacingEnv(num_agents=2, num_sensors=11)
+    assert env.observation_space['0'].shape == (19,)
+    np.random.seed(107)  # tools/make_golden.py seeds 100 + seed before the first reset
+    np.random.seed(101)
+    obs, infos = env.reset()
+    np.testing.assert_allclose(np.stack([obs['0'], obs['1']]), g['obs0'], atol=1e-6)
+    for k in range(60):
+        obs, rew, dones, trunc, infos = env.step({'0': g['actions'][k, 0], '1': g['actions'][k, 1]})
+        np.testing.assert_allclose(np.stack([obs['0'], obs['1']]), g['obs'][k], atol=1e-6)
+        np.testing.assert_allclose([rew['0'], rew['1']], g['reward'][k], atol=1e-9)
+        assert dones['__all__'] == (g['terminated'][k] or g['truncated'][k]) and dones['0'] == g['terminated'][k]
+        if dones['__all__']:
+            assert [infos['0']['placement'], infos['1']['placement']] == list(g['placement'][k])
+            break
+    env.close()
+    # wrapper: learner view of car 0, random opponent in Box([-1,0],[1,1]), then a frozen policy
+    w = env_mod.SelfPlayWrapper(env_mod.MultiRacingEnv(num_agents=2, num_sensors=11), 0)
+    assert w.observation_space.shape == (19,)
+    o, info = w.reset()
+    assert o.shape == (19,)
+    o, r, done, trunc, info = w.step(np.array([0.1, 0.5], np.float32))
+    assert o.shape == (19,) and isinstance(r, float) and isinstance(done, bool)
+    torch.manual_seed(0)
+    pol = agent_mod.Agent(w.observation_space, w.action_space).cuda()
+    w.set_opponent(pol)
+    o, r, done, trunc, info = w.step(np.array([0.0, 1.0], np.float32))
+    assert np.isfinite(o).all()
+    w.close()
+
+
+def test_vec_env_gym_face_matches_reference_vector_golden(pkg, golden):
+    """BatchedRacingVecEnv built from env_fn thunks == SyncVectorEnv(RecordEpisodeStatistics(RacingEnv))."""
+    env_mod, _, _ = pkg
+    g = golden('vector_single4')
+    cps = np.split(g['pool'], np.cumsum(g['pool_sizes'])[:-1])
+    widths = [int(w) for w in g['widths']]
+    fns = [(lambda i=i: env_mod.RacingEnv(num_sensors=11, track_pool=cps, track_id=i, track_width=widths[i]))
+           for i in range(4)]
+    for query in ('exact', 'culled'):
+        vec = env_mod.BatchedRacingVecEnv(fns, query=query)
+        assert vec.single_observation_space.shape == (15,) and vec.single_action_space.shape == (2,)
+        obs, infos = vec.reset()
+        assert obs.dtype == np.float32 and infos == {}
+        np.testing.assert_allclose(obs, g['obs0'], atol=1e-6)
+        for k in range(len(g['actions'])):
+            obs, rew, term, trunc, infos = vec.step(g['actions'][k])
+            assert rew.dtype == np.float64 and term.dtype == np.bool_
+            np.testing.assert_allclose(obs, g['obs'][k], atol=1e-6)
+            np.testing.assert_allclose(rew, g['reward'][k], atol=1e-9)
+            np.testing.assert_array_equal(term, g['terminated'][k])
+            np.testing.assert_array_equal(trunc, g['truncated'][k])
+            if g['ep_mask'][k].any():
+                m = g['ep_mask'][k]
+                np.testing.assert_array_equal(infos['_episode'], m)
+                np.testing.assert_allclose(infos['episode']['r'][m], g['ep_r'][k][m], atol=1e-9)
+                np.testing.assert_array_equal(infos['episode']['l'][m], g['ep_l'][k][m])
+            else:
+                assert 'episode' not in infos
+        vec.close()
+
+
+def test_selfplay_vec_env_vs_oracle(pkg):
+    """SelfPlayWrapper semantics batched: learner = car 0, opponent = fused MLP
+    inference; the oracle is fed the actions the device actually used."""
+    env_mod, agent_mod, _ = pkg
+    rs = np.random.RandomState(4)
+    cps = [O.gen_random_track(12, 60, 15, 0.4, 0.5, rng=rs), O.gen_random_track(10, 55, 12, 0.3, 0.4, rng=rs)]
+    widths = [8, 7]
+    E = 96
+    fns = [(lambda i=i: env_mod.SelfPlayWrapper(env_mod.MultiRacingEnv(
+        num_agents=2, num_sensors=11, track_pool=cps, track_id=i % 2, track_width=widths), 0)) for i in range(E)]
+    vec = env_mod.BatchedRacingVecEnv(fns, seed=3, query='culled')
+    assert vec.selfplay and vec.be.num_tracks == 2
+    tracks = O.make_pool(cps, widths)
+    orc = O.OracleVecEnv(tracks, np.arange(E) % 2, kind='multi', num_agents=2, num_sensors=11, seed=0)
+    so = orc._draw_start_order(E)
+    vec.be.reset(start_slot=torch.from_numpy(so.astype(np.int32)).cuda())
+    oobs, _ = orc.reset(start_order=so)
+    torch.manual_seed(5)
+    pol = agent_mod.Agent(vec.single_observation_space, vec.single_action_space)
+    pol.log_std.data.fill_(-0.3)
+    ended = 0
+    for k in range(150):
+        if k == 40:
+            vec.set_opponent(pol)  # random opponent before, frozen snapshot after
+        a0 = rs.uniform(-1, 1, size=(E, 2)).astype(np.float32)
+        a0[:, 1] = np.abs(a0[:, 1])
+        so = orc._draw_start_order(E)
+        obs, rew, term, trunc, infos = vec.step(a0, start_slot=so)
+        used = vec.be.actions.cpu().numpy()              # [A, E, 2]: what the kernel consumed
+        np.testing.assert_array_equal(used[0], a0)
+        if k < 40:
+            assert (used[1, :, 1] >= 0).all() and (np.abs(used[1]) <= 1).all()
+        oobs, orew, ote, otr, _ = orc.step(np.transpose(used, (1, 0, 2)), start_order=so)
+        v_obs, v_rew, v_done, v_trunc = O.OracleVecEnv.selfplay_view(oobs, orew, ote, otr)
+        np.testing.assert_allclose(obs, v_obs, atol=1e-6, err_msg=f'step {k}')
+        np.testing.assert_allclose(rew, v_rew, atol=1e-9)
+        np.testing.assert_array_equal(term, v_done)
+        np.testing.assert_array_equal(trunc, v_trunc)
+        ended += int(v_done.sum())
+    assert ended > 10
+    vec.close()
+
+
+def test_selfplay_ppo_runs_on_device(pkg, tmp_path):
+    """Two updates of the full self-play loop (rollout + GAE + update + snapshot
+    + checkpoint) at a tiny size: finite losses, parameters move, checkpoint
+    round-trips with the reference's keys."""
+    env_mod, agent_mod, configs = pkg
+    np.random.seed(1)
+    pool = env_mod.gen_tracks(num_tracks=8, seed=1)
+    widths = [int(np.random.randint(6, 10)) for _ in range(8)]
+    cfg = configs.self_play_config(num_envs=256, num_steps=32, total_timesteps=256 * 32 * 3, snapshot_freq=1,
+                                   pool_size=2, update_epochs=2, num_minibatches=4)
+
+    def env_fn(i):
+        return env_mod.MultiRacingEnv(num_agents=2, num_sensors=11, track_pool=pool, track_id=i % 8, track_width=widths)
+    trainer = agent_mod.SelfPlayPPO(env_fn, cfg, device='cuda', checkpoint_dir=str(tmp_path))
+    before = torch.cat([p.detach().flatten().clone() for p in trainer.agent.parameters()])
+    logs = []
+    info = trainer.train(log=logs.append)
+    after = torch.cat([p.detach().flatten() for p in trainer.agent.parameters()])
+    assert torch.isfinite(after).all() and not torch.equal(before, after)
+    assert len(trainer.opponent_pool) == 2 and len(logs) == 3
+    assert set(info) == {'steps', 'rewards', 'opponent_pool_size'}
+    path = trainer.save_checkpoint(2, 3 * cfg['batch_size'], info)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {'update', 'global_step', 'agent_state_dict', 'optimizer_state_dict', 'opponent_pool',
+                       'config', 'training_info'}
+    assert len(ck['agent_state_dict']) == 13
+    t2 = agent_mod.SelfPlayPPO(env_fn, cfg, device='cuda', checkpoint_dir=str(tmp_path))
+    upd, gs, _ = t2.load_checkpoint(path)
+    assert upd == 2 and len(t2.opponent_pool) == 2
+    for a, b in zip(t2.agent.state_dict().values(), trainer.agent.state_dict().values()):
+        assert torch.equal(a, b)
+    t2.envs.close()
+
+
+def test_single_ppo_learns_something(pkg):
+    """A short single-agent PPO run: mean episode return improves over the
+    first updates (a sanity check of rollout/GAE/update wiring, not a claim)."""
+    env_mod, agent_mod, configs = pkg
+    cfg = configs.base_config(num_envs=1024, num_steps=64, total_timesteps=1024 * 64 * 12)
+    trainer = agent_mod.PPO(lambda i: env_mod.RacingEnv(num_sensors=11), cfg, device='cuda')
+    info = trainer.train(log=lambda s: None)
+    r = info['rewards']
+    assert len(r) >= 8 and np.isfinite(r).all()
+    assert np.mean(r[-3:]) > np.mean(r[:3])
+    trainer.envs.close()
