@@ -44,12 +44,17 @@ __device__ __forceinline__ double warp_min_d(double v) {
     return v;
 }
 
+constexpr int kListCapBytes = 512 * 2;
 // per-warp scratch in dynamic shared memory
 struct Scratch {
     double x[RK_MAX_AGENTS], y[RK_MAX_AGENTS], c[RK_MAX_AGENTS], s[RK_MAX_AGENTS];
     double ang[RK_MAX_AGENTS], vx[RK_MAX_AGENTS], vy[RK_MAX_AGENTS];
     double cx[RK_MAX_AGENTS][4], cy[RK_MAX_AGENTS][4];
 };
+
+__host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
+    return (sizeof(Scratch) + (size_t)A * R * (8 + 16 + 8) + kListCapBytes + 15) / 16 * 16;
+}
 
 // car.py:26-43: corners FL, FR, RR, RL = R(angle) * (+-2, +-1) + position
 __device__ __forceinline__ void corners(double x, double y, double c, double s, double* cx, double* cy) {
@@ -146,15 +151,197 @@ __device__ __forceinline__ void raycast_walls_exact(const TrackPool& tp, const T
     }
 }
 
-// ---------------------------------------------------------------------------
+
+// ===========================================================================
+// Culled query path (RK_QUERY_CULLED).  Candidates are found in fp32 on tables
+// stored relative to the track's bbox centre, over bounding circles of kChunk
+// consecutive waypoints / boundary segments (they are arc-length ordered, so a
+// chunk is spatially compact); every winner is then re-evaluated in float64
+// with the reference's formula, so results equal the exact path's.  Culling
+// never removes a possible winner: all bounds carry explicit slack for the
+// fp32 rounding of tables, query and arithmetic.
+// ===========================================================================
+constexpr int kListCap = 512;            // work items per warp batch
+constexpr float kHalfDiag = 2.2361f;     // >= sqrt(2^2 + 1^2): car corner distance from its centre
+constexpr float kPerpSlack = 3e-4f;      // fp32 error bound of a ray-line distance (|p| <= ~200)
+constexpr float kFrontSlack = 1e-3f;
+constexpr unsigned long long kNoKey = ~0ull;
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, m));
+    return v;
+}
+
+struct CullView {
+    unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment index) of the best wall candidate
+    double2* dir64;               // [A*R] (cos, sin) of the ray's world angle
+    float2* dir32;                // [A*R]
+    unsigned short* list;         // [kListCap]
+};
+
+// Waypoint argmin for the car centre + 4 corners (track.py:150-152): one
+// bounding-circle pass picks the chunks that can hold the nearest waypoint of
+// ANY of the five points, then those chunks are scanned exactly in float64.
+__device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackMeta& tm, const double* qx,
+                                               const double* qy, int lane, unsigned short* list, int* out_idx) {
+    const float4* wch = tp.wchunk + tm.wchunk_off;
+    const float cx0 = (float)(qx[0] - tm.org_x), cy0 = (float)(qy[0] - tm.org_y);
+    const int nwc = tm.n_wchunk;
+    float U = INFINITY;
+    for (int c0 = 0; c0 < nwc; c0 += 32) {
+        const int ci = c0 + lane;
+        if (ci < nwc) {
+            const float4 cc = wch[ci];
+            const float dx = cc.x - cx0, dy = cc.y - cy0;
+            U = fminf(U, sqrtf(dx * dx + dy * dy) + cc.z);
+        }
+    }
+    // every corner is within kHalfDiag of the centre: a chunk whose nearest possible
+    // waypoint is farther than U + 2*kHalfDiag from the centre can not win for any of them
+    const float thr = warp_min_f(U) + 2.f * kHalfDiag + 2e-2f;
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c0 = 0; c0 < nwc; c0 += 32) {
+        const int ci = c0 + lane;
+        bool keep = false;
+        if (ci < nwc) {
+            const float4 cc = wch[ci];
+            const float dx = cc.x - cx0, dy = cc.y - cy0;
+            keep = sqrtf(dx * dx + dy * dy) - cc.z <= thr;
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) list[count + __popc(m & lt)] = (unsigned short)ci;
+        count += __popc(m);
+    }
+    __syncwarp();
+    double best[5];
+    int bi[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { best[q] = INFINITY; bi[q] = 0x7fffffff; }
+    const double* wx = tp.wx + tm.wp_off;
+    const double* wy = tp.wy + tm.wp_off;
+    const int half = lane >> 4, j = lane & 15;
+    for (int it = 0; it < count; it += 2) {
+        const int my = it + half;
+        if (my < count) {
+            const int i = (int)list[my] * kChunk + j;
+            if (i < tm.n_wp) {
+                const double px = wx[i], py = wy[i];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const double dx = dsub(px, qx[q]), dy = dsub(py, qy[q]);
+                    const double d = dadd(dmul(dx, dx), dmul(dy, dy));
+                    if (d < best[q] || (d == best[q] && i < bi[q])) { best[q] = d; bi[q] = i; }
+                }
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double od = shfl_xor_d(best[q], m);
+            const int oi = __shfl_xor_sync(kFull, bi[q], m);
+            if (od < best[q] || (od == best[q] && oi < bi[q])) { best[q] = od; bi[q] = oi; }
+        }
+        out_idx[q] = bi[q];
+    }
+}
+
+// fp32 candidate search of all R rays of one car against the walls.  Level 1:
+// lane <-> boundary chunk, loop over rays, circle-vs-ray test; survivors are
+// appended to a work list.  Level 2: half-warp <-> (ray, chunk) item, lane <->
+// segment; a segment whose end points straddle the ray's line (with slack) and
+// lie ahead of the origin posts (t, segment) to the ray's shared-memory key
+// with atomicMin.
 template <int KIND>
+__device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, double oxd, double oyd,
+                                                     int slot0, int R, int lane, const CullView& cv) {
+    const float4* bch = tp.bchunk + tm.bchunk_off;
+    const float2* bpt = tp.bpt + 2 * (size_t)tm.wp_off;
+    const float ox = (float)(oxd - tm.org_x), oy = (float)(oyd - tm.org_y);
+    const int nb = tm.n_bchunk, nch = nb >> 1, N = tm.n_wp;
+    const unsigned lt = (1u << lane) - 1u;
+    const int half = lane >> 4, j = lane & 15;
+    constexpr int kRaysPerBatch = kListCap / 32;
+    for (int rb = 0; rb < R; rb += kRaysPerBatch) {
+        const int nr = min(kRaysPerBatch, R - rb);
+        for (int c0 = 0; c0 < nb; c0 += 32) {
+            // ---- level 1 ----
+            const int ci = c0 + lane;
+            float rx = 0.f, ry = 0.f, rr = -1.f;
+            bool near = false;
+            if (ci < nb) {
+                const float4 cc = bch[ci];
+                rx = cc.x - ox; ry = cc.y - oy; rr = cc.z;
+                // multi env readings are clamped to 50 (multi_track.py:8,26): farther chunks can not matter
+                near = (KIND == RK_ENV_SINGLE) || (rx * rx + ry * ry <= (50.01f + rr) * (50.01f + rr));
+            }
+            int count = 0;
+            for (int k = 0; k < nr; ++k) {
+                const float2 d = cv.dir32[slot0 + rb + k];
+                const float proj = rx * d.x + ry * d.y, perp = rx * d.y - ry * d.x;
+                bool keep = near && fabsf(perp) <= rr && proj >= -rr;
+                if (KIND == RK_ENV_MULTI) keep = keep && (proj - rr <= 50.01f);
+                const unsigned m = __ballot_sync(kFull, keep);
+                if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)((k << 10) | ci);
+                count += __popc(m);
+            }
+            __syncwarp();
+            // ---- level 2 ----
+            for (int it = 0; it < count; it += 2) {
+                const int my = it + half;
+                if (my < count) {
+                    const unsigned item = cv.list[my];
+                    const int k = item >> 10, cj = item & 1023;
+                    const int side = cj >= nch;
+                    const int seg = (cj - side * nch) * kChunk + j;
+                    if (seg < N) {
+                        const int i0 = side * N + seg;
+                        const float2 p = bpt[i0];
+                        const float2 q = bpt[side * N + (seg + 1 == N ? 0 : seg + 1)];
+                        const float2 d = cv.dir32[slot0 + rb + k];
+                        const float px = p.x - ox, py = p.y - oy, qx = q.x - ox, qy = q.y - oy;
+                        const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distance to the ray's line
+                        const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
+                                              (cp >= -kPerpSlack && cq <= kPerpSlack);
+                        if (straddle) {
+                            const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
+                            const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
+                            if (thi >= -kFrontSlack) {
+                                const float den = cq - cp;
+                                float t = (fabsf(den) > 1e-12f) ? (px * (qy - py) - py * (qx - px)) / den : tlo;
+                                t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
+                                atomicMin(&cv.ray_key[slot0 + rb + k],
+                                          ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)i0);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <int KIND, int QUERY>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e = blockIdx.x * kWarpsPerCta + warp;
     if (e >= p.E) return;
-    Scratch& S = reinterpret_cast<Scratch*>(smem_raw)[warp];
     const int A = p.A, R = p.R;
+    unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
+    Scratch& S = *reinterpret_cast<Scratch*>(wbase);
+    CullView cv;
+    static_assert(sizeof(Scratch) % 16 == 0, "dir64 must stay 16-byte aligned");
+    cv.dir64 = reinterpret_cast<double2*>(wbase + sizeof(Scratch));
+    cv.ray_key = reinterpret_cast<unsigned long long*>(cv.dir64 + A * R);
+    cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
+    cv.list = reinterpret_cast<unsigned short*>(cv.dir32 + A * R);
     const TrackPool& tp = p.trk;
     const TrackMeta tm = tp.meta[tp.env_to_track[e]];
     const double Nd = (double)tm.n_wp;
@@ -240,7 +427,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
 #pragma unroll
             for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[a][k]; qy[k + 1] = S.cy[a][k]; }
             int idx[5];
-            argmin_exact<5>(tp, tm, qx, qy, lane, idx);
+            if (QUERY == RK_QUERY_CULLED)
+                argmin_culled5(tp, tm, qx, qy, lane, cv.list, idx);
+            else
+                argmin_exact<5>(tp, tm, qx, qy, lane, idx);
             if (lane == a) {
                 pidx = idx[0];  // car.py:79
                 bool crashed = false;  // track.py:163-171
@@ -490,6 +680,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
     }
     __syncwarp();
     const int D = p.D;
+    if (QUERY == RK_QUERY_CULLED) {
+        const int nslot = A * R;
+        // ray directions: one lane per (car, ray) slot
+        for (int s0 = 0; s0 < nslot; s0 += 32) {
+            const int slot = s0 + lane;
+            if (slot < nslot) {
+                const int a = slot / R, r = slot - a * R;
+                double dsn, dcs;
+                sincos(dadd(S.ang[a], p.sensor_angles[r]), &dsn, &dcs);
+                cv.dir64[slot] = make_double2(dcs, dsn);
+                cv.dir32[slot] = make_float2((float)dcs, (float)dsn);
+                cv.ray_key[slot] = kNoKey;
+            }
+        }
+        __syncwarp();
+        for (int a = 0; a < A; ++a) raycast_walls_culled<KIND>(tp, tm, S.x[a], S.y[a], a * R, R, lane, cv);
+        // float64 re-evaluation of every winner + the other cars' edges, one lane per slot
+        const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
+        const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
+        const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
+        const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
+        for (int s0 = 0; s0 < nslot; s0 += 32) {
+            const int slot = s0 + lane;
+            const bool live = slot < nslot;
+            const int a = live ? slot / R : 0, r = live ? slot - a * R : 0;
+            const double ox = S.x[a], oy = S.y[a];
+            double v3x = 0.0, v3y = 1.0, wall = INFINITY;
+            bool redo = false;
+            if (live) {
+                const double2 d = cv.dir64[slot];
+                v3x = -d.y; v3y = d.x;  // track.py:178
+                const unsigned long long key = cv.ray_key[slot];
+                if (key != kNoKey) {
+                    const int i = (int)(key & 0xffffffffu);
+                    const double ax = v2x[i], ay = v2y[i];
+                    const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
+                    wall = ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y);
+                    redo = (wall == INFINITY);  // fp32 candidate rejected by the float64 test
+                }
+            }
+            // rare: re-scan that ray exactly with the whole warp
+            unsigned fb = __ballot_sync(kFull, redo);
+            while (fb) {
+                const int b = __ffs(fb) - 1;
+                fb &= fb - 1;
+                const int bs = s0 + b, ba = bs / R;
+                const double2 d = cv.dir64[bs];
+                double bx[kRayBlock], by[kRayBlock], bt[kRayBlock];
+#pragma unroll
+                for (int k = 0; k < kRayBlock; ++k) { bx[k] = -d.y; by[k] = d.x; bt[k] = INFINITY; }
+                raycast_walls_exact(tp, tm, S.x[ba], S.y[ba], bx, by, 1, lane, bt);
+                const double t = warp_min_d(bt[0]);
+                if (lane == b) wall = t;
+            }
+            if (live) {
+                double t = wall;
+                if (KIND == RK_ENV_MULTI) {
+                    for (int oc = 0; oc < A; ++oc) {  // multi_track.py:10-24
+                        const double ddx = dsub(S.x[oc], ox), ddy = dsub(S.y[oc], oy);
+                        if (sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5) continue;  // multi_track.py:13
+#pragma unroll
+                        for (int ed = 0; ed < 4; ++ed) {
+                            const double ex0 = S.cx[oc][ed], ey0 = S.cy[oc][ed];
+                            const double ax = dsub(S.cx[oc][(ed + 1) & 3], ex0), ay = dsub(S.cy[oc][(ed + 1) & 3], ey0);
+                            const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
+                            const double dotp = dadd(dmul(ax, v3x), dmul(ay, v3y));
+                            const double dv = dadd(dmul(v1x, v3x), dmul(v1y, v3y));
+                            const double adot = fabs(dotp);
+                            if (!(adot < 1e-10) && fabs(dv) <= adot * (1.0 + 1e-12)) {  // multi_track.py:35
+                                const double tt = ddiv(dsub(dmul(ax, v1y), dmul(ay, v1x)), dotp), ss = ddiv(dv, dotp);
+                                if (tt >= 0.0 && ss >= 0.0 && ss <= 1.0) t = fmin(t, tt);
+                            }
+                        }
+                    }
+                    t = fmin(t, kMaxRange);  // multi_track.py:8,26
+                } else if (t == INFINITY) {
+                    t = kMaxRange;  // track.py:196-197
+                }
+                obs[io_index(a) * D + r] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+            }
+        }
+    } else
     for (int a = 0; a < A; ++a) {
         const double ox = S.x[a], oy = S.y[a], oang = S.ang[a];
         float* orow = obs + io_index(a) * D;
@@ -566,13 +838,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
 }  // namespace
 
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
-    (void)query_mode;
     const int grid = (p.E + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t smem = kWarpsPerCta * sizeof(Scratch);
+    const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R);
+    using Kern = void (*)(const StepParams);
+    Kern k;
     if (env_kind == RK_ENV_SINGLE)
-        step_kernel<RK_ENV_SINGLE><<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
+        k = (query_mode == RK_QUERY_CULLED) ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED>
+                                            : step_kernel<RK_ENV_SINGLE, RK_QUERY_EXACT_F64>;
     else
-        step_kernel<RK_ENV_MULTI><<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
+        k = (query_mode == RK_QUERY_CULLED) ? step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED>
+                                            : step_kernel<RK_ENV_MULTI, RK_QUERY_EXACT_F64>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -333,16 +333,21 @@ def test_policy_act_matches_torch_agent(B, golden):
     ref_lp = (-((a - g['mu']) ** 2) / (2 * std * std) - np.float32(-0.3) - 0.5 * np.log(2 * np.pi)).sum(1)
     np.testing.assert_allclose(lp.cpu().numpy(), ref_lp, rtol=0, atol=1e-4)
     # noise statistics over a large batch: z = (a - mu)/std ~ N(0,1) where not clamped
+    # (log_std lowered to -2 so that the [-1, 1] clamp does not truncate the sample)
     big = obs.repeat(4096, 1)
     nb = big.shape[0]
     act = torch.zeros(nb, 2, device='cuda'); mu = torch.zeros(nb, 2, device='cuda')
-    B.policy_act(params, big, act, seed=2, counter=7, mean=mu)
-    z = ((act - mu) / float(std))[(act.abs() < 1).all(1)]
-    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1) < 0.03
+    quiet = params.clone()
+    quiet[5570:5572] = -2.0
+    B.policy_act(quiet, big, act, seed=2, counter=7, mean=mu)
+    z = (act - mu) / float(np.exp(-2.0))
+    assert float((act.abs() >= 1).float().mean()) < 1e-3
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1) < 0.02
+    assert abs(float((z[:, 0] * z[:, 1]).mean())) < 0.02   # the two action dims are independent
     act2 = torch.zeros_like(act)
-    B.policy_act(params, big, act2, seed=2, counter=7)
+    B.policy_act(quiet, big, act2, seed=2, counter=7)
     assert torch.equal(act, act2)                      # counter-based: reproducible
-    B.policy_act(params, big, act2, seed=2, counter=8)
+    B.policy_act(quiet, big, act2, seed=2, counter=8)
     assert not torch.equal(act, act2)
     # strided views: write car 1's action slice from car 1's obs slice of [E,A,*] tensors
     E = 128
