@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librk_b200.so')
+LIB_PATH = os.environ.get('RK_B200_LIB') or os.path.join(_HERE, 'librk_b200.so')  # env override: A/B kernel builds
 
 RK_ENV_SINGLE, RK_ENV_MULTI = 0, 1
 RK_AUTORESET_NEXT_STEP, RK_AUTORESET_SAME_STEP, RK_AUTORESET_DISABLED = 0, 1, 2

@@ -36,7 +36,7 @@ struct rk_env_s {
     int D = 0;
     PoolBuffers* pool = nullptr;
     EnvState st{};
-    double* sensor_angles = nullptr;
+    double* sensor_angles = nullptr;  // [3R]: angles, cos, sin
     std::vector<void*> owned;
     char err[512] = {0};
 };
@@ -110,14 +110,14 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
          dev_alloc(h, &h->st.fstep, C) || dev_alloc(h, &h->st.steps, (size_t)E) ||
          dev_alloc(h, &h->st.needs_reset, (size_t)E) || dev_alloc(h, &h->st.ep_return, (size_t)E) ||
          dev_alloc(h, &h->st.ep_length, (size_t)E) || dev_alloc(h, &h->st.reset_count, (size_t)E) ||
-         dev_alloc(h, &h->sensor_angles, (size_t)R);
+         dev_alloc(h, &h->sensor_angles, (size_t)3 * R);
     if (rc) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_create: %s", h->err[0] ? h->err : "cudaSetDevice failed");
         rk_destroy(h);
         return 1;
     }
     // np.linspace(-half, half, R): racing_env.py:45 (120 deg) / multi_racing_env.py:50 (180 deg)
-    std::vector<double> ang(R);
+    std::vector<double> ang(3 * R);
     const double half = single ? M_PI / 3 : M_PI / 2;
     const double start = -half, stop = half;
     if (R == 1) {
@@ -130,7 +130,11 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
         }
         ang[R - 1] = stop;
     }
-    cudaMemcpy(h->sensor_angles, ang.data(), R * sizeof(double), cudaMemcpyHostToDevice);
+    for (int k = 0; k < R; ++k) {
+        ang[R + k] = cos(ang[k]);
+        ang[2 * R + k] = sin(ang[k]);
+    }
+    cudaMemcpy(h->sensor_angles, ang.data(), 3 * R * sizeof(double), cudaMemcpyHostToDevice);
     *out = h;
     return 0;
 }
@@ -256,6 +260,8 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
     p.trk = pool_view(h->pool);
     p.st = h->st;
     p.sensor_angles = h->sensor_angles;
+    p.sensor_cos = h->sensor_angles + h->cfg.num_sensors;
+    p.sensor_sin = h->sensor_angles + 2 * h->cfg.num_sensors;
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
     p.autoreset = h->cfg.autoreset_mode;
     p.max_steps = h->cfg.max_episode_steps;

@@ -1,4 +1,4 @@
-// The fused environment step: one warp per environment.
+// The fused environment step.
 //
 // Replaces, in one launch for E environments (reference paths relative to its
 // root): Car.update (environment/car.py:45-80), Track.closest_waypoint_idx /
@@ -10,12 +10,20 @@
 // (environment/multi_racing_env.py:48-268) and gymnasium's NEXT_STEP auto-reset
 // plus RecordEpisodeStatistics (call sites agent/ppo.py:70,88,114-130).
 //
-// Arithmetic contract: the car state and everything that decides a discrete
+// Thread mapping.  A warp owns EPW = 32/A consecutive environments.  In the
+// scalar phases (dynamics, wall test, SAT, reward, termination, placement,
+// reset, non-ray observation slots) every lane is ONE CAR (lane = g*A + a), so
+// those phases run at full warp width.  For the two geometric queries (waypoint
+// argmin, raycast) the warp walks over its environments and all 32 lanes
+// cooperate on one query set, exchanging data through shared memory and
+// reducing with warp shuffles.  No block-level barrier is used.
+//
+// Arithmetic contract.  The car state and everything that decides a discrete
 // event (waypoint argmin, wall test, SAT, checkpoints, finish, placement) is
 // float64 in the reference's operation order with round-to-nearest intrinsics
 // (no FMA contraction), so those events are bit-comparable with the reference.
-// Lane a < A owns car a's scalars; the whole warp cooperates on the argmin and
-// the raycast, reducing with warp shuffles.
+// RK_QUERY_CULLED finds argmin / ray candidates in fp32 over bounding-circle
+// chunks and re-evaluates every winner in float64 with the reference's formula.
 #include <math.h>
 #include <stdio.h>
 
@@ -43,44 +51,42 @@ __device__ __forceinline__ double warp_min_d(double v) {
     for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
     return v;
 }
-
-constexpr int kListCapBytes = 512 * 2;
-// per-warp scratch in dynamic shared memory
-struct Scratch {
-    double x[RK_MAX_AGENTS], y[RK_MAX_AGENTS], c[RK_MAX_AGENTS], s[RK_MAX_AGENTS];
-    double ang[RK_MAX_AGENTS], vx[RK_MAX_AGENTS], vy[RK_MAX_AGENTS];
-    double cx[RK_MAX_AGENTS][4], cy[RK_MAX_AGENTS][4];
-};
-
-__host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
-    return (sizeof(Scratch) + (size_t)A * R * (8 + 16 + 8) + kListCapBytes + 15) / 16 * 16;
-}
-
-// car.py:26-43: corners FL, FR, RR, RL = R(angle) * (+-2, +-1) + position
-__device__ __forceinline__ void corners(double x, double y, double c, double s, double* cx, double* cy) {
-    const double lx[4] = {2.0, 2.0, -2.0, -2.0}, ly[4] = {1.0, -1.0, -1.0, 1.0};
+__device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        cx[k] = dadd(dadd(dmul(c, lx[k]), dmul(-s, ly[k])), x);
-        cy[k] = dadd(dadd(dmul(s, lx[k]), dmul(c, ly[k])), y);
-    }
+    for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, m));
+    return v;
+}
+
+constexpr int kListCap = 512;  // (ray, chunk) work items per warp batch
+
+// Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
+// one column per lane: conflict free) and the scratch of the culled queries.
+struct CarS {
+    double x[32], y[32], c[32], s[32], vx[32], vy[32];
+    double cx[4][32], cy[4][32];  // corners FL, FR, RR, RL (car.py:31-36)
+};
+struct CullView {
+    double2* dir64;               // [A*R] (cos, sin) of each ray's world angle, current environment
+    unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment) of the best wall candidate
+    float2* dir32;                // [A*R]
+    unsigned short* list;         // [kListCap]
+};
+__host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
+    return (sizeof(CarS) + (size_t)A * R * (16 + 8 + 8) + kListCap * 2 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
-// Waypoint argmin for NQ query points (track.py:150-152), exact float64 brute
-// force: every lane scans waypoints lane, lane+32, ...; ties resolve to the
-// lowest index, as numpy's argmin does.
+// Exact queries (RK_QUERY_EXACT_F64): float64 brute force over the whole table.
 // ---------------------------------------------------------------------------
+// Waypoint argmin for NQ points (track.py:150-152): lanes stride over the
+// waypoints; ties resolve to the lowest index, as numpy's argmin does.
 template <int NQ>
 __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMeta& tm, const double* qx,
                                              const double* qy, int lane, int* out_idx) {
     double best[NQ];
     int bi[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        best[q] = INFINITY;
-        bi[q] = 0x7fffffff;
-    }
+    for (int q = 0; q < NQ; ++q) { best[q] = INFINITY; bi[q] = 0x7fffffff; }
     const double* wx = tp.wx + tm.wp_off;
     const double* wy = tp.wy + tm.wp_off;
     for (int i = lane; i < tm.n_wp; i += 32) {
@@ -89,10 +95,7 @@ __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMet
         for (int q = 0; q < NQ; ++q) {
             const double dx = dsub(px, qx[q]), dy = dsub(py, qy[q]);
             const double d = dadd(dmul(dx, dx), dmul(dy, dy));
-            if (d < best[q]) {
-                best[q] = d;
-                bi[q] = i;
-            }
+            if (d < best[q]) { best[q] = d; bi[q] = i; }
         }
     }
 #pragma unroll
@@ -101,38 +104,34 @@ __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMet
         for (int m = 16; m > 0; m >>= 1) {
             const double od = shfl_xor_d(best[q], m);
             const int oi = __shfl_xor_sync(kFull, bi[q], m);
-            if (od < best[q] || (od == best[q] && oi < bi[q])) {
-                best[q] = od;
-                bi[q] = oi;
-            }
+            if (od < best[q] || (od == best[q] && oi < bi[q])) { best[q] = od; bi[q] = oi; }
         }
         out_idx[q] = bi[q];
     }
 }
 
-// ---------------------------------------------------------------------------
 // One ray against one segment, the reference's formula (track.py:176-195 /
 // multi_track.py:28-44).  Returns t if hit, +inf otherwise.  The divisions are
-// only evaluated when the sign/magnitude pre-test (which can not reject a true
-// hit) passes.
-// ---------------------------------------------------------------------------
+// only evaluated when a magnitude pre-test (which can not reject a true hit:
+// s <= 1 implies |dv| <= |dotp| up to one rounding) passes.
 __device__ __forceinline__ double ray_segment(double v1x, double v1y, double v2x, double v2y, double cross,
-                                              double v3x, double v3y) {
+                                              double v3x, double v3y, double min_abs_dot) {
     const double dotp = dadd(dmul(v2x, v3x), dmul(v2y, v3y));
     const double dv = dadd(dmul(v1x, v3x), dmul(v1y, v3y));
     const double adot = fabs(dotp);
-    if (adot > 1e-10 && fabs(dv) <= adot * (1.0 + 1e-12)) {
+    if (adot >= min_abs_dot && fabs(dv) <= adot * (1.0 + 1e-12)) {
         const double t = ddiv(cross, dotp), s = ddiv(dv, dotp);
         if (t >= 0.0 && s >= 0.0 && s <= 1.0) return t;
     }
     return INFINITY;
 }
+// track.py:182 keeps |dotp| > 1e-10; multi_track.py:35 drops |dotp| < 1e-10
+constexpr double kWallMinDot = 1.0000000000000002e-10;  // the double after 1e-10: ">" written as ">="
+constexpr double kEdgeMinDot = 1e-10;
 
 constexpr int kRayBlock = 8;  // rays whose running minima are kept in registers at once
 
-// All R rays of one car against all walls of its track, exact float64 brute
-// force; lanes stride over the 2N segments, then shuffle-min.  ray_out[r] for
-// r in [r0, r0 + kRayBlock) is valid on every lane on return.
+// nr <= kRayBlock rays of one origin against all walls of a track, exact.
 __device__ __forceinline__ void raycast_walls_exact(const TrackPool& tp, const TrackMeta& tm, double ox, double oy,
                                                     const double* v3x, const double* v3y, int nr, int lane,
                                                     double* best) {
@@ -147,42 +146,45 @@ __device__ __forceinline__ void raycast_walls_exact(const TrackPool& tp, const T
         const double cross = dsub(dmul(ax, v1y), dmul(ay, v1x));
 #pragma unroll
         for (int k = 0; k < kRayBlock; ++k)
-            if (k < nr) best[k] = fmin(best[k], ray_segment(v1x, v1y, ax, ay, cross, v3x[k], v3y[k]));
+            if (k < nr) best[k] = fmin(best[k], ray_segment(v1x, v1y, ax, ay, cross, v3x[k], v3y[k], kWallMinDot));
     }
 }
 
+// The four edges of every other car (multi_track.py:10-24), exact, for ONE ray.
+__device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int A, double ox, double oy,
+                                                    double v3x, double v3y) {
+    double t = INFINITY;
+    for (int oc = 0; oc < A; ++oc) {
+        const int l = base + oc;
+        const double ddx = dsub(S.x[l], ox), ddy = dsub(S.y[l], oy);
+        if (sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5) continue;  // multi_track.py:13 (the car itself)
+#pragma unroll
+        for (int ed = 0; ed < 4; ++ed) {
+            const double ex0 = S.cx[ed][l], ey0 = S.cy[ed][l];
+            const double ax = dsub(S.cx[(ed + 1) & 3][l], ex0), ay = dsub(S.cy[(ed + 1) & 3][l], ey0);
+            const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
+            t = fmin(t, ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kEdgeMinDot));
+        }
+    }
+    return t;
+}
 
-// ===========================================================================
-// Culled query path (RK_QUERY_CULLED).  Candidates are found in fp32 on tables
-// stored relative to the track's bbox centre, over bounding circles of kChunk
-// consecutive waypoints / boundary segments (they are arc-length ordered, so a
-// chunk is spatially compact); every winner is then re-evaluated in float64
-// with the reference's formula, so results equal the exact path's.  Culling
-// never removes a possible winner: all bounds carry explicit slack for the
-// fp32 rounding of tables, query and arithmetic.
-// ===========================================================================
-constexpr int kListCap = 512;            // work items per warp batch
-constexpr float kHalfDiag = 2.2361f;     // >= sqrt(2^2 + 1^2): car corner distance from its centre
-constexpr float kPerpSlack = 3e-4f;      // fp32 error bound of a ray-line distance (|p| <= ~200)
+// ---------------------------------------------------------------------------
+// Culled queries (RK_QUERY_CULLED).  Tables are fp32 relative to the track's
+// bbox centre; kChunk consecutive waypoints / boundary segments (arc-length
+// ordered, hence spatially compact) share a bounding circle.  Culling never
+// removes a possible winner: every bound carries explicit slack for the fp32
+// rounding of tables, query and arithmetic, and winners are re-evaluated in
+// float64 (with an exact re-scan if float64 rejects the fp32 candidate).
+// ---------------------------------------------------------------------------
+constexpr float kHalfDiag = 2.2361f;   // >= sqrt(2^2 + 1^2): corner distance from the car centre
+constexpr float kPerpSlack = 3e-4f;    // bound on the fp32 error of a point-to-ray-line distance (|p| <~ 250)
 constexpr float kFrontSlack = 1e-3f;
 constexpr unsigned long long kNoKey = ~0ull;
 
-__device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, m));
-    return v;
-}
-
-struct CullView {
-    unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment index) of the best wall candidate
-    double2* dir64;               // [A*R] (cos, sin) of the ray's world angle
-    float2* dir32;                // [A*R]
-    unsigned short* list;         // [kListCap]
-};
-
-// Waypoint argmin for the car centre + 4 corners (track.py:150-152): one
-// bounding-circle pass picks the chunks that can hold the nearest waypoint of
-// ANY of the five points, then those chunks are scanned exactly in float64.
+// Waypoint argmin for the car centre + 4 corners: one bounding-circle pass picks
+// the chunks that can hold the nearest waypoint of ANY of the five points, then
+// those chunks are scanned exactly in float64 (half a warp per chunk).
 __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackMeta& tm, const double* qx,
                                                const double* qy, int lane, unsigned short* list, int* out_idx) {
     const float4* wch = tp.wchunk + tm.wchunk_off;
@@ -197,8 +199,9 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
             U = fminf(U, sqrtf(dx * dx + dy * dy) + cc.z);
         }
     }
-    // every corner is within kHalfDiag of the centre: a chunk whose nearest possible
-    // waypoint is farther than U + 2*kHalfDiag from the centre can not win for any of them
+    // the nearest waypoint of the centre is within U; every corner is within kHalfDiag of
+    // the centre, so a chunk whose closest possible waypoint is farther than
+    // U + 2*kHalfDiag from the centre can not hold the argmin of any of the five points
     const float thr = warp_min_f(U) + 2.f * kHalfDiag + 2e-2f;
     int count = 0;
     const unsigned lt = (1u << lane) - 1u;
@@ -250,12 +253,11 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     }
 }
 
-// fp32 candidate search of all R rays of one car against the walls.  Level 1:
-// lane <-> boundary chunk, loop over rays, circle-vs-ray test; survivors are
-// appended to a work list.  Level 2: half-warp <-> (ray, chunk) item, lane <->
-// segment; a segment whose end points straddle the ray's line (with slack) and
-// lie ahead of the origin posts (t, segment) to the ray's shared-memory key
-// with atomicMin.
+// fp32 candidate search of the R rays of one car against the walls.  Level 1:
+// lane <-> boundary chunk, loop over rays, circle-vs-ray test; survivors go to a
+// work list.  Level 2: half-warp <-> (ray, chunk) item, lane <-> segment; a
+// segment whose end points straddle the ray's line (with slack) and which is
+// not entirely behind the origin posts (t, segment) to the ray's key.
 template <int KIND>
 __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, double oxd, double oyd,
                                                      int slot0, int R, int lane, const CullView& cv) {
@@ -268,6 +270,8 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     constexpr int kRaysPerBatch = kListCap / 32;
     for (int rb = 0; rb < R; rb += kRaysPerBatch) {
         const int nr = min(kRaysPerBatch, R - rb);
+        const float2* dirs = cv.dir32 + slot0 + rb;
+        unsigned long long* keys = cv.ray_key + slot0 + rb;
         for (int c0 = 0; c0 < nb; c0 += 32) {
             // ---- level 1 ----
             const int ci = c0 + lane;
@@ -280,14 +284,16 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 near = (KIND == RK_ENV_SINGLE) || (rx * rx + ry * ry <= (50.01f + rr) * (50.01f + rr));
             }
             int count = 0;
-            for (int k = 0; k < nr; ++k) {
-                const float2 d = cv.dir32[slot0 + rb + k];
-                const float proj = rx * d.x + ry * d.y, perp = rx * d.y - ry * d.x;
-                bool keep = near && fabsf(perp) <= rr && proj >= -rr;
-                if (KIND == RK_ENV_MULTI) keep = keep && (proj - rr <= 50.01f);
-                const unsigned m = __ballot_sync(kFull, keep);
-                if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)((k << 10) | ci);
-                count += __popc(m);
+            if (__any_sync(kFull, near)) {
+                for (int k = 0; k < nr; ++k) {
+                    const float2 d = dirs[k];
+                    const float proj = rx * d.x + ry * d.y, perp = rx * d.y - ry * d.x;
+                    bool keep = near && fabsf(perp) <= rr && proj >= -rr;
+                    if (KIND == RK_ENV_MULTI) keep = keep && (proj - rr <= 50.01f);
+                    const unsigned m = __ballot_sync(kFull, keep);
+                    if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)((k << 10) | ci);
+                    count += __popc(m);
+                }
             }
             __syncwarp();
             // ---- level 2 ----
@@ -299,12 +305,12 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                     const int side = cj >= nch;
                     const int seg = (cj - side * nch) * kChunk + j;
                     if (seg < N) {
-                        const int i0 = side * N + seg;
-                        const float2 p = bpt[i0];
-                        const float2 q = bpt[side * N + (seg + 1 == N ? 0 : seg + 1)];
-                        const float2 d = cv.dir32[slot0 + rb + k];
+                        const float2* row = bpt + side * N;
+                        const float2 p = row[seg];
+                        const float2 q = row[seg + 1 == N ? 0 : seg + 1];
+                        const float2 d = dirs[k];
                         const float px = p.x - ox, py = p.y - oy, qx = q.x - ox, qy = q.y - oy;
-                        const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distance to the ray's line
+                        const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
                         const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
                                               (cp >= -kPerpSlack && cq <= kPerpSlack);
                         if (straddle) {
@@ -314,8 +320,8 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                                 const float den = cq - cp;
                                 float t = (fabsf(den) > 1e-12f) ? (px * (qy - py) - py * (qx - px)) / den : tlo;
                                 t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
-                                atomicMin(&cv.ray_key[slot0 + rb + k],
-                                          ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)i0);
+                                atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) |
+                                                        (unsigned)(side * N + seg));
                             }
                         }
                     }
@@ -326,60 +332,88 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     }
 }
 
+// Philox Fisher-Yates over the A car ids of an environment; returns the grid
+// slot of car `a` (multi_racing_env.py:127-133).  Every lane of the environment
+// draws the same numbers, so no communication is needed.
+__device__ __forceinline__ int philox_start_slot(uint64_t seed, int e, uint32_t reset_count, int A, int a) {
+    uint32_t perm = 0x76543210u;  // nibble k = car id at grid position k
+    for (int i = A - 1; i > 0; --i) {
+        uint32_t ctr[4] = {(uint32_t)e, reset_count, (uint32_t)i, 0x736c6f74u};
+        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const int j = (int)(((uint64_t)ctr[0] * (uint64_t)(i + 1)) >> 32);
+        const uint32_t vi = (perm >> (4 * i)) & 15u, vj = (perm >> (4 * j)) & 15u;
+        perm &= ~((15u << (4 * i)) | (15u << (4 * j)));
+        perm |= (vj << (4 * i)) | (vi << (4 * j));
+    }
+    int slot = 0;
+    for (int k = 0; k < A; ++k)
+        if (((perm >> (4 * k)) & 15u) == (uint32_t)a) slot = k;
+    return slot;
+}
+
 // ---------------------------------------------------------------------------
+#ifndef RK_STEP_MIN_BLOCKS
+#define RK_STEP_MIN_BLOCKS 8
+#endif
 template <int KIND, int QUERY>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kWarpsPerCta + warp;
-    if (e >= p.E) return;
-    const int A = p.A, R = p.R;
+    const int A = p.A, R = p.R, D = p.D;
+    const int epw = 32 / A;                                       // environments per warp
+    const int e_base = (blockIdx.x * kWarpsPerCta + warp) * epw;
+    if (e_base >= p.E) return;
+    const int n_env = min(epw, p.E - e_base);
     unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
-    Scratch& S = *reinterpret_cast<Scratch*>(wbase);
+    CarS& S = *reinterpret_cast<CarS*>(wbase);
     CullView cv;
-    static_assert(sizeof(Scratch) % 16 == 0, "dir64 must stay 16-byte aligned");
-    cv.dir64 = reinterpret_cast<double2*>(wbase + sizeof(Scratch));
+    static_assert(sizeof(CarS) % 16 == 0, "dir64 must stay 16-byte aligned");
+    cv.dir64 = reinterpret_cast<double2*>(wbase + sizeof(CarS));
     cv.ray_key = reinterpret_cast<unsigned long long*>(cv.dir64 + A * R);
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(cv.dir32 + A * R);
     const TrackPool& tp = p.trk;
-    const TrackMeta tm = tp.meta[tp.env_to_track[e]];
-    const double Nd = (double)tm.n_wp;
-    const bool is_car = lane < A;
-    const int c = e * A + (is_car ? lane : 0);  // state index
-    // index of car (e, a) in the caller's per-car arrays
-    const bool agent_major = p.io.layout == RK_LAYOUT_AGENT_MAJOR;
-    auto io_index = [&](int a) -> size_t { return agent_major ? (size_t)a * p.E + e : (size_t)e * A + a; };
-    const size_t ci = io_index(is_car ? lane : 0);
 
-    // ---- which of {step, reset, observe} applies to this environment -------
-    bool stepping = (p.mode == 0);
+    // ---- lane = one car -------------------------------------------------------
+    const int g = lane / A, a = lane - g * A;     // environment within the warp, car within the environment
+    const bool is_car = g < n_env;
+    const int e = e_base + (is_car ? g : 0);
+    const int base = g * A;                       // first lane of this car's environment
+    const bool lead = is_car && a == 0;           // writes the per-environment outputs
+    const int c = e * A + a;                      // state index
+    const bool agent_major = p.io.layout == RK_LAYOUT_AGENT_MAJOR;
+    const size_t ci = agent_major ? (size_t)a * p.E + e : (size_t)c;  // index in the caller's per-car arrays
+    const int tid = tp.env_to_track[e];
+    const TrackMeta* tmp = tp.meta + tid;
+    const int n_wp = tmp->n_wp;
+    const double Nd = (double)n_wp;
+
+    // which of {step, reset, observe} applies to this car's environment
+    bool stepping = is_car && (p.mode == 0);
     bool resetting = false;
-    if (p.mode == 0 && p.autoreset == RK_AUTORESET_NEXT_STEP && p.st.needs_reset[e]) {
+    if (is_car && p.mode == 0 && p.autoreset == RK_AUTORESET_NEXT_STEP && p.st.needs_reset[e]) {
         stepping = false;  // the action is ignored (gymnasium NEXT_STEP)
         resetting = true;
     }
-    if (p.mode == 1) resetting = (p.reset_mask == nullptr) || (p.reset_mask[e] != 0);
+    if (is_car && p.mode == 1) resetting = (p.reset_mask == nullptr) || (p.reset_mask[e] != 0);
 
-    // ---- load car state ------------------------------------------------------
     double x = 0, y = 0, ang = 0, vx = 0, vy = 0;
     float last_steer = 0.f;
-    int pidx = 0, lpidx = 0, flags = 0, fstep = 0;
+    int pidx = 0, lpidx = 0, flags = 0, fstep = 0, steps = 0;
     if (is_car) {
         x = p.st.x[c]; y = p.st.y[c]; ang = p.st.ang[c]; vx = p.st.vx[c]; vy = p.st.vy[c];
         last_steer = p.st.last_steer[c];
         pidx = p.st.pidx[c]; lpidx = p.st.lpidx[c]; flags = p.st.flags[c]; fstep = p.st.fstep[c];
+        steps = p.st.steps[e];
     }
-    int steps = p.st.steps[e];
-    double reward = 0.0, delta = 0.0;
+    double reward = 0.0, delta = 0.0, cs = 1.0, sn = 0.0;
     int placement = 0;
     bool terminated = false, truncated = false;
 
-    if (stepping) {
-        // ---- D: vehicle dynamics (car.py:45-80), one lane per car -------------
-        const bool moving = is_car && !(flags & F_CRASHED);  // car.py:51-52
-        double cs = 1.0, sn = 0.0;
-        if (is_car) {
+    if (p.mode == 0) {
+        // ---- D: vehicle dynamics (car.py:45-80) ---------------------------------
+        const bool moving = stepping && !(flags & F_CRASHED);  // car.py:51-52
+        if (stepping) {
             const float a0 = p.io.actions[2 * ci], a1 = p.io.actions[2 * ci + 1];
             const float steer_f = fminf(fmaxf(a0, -1.f), 1.f);  // racing_env.py:106
             float thr_f;
@@ -395,11 +429,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
                 if (na != 0.0) { if (na < 0.0) na = dadd(na, kTwoPi); } else na = 0.0;
                 ang = na;
                 sincos(ang, &sn, &cs);
-                double vf = dadd(dmul(vx, cs), dmul(vy, sn));          // car.py:59
-                double vl = dadd(dmul(vx, -sn), dmul(vy, cs));         // car.py:60
+                double vf = dadd(dmul(vx, cs), dmul(vy, sn));            // car.py:59
+                double vl = dadd(dmul(vx, -sn), dmul(vy, cs));           // car.py:60
                 vf = dmul(dadd(vf, dmul(dmul(thr, 10.0), kDt)), 0.985);  // car.py:61-62
-                vl = dmul(dmul(vl, 0.85), 0.9);                        // car.py:63
-                vx = dsub(dmul(vf, cs), dmul(vl, sn));                 // car.py:66-67
+                vl = dmul(dmul(vl, 0.85), 0.9);                          // car.py:63
+                vx = dsub(dmul(vf, cs), dmul(vl, sn));                   // car.py:66-67
                 vy = dadd(dmul(vf, sn), dmul(vl, cs));
                 const double speed = sqrt(dadd(dmul(vx, vx), dmul(vy, vy)));  // car.py:70
                 if (speed > kMaxSpeed) {
@@ -409,87 +443,90 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
                 }
                 x = dadd(x, dmul(vx, kDt));  // car.py:77-78
                 y = dadd(y, dmul(vy, kDt));
-            } else {
-                sincos(ang, &sn, &cs);
             }
-            S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn;
-            corners(x, y, cs, sn, S.cx[lane], S.cy[lane]);
+        }
+        if (!moving) sincos(ang, &sn, &cs);
+        // publish pose and corners (car.py:26-43) for the cooperative phases
+        S.x[lane] = x; S.y[lane] = y;
+        {
+            const double lx[4] = {2.0, 2.0, -2.0, -2.0}, ly[4] = {1.0, -1.0, -1.0, 1.0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                S.cx[k][lane] = dadd(dadd(dmul(cs, lx[k]), dmul(-sn, ly[k])), x);
+                S.cy[k][lane] = dadd(dadd(dmul(sn, lx[k]), dmul(cs, ly[k])), y);
+            }
         }
         __syncwarp();
 
-        // ---- W + C: progress index and wall test for every moving car ---------
+        // ---- W: closest waypoint of the centre and the 4 corners, one car at a time,
+        //         all lanes cooperating (track.py:150-152) ---------------------------
+        int cidx1 = 0, cidx2 = 0, cidx3 = 0, cidx4 = 0;
         unsigned todo = __ballot_sync(kFull, moving);
         while (todo) {
-            const int a = __ffs(todo) - 1;
+            const int l = __ffs(todo) - 1;
             todo &= todo - 1;
+            const TrackMeta tm = tp.meta[__shfl_sync(kFull, tid, l)];
             double qx[5], qy[5];
-            qx[0] = S.x[a]; qy[0] = S.y[a];
+            qx[0] = S.x[l]; qy[0] = S.y[l];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[a][k]; qy[k + 1] = S.cy[a][k]; }
+            for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[k][l]; qy[k + 1] = S.cy[k][l]; }
             int idx[5];
             if (QUERY == RK_QUERY_CULLED)
                 argmin_culled5(tp, tm, qx, qy, lane, cv.list, idx);
             else
                 argmin_exact<5>(tp, tm, qx, qy, lane, idx);
-            if (lane == a) {
-                pidx = idx[0];  // car.py:79
-                bool crashed = false;  // track.py:163-171
+            if (lane == l) { pidx = idx[0]; cidx1 = idx[1]; cidx2 = idx[2]; cidx3 = idx[3]; cidx4 = idx[4]; }  // car.py:79
+        }
+        // ---- C: wall test of the 4 corners (track.py:163-171), every car in parallel
+        if (moving) {
+            const int off = tmp->wp_off;
+            const double width = tmp->width;
+            const int cidx[4] = {cidx1, cidx2, cidx3, cidx4};
+            bool crashed = false;
 #pragma unroll
-                for (int k = 1; k < 5; ++k) {
-                    const int i = tm.wp_off + idx[k];
-                    const double dist = fabs(dadd(dmul(dsub(qx[k], tp.wx[i]), tp.nx[i]),
-                                                  dmul(dsub(qy[k], tp.wy[i]), tp.ny[i])));
-                    crashed |= dist > tm.width;
-                }
-                if (crashed) flags |= F_CRASHED;
+            for (int k = 0; k < 4; ++k) {
+                const int i = off + cidx[k];
+                const double dist = fabs(dadd(dmul(dsub(S.cx[k][lane], tp.wx[i]), tp.nx[i]),
+                                              dmul(dsub(S.cy[k][lane], tp.wy[i]), tp.ny[i])));
+                crashed |= dist > width;
             }
+            if (crashed) flags |= F_CRASHED;
         }
 
-        // ---- X: car-car collisions (multi_racing_env.py:222-231) --------------
+        // ---- X: car-car collisions (multi_racing_env.py:222-231): every car tests
+        //         itself against every other car of its environment ------------------
         double touching = 0.0;
-        if (KIND == RK_ENV_MULTI && A > 1) {
-            // lane pr < A*(A-1)/2 tests pair pr; every lane then applies its own hits
-            int pi = 0, pj = 0;
-            {
-                int k = lane, i = 0;
-                while (i < A - 1 && k >= A - 1 - i) { k -= A - 1 - i; ++i; }
-                pi = i; pj = i + 1 + k;
-            }
-            bool hit = false;
-            if (pi < A - 1 && pj < A) {
-                hit = true;  // multi_car.py:16-43: 4 axes, strict separation test
+        if (KIND == RK_ENV_MULTI && A > 1 && stepping) {
+            for (int o = 0; o < A; ++o) {
+                if (o == a) continue;
+                const int li = base + min(a, o), lj = base + max(a, o);  // the reference's (i, j), i < j
+                bool hit = true;  // multi_car.py:16-43: 4 axes, strict separation test
 #pragma unroll
                 for (int ax = 0; ax < 4; ++ax) {
-                    const int o = (ax < 2) ? pi : pj, k0 = ax & 1;
-                    const double ex = dsub(S.cx[o][k0 + 1], S.cx[o][k0]), ey = dsub(S.cy[o][k0 + 1], S.cy[o][k0]);
+                    const int lo = (ax < 2) ? li : lj, k0 = ax & 1;
+                    const double ex = dsub(S.cx[k0 + 1][lo], S.cx[k0][lo]), ey = dsub(S.cy[k0 + 1][lo], S.cy[k0][lo]);
                     const double nx = -ey, ny = ex;
                     double amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const double pa = dadd(dmul(S.cx[pi][k], nx), dmul(S.cy[pi][k], ny));
-                        const double pb = dadd(dmul(S.cx[pj][k], nx), dmul(S.cy[pj][k], ny));
+                        const double pa = dadd(dmul(S.cx[k][li], nx), dmul(S.cy[k][li], ny));
+                        const double pb = dadd(dmul(S.cx[k][lj], nx), dmul(S.cy[k][lj], ny));
                         amin = fmin(amin, pa); amax = fmax(amax, pa);
                         bmin = fmin(bmin, pb); bmax = fmax(bmax, pb);
                     }
                     if (amax < bmin || bmax < amin) hit = false;
                 }
-            }
-            const unsigned hits = __ballot_sync(kFull, hit);
-            if (is_car && hits) {  // pairs in (i, j) order, as the reference's nested loops
-                int pr = 0;
-                for (int i = 0; i < A - 1; ++i)
-                    for (int j = i + 1; j < A; ++j, ++pr)
-                        if (((hits >> pr) & 1u) && (i == lane || j == lane)) {
-                            vx = dmul(vx, 0.92);
-                            vy = dmul(vy, 0.92);
-                            touching = dadd(touching, -5.0);
-                        }
+                if (hit) {
+                    vx = dmul(vx, 0.92);
+                    vy = dmul(vy, 0.92);
+                    touching = dadd(touching, -5.0);
+                }
             }
         }
-        steps += 1;  // racing_env.py:110 / multi_racing_env.py:233
+        if (stepping) steps += 1;  // racing_env.py:110 / multi_racing_env.py:233
 
-        // ---- reward and episode logic, one lane per car ------------------------
-        if (is_car) {
+        // ---- reward and episode logic ------------------------------------------------
+        if (stepping) {
             const double prog = ddiv((double)pidx, Nd), lprog = ddiv((double)lpidx, Nd);  // track.py:161
             delta = dsub(prog, lprog);  // racing_env.py:112-116 / multi:159-163
             if (lprog > 0.9 && prog < 0.1) delta = dadd(dsub(1.0, lprog), prog);
@@ -526,18 +563,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
                 reward = dadd(reward, touching);  // multi:240
             }
         }
-        const unsigned car_mask = (A >= 32) ? kFull : ((1u << A) - 1u);
-        const unsigned fin_b = __ballot_sync(kFull, is_car && (flags & F_FINISHED));
-        const unsigned crash_b = __ballot_sync(kFull, is_car && (flags & F_CRASHED));
-        if (KIND == RK_ENV_SINGLE)
-            terminated = (fin_b | crash_b) & 1u;  // racing_env.py:161
-        else
-            terminated = (fin_b != 0u) || ((crash_b & car_mask) == car_mask);  // multi:247-249
-        truncated = steps >= p.max_steps;
-        if (KIND == RK_ENV_MULTI && (terminated || truncated)) {
-            // place() multi:198-211: descending (score, idx); ties go to the higher index
+        // environment-level termination from the flags of its A cars
+        const unsigned grp_mask = ((A >= 32) ? kFull : ((1u << A) - 1u));
+        const unsigned fin_b = (__ballot_sync(kFull, stepping && (flags & F_FINISHED)) >> base) & grp_mask;
+        const unsigned crash_b = (__ballot_sync(kFull, stepping && (flags & F_CRASHED)) >> base) & grp_mask;
+        if (stepping) {
+            if (KIND == RK_ENV_SINGLE)
+                terminated = (fin_b | crash_b) != 0u;  // racing_env.py:161
+            else
+                terminated = (fin_b != 0u) || (crash_b == grp_mask);  // multi:247-249
+            truncated = steps >= p.max_steps;
+        }
+        if (KIND == RK_ENV_MULTI) {
+            // place() multi:198-211: descending (score, idx); exact ties go to the higher index
             double score = 0.0;
-            if (is_car) {
+            if (stepping) {
                 const double prog = ddiv((double)pidx, Nd);
                 score = dadd(dadd(dadd((flags & F_FINISHED) ? 10000.0 : 0.0, dmul(prog, 100.0)),
                                   (flags & F_CRASHED) ? 0.0 : 10.0),
@@ -545,21 +585,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
             }
             int ahead = 0;
             for (int o = 0; o < A; ++o) {
-                const double so = __shfl_sync(kFull, score, o);
-                if (is_car && o != lane && (so > score || (so == score && o > lane))) ++ahead;
+                const double so = __shfl_sync(kFull, score, (base + o) & 31);
+                if (o != a && (so > score || (so == score && o > a))) ++ahead;
             }
-            placement = ahead + 1;
-            if (is_car && placement == 1) reward = dadd(reward, 250.0);  // multi:256-257
+            if (stepping && (terminated || truncated)) {
+                placement = ahead + 1;
+                if (placement == 1) reward = dadd(reward, 250.0);  // multi:256-257
+            }
         }
-        if (is_car) lpidx = pidx;  // racing_env.py:165 / multi:266-267
+        if (stepping) lpidx = pidx;  // racing_env.py:165 / multi:266-267
     }
 
-    // ---- episode statistics (RecordEpisodeStatistics) -------------------------
+    // ---- episode statistics (RecordEpisodeStatistics) -----------------------------
     const bool ended = terminated || truncated;
-    if (stepping) {
-        const double r0 = __shfl_sync(kFull, reward, 0);
-        if (lane == 0) {
-            const double er = dadd(p.st.ep_return[e], r0);
+    if (p.mode == 0 && lead) {
+        if (stepping) {
+            const double er = dadd(p.st.ep_return[e], reward);
             const int el = p.st.ep_length[e] + 1;
             p.st.ep_return[e] = er;
             p.st.ep_length[e] = el;
@@ -571,11 +612,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
                 atomicAdd(p.io.ep_stats + 1, (double)el);
                 atomicAdd(p.io.ep_stats + 2, 1.0);
             }
+        } else {
+            if (p.io.ep_mask) p.io.ep_mask[e] = 0;
+            if (p.io.ep_return) p.io.ep_return[e] = 0.0;
+            if (p.io.ep_length) p.io.ep_length[e] = 0;
         }
-    } else if (p.mode == 0 && lane == 0) {
-        if (p.io.ep_mask) p.io.ep_mask[e] = 0;
-        if (p.io.ep_return) p.io.ep_return[e] = 0.0;
-        if (p.io.ep_length) p.io.ep_length[e] = 0;
     }
     // per-car info of the step itself (before any same-step reset)
     if (p.mode == 0 && is_car) {
@@ -593,58 +634,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
         }
     }
 
-    // ---- reset (racing_env.py:86-102 / multi_racing_env.py:118-153) ------------
+    // ---- reset (racing_env.py:86-102 / multi_racing_env.py:118-153) ------------------
     if (p.mode == 0 && p.autoreset == RK_AUTORESET_SAME_STEP && ended) resetting = true;
     if (resetting) {
-        int slot = lane;
-        if (KIND == RK_ENV_MULTI) {
-            const int32_t* ss = (p.mode == 1) ? p.io.start_slot : p.io.start_slot;
-            if (ss) {
-                slot = is_car ? ss[c] : 0;
-            } else {
-                // Fisher-Yates over car ids from Philox(seed; env, reset_count); slot = position of this car
-                const uint32_t rc = p.st.reset_count[e];
-                int perm = lane;  // perm[lane] = car id at grid position `lane`
-                for (int i = A - 1; i > 0; --i) {
-                    uint32_t ctr[4] = {(uint32_t)e, rc, (uint32_t)i, 0x736c6f74u};
-                    philox4x32_10(ctr, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                    const int j = (int)(((uint64_t)ctr[0] * (uint64_t)(i + 1)) >> 32);
-                    const int vi = __shfl_sync(kFull, perm, i), vj = __shfl_sync(kFull, perm, j);
-                    if (lane == i) perm = vj;
-                    else if (lane == j) perm = vi;
-                }
-                slot = 0;
-                for (int k = 0; k < A; ++k)
-                    if (__shfl_sync(kFull, perm, k) == lane) slot = k;
-            }
+        x = tmp->start_x; y = tmp->start_y; ang = tmp->start_angle;  // car.py:17-24
+        if (KIND == RK_ENV_MULTI) {  // multi:124-138
+            const int slot = p.io.start_slot ? p.io.start_slot[c]
+                                             : philox_start_slot(p.seed, e, p.st.reset_count[e], A, a);
+            const double center = ddiv((double)(A - 1), 2.0);
+            const double off = dmul(dsub((double)slot, center), 3.5);
+            x = dadd(tmp->start_x, dmul(tmp->start_nx, off));
+            y = dadd(tmp->start_y, dmul(tmp->start_ny, off));
         }
-        if (is_car) {
-            x = tm.start_x; y = tm.start_y; ang = tm.start_angle;  // car.py:17-24
-            if (KIND == RK_ENV_MULTI) {  // multi:124-138
-                const double center = ddiv((double)(A - 1), 2.0);
-                const double off = dmul(dsub((double)slot, center), 3.5);
-                x = dadd(tm.start_x, dmul(tm.start_nx, off));
-                y = dadd(tm.start_y, dmul(tm.start_ny, off));
-            }
-            vx = 0.0; vy = 0.0; last_steer = 0.f;
-            pidx = 0; lpidx = 0; flags = 0; fstep = 0;
-        }
-        steps = 0;
-        if (lane == 0) {
-            p.st.ep_return[e] = 0.0;
-            p.st.ep_length[e] = 0;
-            p.st.reset_count[e] += 1;
-        }
+        vx = 0.0; vy = 0.0; last_steer = 0.f;
+        pidx = 0; lpidx = 0; flags = 0; fstep = 0; steps = 0;
+    }
+    __syncwarp();  // every lane has read reset_count before the lead lane bumps it
+    if (resetting && lead) {
+        p.st.ep_return[e] = 0.0;
+        p.st.ep_length[e] = 0;
+        p.st.reset_count[e] += 1;
     }
 
-    // ---- write state back ------------------------------------------------------
-    if (p.mode != 2) {
-        if (is_car) {
-            p.st.x[c] = x; p.st.y[c] = y; p.st.ang[c] = ang; p.st.vx[c] = vx; p.st.vy[c] = vy;
-            p.st.last_steer[c] = last_steer;
-            p.st.pidx[c] = pidx; p.st.lpidx[c] = lpidx; p.st.flags[c] = flags; p.st.fstep[c] = fstep;
-        }
-        if (lane == 0) {
+    // ---- write state back ----------------------------------------------------------------
+    if (p.mode != 2 && is_car) {
+        p.st.x[c] = x; p.st.y[c] = y; p.st.ang[c] = ang; p.st.vx[c] = vx; p.st.vy[c] = vy;
+        p.st.last_steer[c] = last_steer;
+        p.st.pidx[c] = pidx; p.st.lpidx[c] = lpidx; p.st.flags[c] = flags; p.st.fstep[c] = fstep;
+        if (a == 0) {
             p.st.steps[e] = steps;
             if (p.mode == 0)
                 p.st.needs_reset[e] = (p.autoreset == RK_AUTORESET_NEXT_STEP) ? (stepping && ended) : 0;
@@ -652,167 +669,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
                 p.st.needs_reset[e] = 0;
         }
     }
-    if (p.mode == 0) {
-        if (is_car) {
-            const double r = stepping ? reward : 0.0;
-            if (p.io.reward_f32) p.io.reward_f32[ci] = (float)r;
-            if (p.io.reward_f64) p.io.reward_f64[ci] = r;
-        }
-        if (lane == 0) {
+    if (p.mode == 0 && is_car) {
+        const double r = stepping ? reward : 0.0;
+        if (p.io.reward_f32) p.io.reward_f32[ci] = (float)r;
+        if (p.io.reward_f64) p.io.reward_f64[ci] = r;
+        if (a == 0) {
             p.io.terminated[e] = terminated;
             p.io.truncated[e] = truncated;
             if (p.io.done) p.io.done[e] = ended;
             if (p.io.done_f32) p.io.done_f32[e] = ended ? 1.f : 0.f;
         }
     }
-    float* obs = (p.mode == 1) ? p.io.obs : p.io.obs;
-    if (obs == nullptr || (p.mode == 1 && !resetting)) return;
+    float* obs = p.io.obs;
+    if (obs == nullptr) return;
+    const bool want_obs = is_car && (p.mode != 1 || resetting);
 
-    // ---- observations (racing_env.py:44-75 / multi_racing_env.py:48-105) --------
-    // publish the final pose of every car
-    double cs, sn;
+    // ---- observations (racing_env.py:44-75 / multi_racing_env.py:48-105) ------------------
     sincos(ang, &sn, &cs);
     __syncwarp();
-    if (is_car) {
-        S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn; S.ang[lane] = ang;
-        S.vx[lane] = vx; S.vy[lane] = vy;
-        corners(x, y, cs, sn, S.cx[lane], S.cy[lane]);
+    S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn; S.vx[lane] = vx; S.vy[lane] = vy;
+    {
+        const double lx[4] = {2.0, 2.0, -2.0, -2.0}, ly[4] = {1.0, -1.0, -1.0, 1.0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            S.cx[k][lane] = dadd(dadd(dmul(cs, lx[k]), dmul(-sn, ly[k])), x);
+            S.cy[k][lane] = dadd(dadd(dmul(sn, lx[k]), dmul(cs, ly[k])), y);
+        }
     }
     __syncwarp();
-    const int D = p.D;
-    if (QUERY == RK_QUERY_CULLED) {
-        const int nslot = A * R;
-        // ray directions: one lane per (car, ray) slot
-        for (int s0 = 0; s0 < nslot; s0 += 32) {
-            const int slot = s0 + lane;
-            if (slot < nslot) {
-                const int a = slot / R, r = slot - a * R;
-                double dsn, dcs;
-                sincos(dadd(S.ang[a], p.sensor_angles[r]), &dsn, &dcs);
-                cv.dir64[slot] = make_double2(dcs, dsn);
-                cv.dir32[slot] = make_float2((float)dcs, (float)dsn);
-                cv.ray_key[slot] = kNoKey;
-            }
-        }
-        __syncwarp();
-        for (int a = 0; a < A; ++a) raycast_walls_culled<KIND>(tp, tm, S.x[a], S.y[a], a * R, R, lane, cv);
-        // float64 re-evaluation of every winner + the other cars' edges, one lane per slot
-        const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
-        const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
-        const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
-        const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
-        for (int s0 = 0; s0 < nslot; s0 += 32) {
-            const int slot = s0 + lane;
-            const bool live = slot < nslot;
-            const int a = live ? slot / R : 0, r = live ? slot - a * R : 0;
-            const double ox = S.x[a], oy = S.y[a];
-            double v3x = 0.0, v3y = 1.0, wall = INFINITY;
-            bool redo = false;
-            if (live) {
-                const double2 d = cv.dir64[slot];
-                v3x = -d.y; v3y = d.x;  // track.py:178
-                const unsigned long long key = cv.ray_key[slot];
-                if (key != kNoKey) {
-                    const int i = (int)(key & 0xffffffffu);
-                    const double ax = v2x[i], ay = v2y[i];
-                    const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
-                    wall = ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y);
-                    redo = (wall == INFINITY);  // fp32 candidate rejected by the float64 test
-                }
-            }
-            // rare: re-scan that ray exactly with the whole warp
-            unsigned fb = __ballot_sync(kFull, redo);
-            while (fb) {
-                const int b = __ffs(fb) - 1;
-                fb &= fb - 1;
-                const int bs = s0 + b, ba = bs / R;
-                const double2 d = cv.dir64[bs];
-                double bx[kRayBlock], by[kRayBlock], bt[kRayBlock];
-#pragma unroll
-                for (int k = 0; k < kRayBlock; ++k) { bx[k] = -d.y; by[k] = d.x; bt[k] = INFINITY; }
-                raycast_walls_exact(tp, tm, S.x[ba], S.y[ba], bx, by, 1, lane, bt);
-                const double t = warp_min_d(bt[0]);
-                if (lane == b) wall = t;
-            }
-            if (live) {
-                double t = wall;
-                if (KIND == RK_ENV_MULTI) {
-                    for (int oc = 0; oc < A; ++oc) {  // multi_track.py:10-24
-                        const double ddx = dsub(S.x[oc], ox), ddy = dsub(S.y[oc], oy);
-                        if (sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5) continue;  // multi_track.py:13
-#pragma unroll
-                        for (int ed = 0; ed < 4; ++ed) {
-                            const double ex0 = S.cx[oc][ed], ey0 = S.cy[oc][ed];
-                            const double ax = dsub(S.cx[oc][(ed + 1) & 3], ex0), ay = dsub(S.cy[oc][(ed + 1) & 3], ey0);
-                            const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
-                            const double dotp = dadd(dmul(ax, v3x), dmul(ay, v3y));
-                            const double dv = dadd(dmul(v1x, v3x), dmul(v1y, v3y));
-                            const double adot = fabs(dotp);
-                            if (!(adot < 1e-10) && fabs(dv) <= adot * (1.0 + 1e-12)) {  // multi_track.py:35
-                                const double tt = ddiv(dsub(dmul(ax, v1y), dmul(ay, v1x)), dotp), ss = ddiv(dv, dotp);
-                                if (tt >= 0.0 && ss >= 0.0 && ss <= 1.0) t = fmin(t, tt);
-                            }
-                        }
-                    }
-                    t = fmin(t, kMaxRange);  // multi_track.py:8,26
-                } else if (t == INFINITY) {
-                    t = kMaxRange;  // track.py:196-197
-                }
-                obs[io_index(a) * D + r] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
-            }
-        }
-    } else
-    for (int a = 0; a < A; ++a) {
-        const double ox = S.x[a], oy = S.y[a], oang = S.ang[a];
-        float* orow = obs + io_index(a) * D;
-        for (int r0 = 0; r0 < R; r0 += kRayBlock) {
-            const int nr = min(kRayBlock, R - r0);
-            double v3x[kRayBlock], v3y[kRayBlock], best[kRayBlock];
-#pragma unroll
-            for (int k = 0; k < kRayBlock; ++k) {
-                // lane k computes ray r0+k's direction, then it is broadcast
-                double dsn = 0.0, dcs = 1.0;
-                if (lane == k && k < nr) sincos(dadd(oang, p.sensor_angles[r0 + k]), &dsn, &dcs);
-                v3x[k] = -__shfl_sync(kFull, dsn, k);  // track.py:178 v3 = (-dir_y, dir_x)
-                v3y[k] = __shfl_sync(kFull, dcs, k);
-                best[k] = INFINITY;
-            }
-            raycast_walls_exact(tp, tm, ox, oy, v3x, v3y, nr, lane, best);
-            if (KIND == RK_ENV_MULTI) {
-                // multi_track.py:10-24: lane k < 4A tests edge k%4 of car k/4
-                const int oc = lane >> 2, ed = lane & 3;
-                if (oc < A) {
-                    const double ddx = dsub(S.x[oc], ox), ddy = dsub(S.y[oc], oy);
-                    const bool skip = sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5;  // multi_track.py:13
-                    if (!skip) {
-                        const double ex0 = S.cx[oc][ed], ey0 = S.cy[oc][ed];
-                        const double ex1 = S.cx[oc][(ed + 1) & 3], ey1 = S.cy[oc][(ed + 1) & 3];
-                        const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
-                        const double ax = dsub(ex1, ex0), ay = dsub(ey1, ey0);
-                        const double cross = dsub(dmul(ax, v1y), dmul(ay, v1x));
-#pragma unroll
-                        for (int k = 0; k < kRayBlock; ++k)
-                            if (k < nr) {
-                                const double dotp = dadd(dmul(ax, v3x[k]), dmul(ay, v3y[k]));
-                                if (!(fabs(dotp) < 1e-10)) {  // multi_track.py:35
-                                    const double t = ddiv(cross, dotp);
-                                    const double s = ddiv(dadd(dmul(v1x, v3x[k]), dmul(v1y, v3y[k])), dotp);
-                                    if (t >= 0.0 && s >= 0.0 && s <= 1.0) best[k] = fmin(best[k], t);
-                                }
-                            }
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kRayBlock; ++k) {
-                double t = warp_min_d(best[k]);
-                if (KIND == RK_ENV_MULTI) t = fmin(t, kMaxRange);       // multi_track.py:8,26
-                else if (t == INFINITY) t = kMaxRange;                  // track.py:196-197
-                if (lane == k && k < nr) orow[r0 + k] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
-            }
-        }
-    }
-    if (is_car) {
+    // non-ray slots, every car in parallel
+    if (want_obs) {
         float* orow = obs + ci * D + R;
         const double vf = clipd(ddiv(dadd(dmul(vx, cs), dmul(vy, sn)), kMaxSpeed), -1.0, 1.0);
         const double vl = clipd(ddiv(dadd(dmul(-vx, sn), dmul(vy, cs)), kMaxSpeed), -1.0, 1.0);
@@ -821,15 +707,125 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
         orow[2] = 0.f;  // Car.angular_velocity is never updated
         orow[3] = last_steer;
         if (KIND == RK_ENV_MULTI) {
+            const double mtd = tmp->max_track_distance;
             int w = 4;
             for (int o = 0; o < A; ++o) {
-                if (o == lane) continue;
-                const double rx = dsub(S.x[o], x), ry = dsub(S.y[o], y);
-                const double rvx = dsub(S.vx[o], vx), rvy = dsub(S.vy[o], vy);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(rx, cs), dmul(ry, sn)), tm.max_track_distance), -1.0, 1.0);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rx, sn), dmul(ry, cs)), tm.max_track_distance), -1.0, 1.0);
+                if (o == a) continue;
+                const int l = base + o;
+                const double rx = dsub(S.x[l], x), ry = dsub(S.y[l], y);
+                const double rvx = dsub(S.vx[l], vx), rvy = dsub(S.vy[l], vy);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(rx, cs), dmul(ry, sn)), mtd), -1.0, 1.0);
+                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rx, sn), dmul(ry, cs)), mtd), -1.0, 1.0);
                 orow[w++] = (float)clipd(ddiv(dadd(dmul(rvx, cs), dmul(rvy, sn)), kMaxSpeed), -1.0, 1.0);
                 orow[w++] = (float)clipd(ddiv(dadd(dmul(-rvx, sn), dmul(rvy, cs)), kMaxSpeed), -1.0, 1.0);
+            }
+        }
+    }
+
+    // rays: the warp walks over its environments, all lanes cooperating on one
+    const unsigned obs_envs = __ballot_sync(kFull, want_obs && a == 0);
+    const int nslot = A * R;
+    for (int gg = 0; gg < n_env; ++gg) {
+        const int gbase = gg * A;
+        if (!((obs_envs >> gbase) & 1u)) continue;
+        const int ee = e_base + gg;
+        const TrackMeta tm = tp.meta[__shfl_sync(kFull, tid, gbase)];
+        if (QUERY == RK_QUERY_CULLED) {
+            // ray directions by angle addition from the car's (cos, sin): one lane per (car, ray) slot
+            for (int s0 = 0; s0 < nslot; s0 += 32) {
+                const int slot = s0 + lane;
+                if (slot < nslot) {
+                    const int ca = slot / R, r = slot - ca * R;
+                    const double cc = S.c[gbase + ca], ss = S.s[gbase + ca];
+                    const double rc = p.sensor_cos[r], rs = p.sensor_sin[r];
+                    const double dcs = dsub(dmul(cc, rc), dmul(ss, rs)), dsn = dadd(dmul(ss, rc), dmul(cc, rs));
+                    cv.dir64[slot] = make_double2(dcs, dsn);
+                    cv.dir32[slot] = make_float2((float)dcs, (float)dsn);
+                    cv.ray_key[slot] = kNoKey;
+                }
+            }
+            __syncwarp();
+            for (int ca = 0; ca < A; ++ca)
+                raycast_walls_culled<KIND>(tp, tm, S.x[gbase + ca], S.y[gbase + ca], ca * R, R, lane, cv);
+            // float64 re-evaluation of every winner + the other cars' edges, one lane per slot
+            const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
+            const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
+            const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
+            const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
+            for (int s0 = 0; s0 < nslot; s0 += 32) {
+                const int slot = s0 + lane;
+                const bool live = slot < nslot;
+                const int ca = live ? slot / R : 0, r = live ? slot - ca * R : 0;
+                const double ox = S.x[gbase + ca], oy = S.y[gbase + ca];
+                double v3x = 0.0, v3y = 1.0, wall = INFINITY;
+                bool redo = false;
+                if (live) {
+                    const double2 d = cv.dir64[slot];
+                    v3x = -d.y; v3y = d.x;  // track.py:178
+                    const unsigned long long key = cv.ray_key[slot];
+                    if (key != kNoKey) {
+                        const int i = (int)(key & 0xffffffffu);
+                        const double ax = v2x[i], ay = v2y[i];
+                        const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
+                        wall = ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
+                        redo = (wall == INFINITY);  // fp32 candidate rejected by the float64 test
+                    }
+                }
+                unsigned fb = __ballot_sync(kFull, redo);
+                while (fb) {  // rare: re-scan that ray exactly with the whole warp
+                    const int b = __ffs(fb) - 1;
+                    fb &= fb - 1;
+                    const int bs = s0 + b, ba = bs / R;
+                    const double2 d = cv.dir64[bs];
+                    double bx[kRayBlock], by[kRayBlock], bt[kRayBlock];
+#pragma unroll
+                    for (int k = 0; k < kRayBlock; ++k) { bx[k] = -d.y; by[k] = d.x; bt[k] = INFINITY; }
+                    raycast_walls_exact(tp, tm, S.x[gbase + ba], S.y[gbase + ba], bx, by, 1, lane, bt);
+                    const double t = warp_min_d(bt[0]);
+                    if (lane == b) wall = t;
+                }
+                if (live) {
+                    double t = wall;
+                    if (KIND == RK_ENV_MULTI)
+                        t = fmin(fmin(t, raycast_car_edges(S, gbase, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
+                    else if (t == INFINITY)
+                        t = kMaxRange;  // track.py:196-197
+                    const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
+                    obs[oi * D + r] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+                }
+            }
+            __syncwarp();
+        } else {
+            for (int ca = 0; ca < A; ++ca) {
+                const double ox = S.x[gbase + ca], oy = S.y[gbase + ca];
+                const double oang = __shfl_sync(kFull, ang, gbase + ca);
+                const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
+                float* orow = obs + oi * D;
+                for (int r0 = 0; r0 < R; r0 += kRayBlock) {
+                    const int nr = min(kRayBlock, R - r0);
+                    double v3x[kRayBlock], v3y[kRayBlock], best[kRayBlock];
+#pragma unroll
+                    for (int k = 0; k < kRayBlock; ++k) {
+                        // lane k computes ray r0+k's direction, then it is broadcast
+                        double dsn = 0.0, dcs = 1.0;
+                        if (lane == k && k < nr) sincos(dadd(oang, p.sensor_angles[r0 + k]), &dsn, &dcs);
+                        v3x[k] = -__shfl_sync(kFull, dsn, k);  // track.py:178 v3 = (-dir_y, dir_x)
+                        v3y[k] = __shfl_sync(kFull, dcs, k);
+                        best[k] = INFINITY;
+                    }
+                    raycast_walls_exact(tp, tm, ox, oy, v3x, v3y, nr, lane, best);
+#pragma unroll
+                    for (int k = 0; k < kRayBlock; ++k) {
+                        double t = warp_min_d(best[k]);
+                        if (lane == k && k < nr) {
+                            if (KIND == RK_ENV_MULTI)
+                                t = fmin(fmin(t, raycast_car_edges(S, gbase, A, ox, oy, v3x[k], v3y[k])), kMaxRange);
+                            else if (t == INFINITY)
+                                t = kMaxRange;
+                            orow[r0 + k] = __fdiv_rn((float)t, 50.0f);
+                        }
+                    }
+                }
             }
         }
     }
@@ -838,7 +834,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const StepParam
 }  // namespace
 
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
-    const int grid = (p.E + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int epw = 32 / p.A;
+    const int warps = (p.E + epw - 1) / epw;
+    const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R);
     using Kern = void (*)(const StepParams);
     Kern k;

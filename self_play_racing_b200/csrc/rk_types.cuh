@@ -9,7 +9,7 @@ namespace rk {
 
 constexpr int kChunk = 16;          // boundary points / waypoints per bounding-circle chunk
 constexpr int kMaxKnots = 130;      // n_ctrl + 1 <= kMaxKnots
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 
 // flags word of a car
 enum : int { F_CRASHED = 1, F_FINISHED = 2, F_CP25 = 4, F_CP50 = 8, F_CP75 = 16, F_HAS_CRASHED = 32 };
@@ -64,6 +64,7 @@ struct StepParams {
     EnvState st;
     rk_step_io io;
     const double* sensor_angles;  // [R] np.linspace(-half, half, R)
+    const double *sensor_cos, *sensor_sin;  // [R] cos / sin of the above
     int32_t E, A, R, D;
     int32_t autoreset, max_steps;
     double speed_weight;
