@@ -262,6 +262,14 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
     p.sensor_angles = h->sensor_angles;
     p.sensor_cos = h->sensor_angles + h->cfg.num_sensors;
     p.sensor_sin = h->sensor_angles + 2 * h->cfg.num_sensors;
+    {
+        const double half = (h->cfg.env_kind == RK_ENV_SINGLE) ? M_PI / 3 : M_PI / 2;
+        const int R = h->cfg.num_sensors;
+        p.inv_dphi = (R > 1) ? (float)((R - 1) / (2.0 * half)) : 1.0f;
+        p.cone_half = (float)half;
+        p.cone_sin = (float)sin(half + 2e-3);
+        p.cone_cos = (float)cos(half + 2e-3);
+    }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
     p.autoreset = h->cfg.autoreset_mode;
     p.max_steps = h->cfg.max_episode_steps;

@@ -57,7 +57,18 @@ __device__ __forceinline__ float warp_min_f(float v) {
     return v;
 }
 
-constexpr int kListCap = 512;  // (ray, chunk) work items per warp batch
+
+// Lexicographic warp minimum of (non-negative double, index) with three REDUX
+// instructions: a non-negative IEEE double orders like its bit pattern.
+__device__ __forceinline__ int warp_argmin_d(double d, int idx) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+    return (int)__reduce_min_sync(kFull, (hi == mh && lo == ml) ? (unsigned)idx : 0xffffffffu);
+}
+
+constexpr int kListCap = 512;  // chunk work items per warp batch
 
 // Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
 // one column per lane: conflict free) and the scratch of the culled queries.
@@ -99,15 +110,7 @@ __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMet
         }
     }
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            const double od = shfl_xor_d(best[q], m);
-            const int oi = __shfl_xor_sync(kFull, bi[q], m);
-            if (od < best[q] || (od == best[q] && oi < bi[q])) { best[q] = od; bi[q] = oi; }
-        }
-        out_idx[q] = bi[q];
-    }
+    for (int q = 0; q < NQ; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
 // One ray against one segment, the reference's formula (track.py:176-195 /
@@ -242,94 +245,100 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            const double od = shfl_xor_d(best[q], m);
-            const int oi = __shfl_xor_sync(kFull, bi[q], m);
-            if (od < best[q] || (od == best[q] && oi < bi[q])) { best[q] = od; bi[q] = oi; }
-        }
-        out_idx[q] = bi[q];
-    }
+    for (int q = 0; q < 5; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
-// fp32 candidate search of the R rays of one car against the walls.  Level 1:
-// lane <-> boundary chunk, loop over rays, circle-vs-ray test; survivors go to a
-// work list.  Level 2: half-warp <-> (ray, chunk) item, lane <-> segment; a
-// segment whose end points straddle the ray's line (with slack) and which is
-// not entirely behind the origin posts (t, segment) to the ray's key.
+// fp32 candidate search of the R rays of one car against the walls, as an
+// angular sweep.  The rays are uniformly spaced in angle around the heading
+// (np.linspace, racing_env.py:45 / multi_racing_env.py:50), so a boundary
+// point's polar angle in the car frame, scaled to "ray index" units u, says
+// between which rays it lies; a segment (p, q) can only be hit by the rays whose
+// index lies in [min(u_p, u_q), max(u_p, u_q)].
+//   Level 1: lane <-> boundary chunk: keep the chunks whose bounding circle
+//            reaches into the sensor cone (and, multi env, within the 50-unit
+//            clamp of multi_track.py:8,26).
+//   Level 2: half-warp <-> chunk, lane j <-> point j of its 16 points; lane j+1
+//            holds the end point of lane j's segment (one shuffle).  Candidate
+//            (ray, segment) pairs post (t, segment) to the ray's key.
+// Segments seen under ~180 degrees or closer than 0.5 (the origin practically on
+// the wall) fall back to an explicit straddle test against every ray.
 template <int KIND>
-__device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, double oxd, double oyd,
-                                                     int slot0, int R, int lane, const CullView& cv) {
+__device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, const StepParams& p,
+                                                     double oxd, double oyd, double hcd, double hsd, int slot0,
+                                                     int lane, const CullView& cv) {
     const float4* bch = tp.bchunk + tm.bchunk_off;
-    const float2* bpt = tp.bpt + 2 * (size_t)tm.wp_off;
+    const float2* bpt = tp.bpt + tm.bpt_off;
     const float ox = (float)(oxd - tm.org_x), oy = (float)(oyd - tm.org_y);
-    const int nb = tm.n_bchunk, nch = nb >> 1, N = tm.n_wp;
+    const float hc = (float)hcd, hs = (float)hsd;
+    const int nb = tm.n_bchunk, nrc = nb >> 1, N = tm.n_wp, R = p.R;
     const unsigned lt = (1u << lane) - 1u;
     const int half = lane >> 4, j = lane & 15;
-    constexpr int kRaysPerBatch = kListCap / 32;
-    for (int rb = 0; rb < R; rb += kRaysPerBatch) {
-        const int nr = min(kRaysPerBatch, R - rb);
-        const float2* dirs = cv.dir32 + slot0 + rb;
-        unsigned long long* keys = cv.ray_key + slot0 + rb;
-        for (int c0 = 0; c0 < nb; c0 += 32) {
-            // ---- level 1 ----
-            const int ci = c0 + lane;
-            float rx = 0.f, ry = 0.f, rr = -1.f;
-            bool near = false;
-            if (ci < nb) {
-                const float4 cc = bch[ci];
-                rx = cc.x - ox; ry = cc.y - oy; rr = cc.z;
-                // multi env readings are clamped to 50 (multi_track.py:8,26): farther chunks can not matter
-                near = (KIND == RK_ENV_SINGLE) || (rx * rx + ry * ry <= (50.01f + rr) * (50.01f + rr));
+    const float2* dirs = cv.dir32 + slot0;
+    unsigned long long* keys = cv.ray_key + slot0;
+    // ---- level 1 ----
+    int count = 0;
+    for (int c0 = 0; c0 < nb; c0 += 32) {
+        const int ci = c0 + lane;
+        bool keep = false;
+        if (ci < nb) {
+            const float4 cc = bch[ci];
+            const float rx = cc.x - ox, ry = cc.y - oy, rr = cc.z;
+            const float lx = rx * hc + ry * hs, ly = ry * hc - rx * hs;  // car frame
+            keep = p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr;       // circle reaches into the cone |angle| <= H
+            if (KIND == RK_ENV_MULTI) keep = keep && (rx * rx + ry * ry <= (50.01f + rr) * (50.01f + rr));
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)ci;
+        count += __popc(m);
+    }
+    __syncwarp();
+    // ---- level 2 ----
+    const float inv_dphi = p.inv_dphi, u_off = p.cone_half * inv_dphi;
+    const float wrap_thr = 3.1405926f * inv_dphi;
+    for (int it = 0; it < count; it += 2) {
+        const int my = it + half;
+        const bool act = my < count;
+        const int ci = act ? (int)cv.list[my] : 0;
+        const int side = ci >= nrc;
+        const int pt = (ci - side * nrc) * kRaySegs + j;  // point index in the closed row (0..N)
+        float px = 1e6f, py = 1e6f;
+        if (act && pt <= N) {
+            const float2 P = bpt[side * (N + 1) + pt];
+            px = P.x - ox; py = P.y - oy;
+        }
+        const float d2 = px * px + py * py;
+        const float u = atan2f(py * hc - px * hs, px * hc + py * hs) * inv_dphi + u_off;
+        const float qx = __shfl_down_sync(kFull, px, 1), qy = __shfl_down_sync(kFull, py, 1);
+        const float un = __shfl_down_sync(kFull, u, 1);
+        if (act && j < kRaySegs && pt < N) {
+            const float m2 = fminf(d2, qx * qx + qy * qy);
+            const bool slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
+            // angular error budget: table/origin rounding (<= 1.6e-5 / distance) + atan2f + heading rounding
+            const float slack = (3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
+            int klo = 0, khi = R - 1;
+            if (!slow) {
+                klo = max(0, (int)ceilf(fminf(u, un) - slack));
+                khi = min(R - 1, (int)floorf(fmaxf(u, un) + slack));
             }
-            int count = 0;
-            if (__any_sync(kFull, near)) {
-                for (int k = 0; k < nr; ++k) {
-                    const float2 d = dirs[k];
-                    const float proj = rx * d.x + ry * d.y, perp = rx * d.y - ry * d.x;
-                    bool keep = near && fabsf(perp) <= rr && proj >= -rr;
-                    if (KIND == RK_ENV_MULTI) keep = keep && (proj - rr <= 50.01f);
-                    const unsigned m = __ballot_sync(kFull, keep);
-                    if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)((k << 10) | ci);
-                    count += __popc(m);
+            for (int k = klo; k <= khi; ++k) {
+                const float2 d = dirs[k];
+                const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
+                const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
+                if (slow) {
+                    const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
+                    const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
+                                          (cp >= -kPerpSlack && cq <= kPerpSlack);
+                    if (!straddle || thi < -kFrontSlack) continue;
                 }
+                const float vx = qx - px, vy = qy - py;
+                const float den = d.x * vy - d.y * vx;
+                float t = (fabsf(den) > 1e-12f) ? __fdividef(px * vy - py * vx, den) : tlo;
+                t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
+                atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(side * N + pt));
             }
-            __syncwarp();
-            // ---- level 2 ----
-            for (int it = 0; it < count; it += 2) {
-                const int my = it + half;
-                if (my < count) {
-                    const unsigned item = cv.list[my];
-                    const int k = item >> 10, cj = item & 1023;
-                    const int side = cj >= nch;
-                    const int seg = (cj - side * nch) * kChunk + j;
-                    if (seg < N) {
-                        const float2* row = bpt + side * N;
-                        const float2 p = row[seg];
-                        const float2 q = row[seg + 1 == N ? 0 : seg + 1];
-                        const float2 d = dirs[k];
-                        const float px = p.x - ox, py = p.y - oy, qx = q.x - ox, qy = q.y - oy;
-                        const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
-                        const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
-                                              (cp >= -kPerpSlack && cq <= kPerpSlack);
-                        if (straddle) {
-                            const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
-                            const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
-                            if (thi >= -kFrontSlack) {
-                                const float den = cq - cp;
-                                float t = (fabsf(den) > 1e-12f) ? (px * (qy - py) - py * (qx - px)) / den : tlo;
-                                t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
-                                atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) |
-                                                        (unsigned)(side * N + seg));
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
         }
     }
+    __syncwarp();
 }
 
 // Philox Fisher-Yates over the A car ids of an environment; returns the grid
@@ -746,7 +755,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
             }
             __syncwarp();
             for (int ca = 0; ca < A; ++ca)
-                raycast_walls_culled<KIND>(tp, tm, S.x[gbase + ca], S.y[gbase + ca], ca * R, R, lane, cv);
+                raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
+                                           S.s[gbase + ca], ca * R, lane, cv);
             // float64 re-evaluation of every winner + the other cars' edges, one lane per slot
             const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
             const double* sy = tp.sy + 2 * (size_t)tm.wp_off;

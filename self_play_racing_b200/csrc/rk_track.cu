@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) build_track_kernel(BuildArgs a) {
     double* sy = a.sy + 2 * (size_t)off;
     double* v2x = a.v2x + 2 * (size_t)off;
     double* v2y = a.v2y + 2 * (size_t)off;
-    float2* bpt = a.bpt + 2 * (size_t)off;
+    float2* bpt = a.bpt + tm.bpt_off;
     float2* wpt = a.wpt + off;
     for (int k = tid; k < N; k += nt) {
         const int k1 = (k + 1 == N) ? 0 : k + 1;
@@ -211,23 +211,31 @@ __global__ void __launch_bounds__(256) build_track_kernel(BuildArgs a) {
         sx[k] = lx; sy[k] = ly; v2x[k] = dsub(lx1, lx); v2y[k] = dsub(ly1, ly);
         sx[N + k] = rx; sy[N + k] = ry; v2x[N + k] = dsub(rx1, rx); v2y[N + k] = dsub(ry1, ry);
         bpt[k] = make_float2((float)(lx - ox), (float)(ly - oy));
-        bpt[N + k] = make_float2((float)(rx - ox), (float)(ry - oy));
+        bpt[N + 1 + k] = make_float2((float)(rx - ox), (float)(ry - oy));
+        if (k == 0) {  // each row is closed: point N repeats point 0
+            bpt[N] = bpt[0];
+            bpt[2 * N + 1] = bpt[N + 1];
+        }
         wpt[k] = make_float2((float)(wx[k] - ox), (float)(wy[k] - oy));
     }
     __syncthreads();
-    // bounding circles.  Boundary chunk c of a side covers segments
-    // [c*kChunk, min((c+1)*kChunk, N)), i.e. points c*kChunk .. end inclusive.
-    const int nch = (N + kChunk - 1) / kChunk;
-    for (int c = tid; c < 3 * nch; c += nt) {
-        const int kind = c / nch, cc = c % nch;  // 0 left, 1 right, 2 waypoints
-        const int k0 = cc * kChunk;
-        const int k1 = min(k0 + kChunk, N);
-        const int last = (kind == 2) ? k1 - 1 : k1;  // segments need their end point too
+    // bounding circles.  Waypoint chunk c covers waypoints [c*kChunk, (c+1)*kChunk);
+    // boundary chunk c of a side covers segments [c*kRaySegs, (c+1)*kRaySegs),
+    // i.e. points c*kRaySegs .. end inclusive (point N = point 0).
+    const int nwc = (N + kChunk - 1) / kChunk, nrc = (N + kRaySegs - 1) / kRaySegs;
+    for (int c = tid; c < nwc + 2 * nrc; c += nt) {
+        const bool is_wp = c < nwc;
+        const int kind = is_wp ? 2 : (c - nwc) / nrc;          // 0 left, 1 right, 2 waypoints
+        const int cc = is_wp ? c : (c - nwc) % nrc;
+        const int span = is_wp ? kChunk : kRaySegs;
+        const int k0 = cc * span;
+        const int k1 = min(k0 + span, N);
+        const int last = is_wp ? k1 - 1 : k1;  // segments need their end point too
         double bx0 = INFINITY, bx1 = -INFINITY, by0 = INFINITY, by1 = -INFINITY;
         for (int k = k0; k <= last; ++k) {
             const int kk = (k == N) ? 0 : k;
-            const double qx = (kind == 2) ? wx[kk] : sx[kind * N + kk];
-            const double qy = (kind == 2) ? wy[kk] : sy[kind * N + kk];
+            const double qx = is_wp ? wx[kk] : sx[kind * N + kk];
+            const double qy = is_wp ? wy[kk] : sy[kind * N + kk];
             bx0 = fmin(bx0, qx); bx1 = fmax(bx1, qx);
             by0 = fmin(by0, qy); by1 = fmax(by1, qy);
         }
@@ -235,16 +243,16 @@ __global__ void __launch_bounds__(256) build_track_kernel(BuildArgs a) {
         double r2 = 0.0;
         for (int k = k0; k <= last; ++k) {
             const int kk = (k == N) ? 0 : k;
-            const double qx = (kind == 2) ? wx[kk] : sx[kind * N + kk];
-            const double qy = (kind == 2) ? wy[kk] : sy[kind * N + kk];
+            const double qx = is_wp ? wx[kk] : sx[kind * N + kk];
+            const double qy = is_wp ? wy[kk] : sy[kind * N + kk];
             r2 = fmax(r2, (qx - ccx) * (qx - ccx) + (qy - ccy) * (qy - ccy));
         }
         // margin covers fp32 rounding of the tables, the centre and the query
         const float4 circ = make_float4((float)(ccx - ox), (float)(ccy - oy), (float)(sqrt(r2) + 2e-3), 0.f);
-        if (kind == 2)
+        if (is_wp)
             a.wchunk[tm.wchunk_off + cc] = circ;
         else
-            a.bchunk[tm.bchunk_off + kind * nch + cc] = circ;
+            a.bchunk[tm.bchunk_off + kind * nrc + cc] = circ;
     }
 }
 
@@ -346,7 +354,7 @@ int build_pool(PoolBuffers& pb, int n_tracks, const int32_t* n_ctrl, const int32
     }
     pb.n_tracks = n_tracks;
     pb.host_meta.assign(n_tracks, TrackMeta());
-    size_t wp = 0, ch = 0;
+    size_t wp = 0, ch = 0, bch = 0, bpts = 0;
     for (int t = 0; t < n_tracks; ++t) {
         TrackMeta& m = pb.host_meta[t];
         if (n_wp[t] < 4) {
@@ -358,17 +366,21 @@ int build_pool(PoolBuffers& pb, int n_tracks, const int32_t* n_ctrl, const int32
             return 1;
         }
         const int nch = (n_wp[t] + kChunk - 1) / kChunk;
+        const int nrc = (n_wp[t] + kRaySegs - 1) / kRaySegs;
         m.n_wp = n_wp[t];
         m.wp_off = (int32_t)wp;
         m.n_wchunk = nch;
         m.wchunk_off = (int32_t)ch;
-        m.n_bchunk = 2 * nch;
-        m.bchunk_off = (int32_t)(2 * ch);
+        m.n_bchunk = 2 * nrc;
+        m.bchunk_off = (int32_t)bch;
+        m.bpt_off = (int32_t)bpts;
         m.n_ctrl = n_ctrl ? n_ctrl[t] : 0;
         m.ctrl_off = ctrl_off ? ctrl_off[t] : 0;
         m.width = widths[t];
         wp += n_wp[t];
         ch += nch;
+        bch += 2 * nrc;
+        bpts += 2 * ((size_t)n_wp[t] + 1);
     }
     pb.total_wp = wp;
     pb.total_chunks = ch;
@@ -380,9 +392,9 @@ int build_pool(PoolBuffers& pb, int n_tracks, const int32_t* n_ctrl, const int32
     double** d16[] = {&pb.sx, &pb.sy, &pb.v2x, &pb.v2y};
     for (double** p : d16) RK_CUDA(cudaMalloc(p, 2 * wp * sizeof(double)));
     RK_CUDA(cudaMalloc(&pb.wpt, wp * sizeof(float2)));
-    RK_CUDA(cudaMalloc(&pb.bpt, 2 * wp * sizeof(float2)));
+    RK_CUDA(cudaMalloc(&pb.bpt, bpts * sizeof(float2)));
     RK_CUDA(cudaMalloc(&pb.wchunk, ch * sizeof(float4)));
-    RK_CUDA(cudaMalloc(&pb.bchunk, 2 * ch * sizeof(float4)));
+    RK_CUDA(cudaMalloc(&pb.bchunk, bch * sizeof(float4)));
     RK_CUDA(cudaMemcpy(pb.meta, pb.host_meta.data(), n_tracks * sizeof(TrackMeta), cudaMemcpyHostToDevice));
     std::vector<int32_t> e2t(E);
     for (int e = 0; e < E; ++e) {

@@ -7,7 +7,8 @@
 
 namespace rk {
 
-constexpr int kChunk = 16;          // boundary points / waypoints per bounding-circle chunk
+constexpr int kChunk = 16;          // waypoints per bounding-circle chunk
+constexpr int kRaySegs = 15;        // boundary segments per chunk (16 points: one half-warp, lane j+1 holds lane j's end point)
 constexpr int kMaxKnots = 130;      // n_ctrl + 1 <= kMaxKnots
 constexpr int kWarpsPerCta = 4;
 
@@ -22,8 +23,10 @@ struct TrackMeta {
     int32_t wp_off;      // offset into per-waypoint arrays; segment arrays start at 2*wp_off
     int32_t n_wchunk;    // ceil(N / kChunk) waypoint chunks
     int32_t wchunk_off;
-    int32_t n_bchunk;    // 2 * ceil(N / kChunk) boundary chunks (left side first)
+    int32_t n_bchunk;    // 2 * ceil(N / kRaySegs) boundary chunks (left side first)
     int32_t bchunk_off;
+    int32_t bpt_off;     // offset of this track's fp32 boundary rows: 2 rows of N+1 points (point 0 repeated)
+    int32_t pad0;
     int32_t n_ctrl;
     int32_t ctrl_off;
     double width;               // track.py:77-80
@@ -41,9 +44,9 @@ struct TrackPool {
     const double *sx, *sy, *v2x, *v2y;    // [sum 2N]  segment starts and vectors (track.py:134-148)
     // fp32 tables relative to (org_x, org_y): candidate search only
     const float2* wpt;     // [sum N]  waypoints
-    const float2* bpt;     // [sum 2N] boundary points (left then right)
+    const float2* bpt;     // [sum 2(N+1)] boundary points, per track: left row then right row, each closed
     const float4* wchunk;  // (cx, cy, r, -) bounding circle of kChunk waypoints
-    const float4* bchunk;  // (cx, cy, r, -) bounding circle of kChunk boundary segments
+    const float4* bchunk;  // (cx, cy, r, -) bounding circle of kRaySegs boundary segments
 };
 
 struct EnvState {
@@ -65,6 +68,8 @@ struct StepParams {
     rk_step_io io;
     const double* sensor_angles;  // [R] np.linspace(-half, half, R)
     const double *sensor_cos, *sensor_sin;  // [R] cos / sin of the above
+    float inv_dphi;    // (R-1) / (2H): ray-index units per radian (H = half cone: pi/3 single, pi/2 multi)
+    float cone_half, cone_sin, cone_cos;  // H plus a small margin, and its sine / cosine
     int32_t E, A, R, D;
     int32_t autoreset, max_steps;
     double speed_weight;
