@@ -1,6 +1,7 @@
 // C ABI of librk_b200.so (declared in include/racing_b200.h).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -269,6 +270,24 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
         p.cone_half = (float)half;
         p.cone_sin = (float)sin(half + 2e-3);
         p.cone_cos = (float)cos(half + 2e-3);
+        // distance shells of the ray sweep (last one unbounded); RK_B200_SHELLS="a,b" overrides for tuning
+        const bool single = h->cfg.env_kind == RK_ENV_SINGLE;
+        // measured (profiles/r01_shell_sweep.log): the clamped multi env is fastest in one pass,
+        // the unclamped single env with one split at 30 units
+        float sh[4] = {single ? 30.f : INFINITY, INFINITY, INFINITY, INFINITY};
+        int ns = single ? 2 : 1;
+        if (const char* env = getenv("RK_B200_SHELLS")) {
+            ns = 0;
+            for (const char* q = env; *q && ns < 3;) {
+                sh[ns++] = (float)atof(q);
+                const char* c = strchr(q, ',');
+                if (!c) break;
+                q = c + 1;
+            }
+            sh[ns++] = INFINITY;
+        }
+        p.n_shells = ns;
+        for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
     p.autoreset = h->cfg.autoreset_mode;

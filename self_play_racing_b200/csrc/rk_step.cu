@@ -113,18 +113,22 @@ __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMet
     for (int q = 0; q < NQ; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
-// One ray against one segment, the reference's formula (track.py:176-195 /
-// multi_track.py:28-44).  Returns t if hit, +inf otherwise.  The divisions are
-// only evaluated when a magnitude pre-test (which can not reject a true hit:
-// s <= 1 implies |dv| <= |dotp| up to one rounding) passes.
+// One ray against one segment, the reference's test (track.py:176-195 /
+// multi_track.py:28-44): hit iff |dotp| large enough, t = cross/dotp >= 0 and
+// 0 <= s = dv/dotp <= 1.  Returns t if hit, +inf otherwise.
 __device__ __forceinline__ double ray_segment(double v1x, double v1y, double v2x, double v2y, double cross,
                                               double v3x, double v3y, double min_abs_dot) {
     const double dotp = dadd(dmul(v2x, v3x), dmul(v2y, v3y));
     const double dv = dadd(dmul(v1x, v3x), dmul(v1y, v3y));
-    const double adot = fabs(dotp);
-    if (adot >= min_abs_dot && fabs(dv) <= adot * (1.0 + 1e-12)) {
-        const double t = ddiv(cross, dotp), s = ddiv(dv, dotp);
-        if (t >= 0.0 && s >= 0.0 && s <= 1.0) return t;
+    const double adot = fabs(dotp), adv = fabs(dv);
+    if (adot >= min_abs_dot && adv <= adot * (1.0 + 1e-12)) {
+        // t = cross/dotp >= 0 and s = dv/dotp >= 0 are sign statements about correctly
+        // rounded quotients; s <= 1 follows from |dv| <= |dotp| (rounding is monotonic) and
+        // needs the actual quotient only in the one-ulp band above it.
+        const bool neg = dotp < 0.0;
+        const bool t_ok = (cross == 0.0) || ((cross < 0.0) == neg);
+        const bool s_ok = (dv == 0.0) || ((dv < 0.0) == neg);
+        if (t_ok && s_ok && (adv <= adot || ddiv(dv, dotp) <= 1.0)) return ddiv(cross, dotp);
     }
     return INFINITY;
 }
@@ -248,6 +252,27 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     for (int q = 0; q < 5; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
+// atan2 for the angular sweep: Abramowitz & Stegun 4.4.49 (|error| <= 2e-8 on
+// [0, 1]) plus octant reconstruction; the result only bins points between rays
+// and its error is part of the binning slack.
+__device__ __forceinline__ float sweep_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, mx), s = a * a;
+    float r = 0.0028662257f;
+    r = fmaf(r, s, -0.0161657367f);
+    r = fmaf(r, s, 0.0429096138f);
+    r = fmaf(r, s, -0.0752896400f);
+    r = fmaf(r, s, 0.1065626393f);
+    r = fmaf(r, s, -0.1420889944f);
+    r = fmaf(r, s, 0.1999355085f);
+    r = fmaf(r, s, -0.3333314528f);
+    r = fmaf(r * s, a, a);
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.f) r = 3.14159265359f - r;
+    return copysignf(r, y);
+}
+
 // fp32 candidate search of the R rays of one car against the walls, as an
 // angular sweep.  The rays are uniformly spaced in angle around the heading
 // (np.linspace, racing_env.py:45 / multi_racing_env.py:50), so a boundary
@@ -255,13 +280,19 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
 // between which rays it lies; a segment (p, q) can only be hit by the rays whose
 // index lies in [min(u_p, u_q), max(u_p, u_q)].
 //   Level 1: lane <-> boundary chunk: keep the chunks whose bounding circle
-//            reaches into the sensor cone (and, multi env, within the 50-unit
-//            clamp of multi_track.py:8,26).
+//            reaches into the sensor cone.
 //   Level 2: half-warp <-> chunk, lane j <-> point j of its 16 points; lane j+1
 //            holds the end point of lane j's segment (one shuffle).  Candidate
 //            (ray, segment) pairs post (t, segment) to the ray's key.
+// Chunks are visited in distance shells (StepParams::shell).  From the second shell on a
+// chunk is kept only if one of the rays pointing into its circle still has no
+// candidate, or one that lies beyond the chunk's nearest point: a car inside
+// the closed corridor has most rays blocked nearby, so far chunks are skipped
+// without changing any ray's nearest hit.  The multi env stops at its 50-unit
+// clamp (multi_track.py:8,26).
 // Segments seen under ~180 degrees or closer than 0.5 (the origin practically on
 // the wall) fall back to an explicit straddle test against every ray.
+
 template <int KIND>
 __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, const StepParams& p,
                                                      double oxd, double oyd, double hcd, double hsd, int slot0,
@@ -275,70 +306,90 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     const int half = lane >> 4, j = lane & 15;
     const float2* dirs = cv.dir32 + slot0;
     unsigned long long* keys = cv.ray_key + slot0;
-    // ---- level 1 ----
-    int count = 0;
-    for (int c0 = 0; c0 < nb; c0 += 32) {
-        const int ci = c0 + lane;
-        bool keep = false;
-        if (ci < nb) {
-            const float4 cc = bch[ci];
-            const float rx = cc.x - ox, ry = cc.y - oy, rr = cc.z;
-            const float lx = rx * hc + ry * hs, ly = ry * hc - rx * hs;  // car frame
-            keep = p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr;       // circle reaches into the cone |angle| <= H
-            if (KIND == RK_ENV_MULTI) keep = keep && (rx * rx + ry * ry <= (50.01f + rr) * (50.01f + rr));
-        }
-        const unsigned m = __ballot_sync(kFull, keep);
-        if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)ci;
-        count += __popc(m);
-    }
-    __syncwarp();
-    // ---- level 2 ----
     const float inv_dphi = p.inv_dphi, u_off = p.cone_half * inv_dphi;
     const float wrap_thr = 3.1405926f * inv_dphi;
-    for (int it = 0; it < count; it += 2) {
-        const int my = it + half;
-        const bool act = my < count;
-        const int ci = act ? (int)cv.list[my] : 0;
-        const int side = ci >= nrc;
-        const int pt = (ci - side * nrc) * kRaySegs + j;  // point index in the closed row (0..N)
-        float px = 1e6f, py = 1e6f;
-        if (act && pt <= N) {
-            const float2 P = bpt[side * (N + 1) + pt];
-            px = P.x - ox; py = P.y - oy;
-        }
-        const float d2 = px * px + py * py;
-        const float u = atan2f(py * hc - px * hs, px * hc + py * hs) * inv_dphi + u_off;
-        const float qx = __shfl_down_sync(kFull, px, 1), qy = __shfl_down_sync(kFull, py, 1);
-        const float un = __shfl_down_sync(kFull, u, 1);
-        if (act && j < kRaySegs && pt < N) {
-            const float m2 = fminf(d2, qx * qx + qy * qy);
-            const bool slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
-            // angular error budget: table/origin rounding (<= 1.6e-5 / distance) + atan2f + heading rounding
-            const float slack = (3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
-            int klo = 0, khi = R - 1;
-            if (!slow) {
-                klo = max(0, (int)ceilf(fminf(u, un) - slack));
-                khi = min(R - 1, (int)floorf(fmaxf(u, un) + slack));
-            }
-            for (int k = klo; k <= khi; ++k) {
-                const float2 d = dirs[k];
-                const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
-                const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
-                if (slow) {
-                    const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
-                    const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
-                                          (cp >= -kPerpSlack && cq <= kPerpSlack);
-                    if (!straddle || thi < -kFrontSlack) continue;
+    const float range = (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY;
+    for (int pass = 0; pass < p.n_shells; ++pass) {
+        // shell of this pass: chunks whose nearest possible point lies in (lo, hi]
+        const float lo = (pass == 0) ? -INFINITY : p.shell[pass - 1];
+        const float hi = fminf(p.shell[pass], range);
+        if (!(hi > lo)) break;
+        // ---- level 1 ----
+        int count = 0;
+        for (int c0 = 0; c0 < nb; c0 += 32) {
+            const int ci = c0 + lane;
+            bool keep = false;
+            if (ci < nb) {
+                const float4 cc = bch[ci];
+                const float rx = cc.x - ox, ry = cc.y - oy, rr = cc.z;
+                const float lx = rx * hc + ry * hs, ly = ry * hc - rx * hs;  // car frame
+                const float dc = sqrtf(rx * rx + ry * ry), dmin = dc - rr;   // no point of the chunk is closer than dmin
+                keep = (p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr) &&   // circle reaches into the cone |angle| <= H
+                       dmin > lo && dmin <= hi;
+                if (keep && pass > 0 && dc > rr) {
+                    // per-ray pruning: the circle subtends <= asin(rr/dc) <= (pi/2) rr/dc around its centre;
+                    // keep it only if a ray in that fan has no candidate yet or one farther than dmin
+                    const float uc = sweep_atan2(ly, lx) * inv_dphi + u_off;
+                    const float du = (1.5708f * rr / dc + 1e-3f) * inv_dphi;
+                    const int klo = max(0, (int)ceilf(uc - du)), khi = min(R - 1, (int)floorf(uc + du));
+                    bool open = false;
+                    for (int k = klo; k <= khi; ++k) {
+                        const unsigned tb = (unsigned)(keys[k] >> 32);  // 0xffffffff (no candidate) is a NaN pattern: test first
+                        open = open || tb == 0xffffffffu || __uint_as_float(tb) * 1.0001f + 1e-2f > dmin;
+                    }
+                    keep = open;
                 }
-                const float vx = qx - px, vy = qy - py;
-                const float den = d.x * vy - d.y * vx;
-                float t = (fabsf(den) > 1e-12f) ? __fdividef(px * vy - py * vx, den) : tlo;
-                t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
-                atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(side * N + pt));
+            }
+            const unsigned m = __ballot_sync(kFull, keep);
+            if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)ci;
+            count += __popc(m);
+        }
+        __syncwarp();
+        // ---- level 2 ----
+        for (int it = 0; it < count; it += 2) {
+            const int my = it + half;
+            const bool act = my < count;
+            const int ci = act ? (int)cv.list[my] : 0;
+            const int side = ci >= nrc;
+            const int pt = (ci - side * nrc) * kRaySegs + j;  // point index in the closed row (0..N)
+            float px = 1e6f, py = 1e6f;
+            if (act && pt <= N) {
+                const float2 P = bpt[side * (N + 1) + pt];
+                px = P.x - ox; py = P.y - oy;
+            }
+            const float u = sweep_atan2(py * hc - px * hs, px * hc + py * hs) * inv_dphi + u_off;
+            const float qx = __shfl_down_sync(kFull, px, 1), qy = __shfl_down_sync(kFull, py, 1);
+            const float un = __shfl_down_sync(kFull, u, 1);
+            if (act && j < kRaySegs && pt < N) {
+                const float m2 = fminf(px * px + py * py, qx * qx + qy * qy);
+                const bool slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
+                // angular error budget: table/origin rounding (<= 1.6e-5 / distance) + atan2 + heading rounding
+                const float slack = (3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
+                int klo = 0, khi = R - 1;
+                if (!slow) {
+                    klo = max(0, (int)ceilf(fminf(u, un) - slack));
+                    khi = min(R - 1, (int)floorf(fmaxf(u, un) + slack));
+                }
+                for (int k = klo; k <= khi; ++k) {
+                    const float2 d = dirs[k];
+                    const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
+                    const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
+                    if (slow) {
+                        const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
+                        const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) ||
+                                              (cp >= -kPerpSlack && cq <= kPerpSlack);
+                        if (!straddle || thi < -kFrontSlack) continue;
+                    }
+                    const float vx = qx - px, vy = qy - py;
+                    const float den = d.x * vy - d.y * vx;
+                    float t = (fabsf(den) > 1e-12f) ? __fdividef(px * vy - py * vx, den) : tlo;
+                    t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
+                    atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(side * N + pt));
+                }
             }
         }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // Philox Fisher-Yates over the A car ids of an environment; returns the grid
