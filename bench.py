@@ -116,37 +116,119 @@ def cpu_baseline(wl, budget_envs=64, steps=12):
                       f'240 agent-steps/s 2-car on one core at survey time)'}
 
 
+_REF_ENV = None
+
+
+def _ref_init(kind, A, R, E, seed_base):
+    """Pool initializer: every worker process builds its own oracle batch once."""
+    global _REF_ENV
+    from oracle import racing_oracle as O
+    seed = seed_base + os.getpid() % 1000
+    rs = np.random.RandomState(seed)
+    cps = [O.gen_random_track(rs.randint(10, 15), rs.randint(50, 80), rs.randint(10, 20), rs.uniform(0.2, 0.7),
+                              rs.uniform(0.2, 0.7), rng=rs) for _ in range(4)]
+    env = O.OracleVecEnv(O.make_pool(cps, [8.0, 7.0, 9.0, 8.0]), np.arange(E) % 4, kind=kind, num_agents=A,
+                         num_sensors=R, seed=seed)
+    env.reset()
+    _REF_ENV = (env, rs)
+
+
+def _ref_step(inner):
+    env, rs = _REF_ENV
+    for _ in range(inner):
+        a = rs.uniform(-1, 1, size=(env.E, env.A, 2)).astype(np.float32)
+        a[..., 1] = np.abs(a[..., 1])
+        env.step(a)
+    return env.E * env.A * inner
+
+
+def _cpu_quota():
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        return None if q == 'max' else float(q) / float(per)
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, wl, rank, world):
-    """--impl reference: the oracle port on all host cores (the reference itself
-    is Python under /root/reference and does not exist on the GPU box)."""
+    """--impl reference: the reference's CPU path on all host cores.  The reference is
+    Python under /root/reference and does not exist on the GPU box, so this times the
+    oracle port (oracle/racing_oracle.py), one independent process per core, each
+    stepping its own batch of environments -- the embarrassingly parallel CPU
+    deployment of BASELINE.md section 3."""
     if rank != 0:
         return
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    E_proc, inner = 32, 3
+    E_proc, inner = 32, 2
     ctx = mp.get_context('fork')
-    with ctx.Pool(cores) as pool:
-        jobs = [(wl['kind'], wl['A'], wl['R'], E_proc, inner, 100 + i) for i in range(cores)]
-        for _ in range(max(args.warmup, 1) - 1):
-            pool.map(_oracle_shard, jobs)
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(wl['kind'], wl['A'], wl['R'], E_proc, 100)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_step, [1] * cores, chunksize=1)
         t0 = time.perf_counter()
+        units = 0
         for _ in range(args.steps):
-            pool.map(_oracle_shard, jobs)
+            units += sum(pool.map(_ref_step, [inner] * cores, chunksize=1))
         wall = time.perf_counter() - t0
-    units = cores * E_proc * wl['A'] * inner * args.steps
     val = units / wall
+    sample = f'each step = {cores} processes x {E_proc} envs x {inner} env-steps of the {wl["kind"]} workload'
     line = {'impl': 'reference', 'metric': 'agent_env_steps_per_sec', 'value': val, 'unit': 'agent-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'sample': f'each step = {cores} processes x {E_proc} envs x {inner} env-steps'},
-            'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{cores} processes x {E_proc} envs x {inner} env-steps per bench step'},
+            'config': {'workload': args.workload, 'sample': sample, 'cgroup_cpu_quota': _cpu_quota()},
+            'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------ GPU arm
+def time_ppo(args, wl, vec, dev, rank, world):
+    """Full self-play PPO iterations on the same batch of environments: device-resident
+    rollout (policy + opponent inference + env step), GAE kernel, clipped-surrogate update
+    (10 epochs x 16 minibatches, KL early stop disabled so that every optimizer step is
+    paid for), NCCL all-reduce of gradients and minibatch statistics when world > 1.
+    SPS = learner transitions per second = world * E * T / seconds per iteration."""
+    import torch
+    import torch.distributed as dist
+    from self_play_racing_b200 import configs
+    from self_play_racing_b200.agent import SelfPlayPPO
+    E, T = wl['E'], args.ppo_steps
+    cfg = configs.self_play_config(num_envs=E, num_steps=T, total_timesteps=10 ** 12, kl_target=1e9)
+    trainer = SelfPlayPPO(vec, cfg, device=str(dev))
+    trainer.opponent_pool = [trainer.snapshot_agent() for _ in range(cfg['pool_size'])]  # pool of 5 snapshots
+    buf = trainer.alloc_buffers()
+    buf['obs'][0].copy_(trainer._reset_all())
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    times = []
+    for it in range(args.ppo_updates + 1):  # first iteration is warm-up
+        trainer.update_opponent()
+        trainer._anneal(it, 100)
+        e0, e1, e2 = ev(), ev(), ev()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        trainer.collect_rollout(buf)
+        e1.record()
+        steps = trainer._learn_from(buf)
+        e2.record()
+        torch.cuda.synchronize(dev)
+        if it > 0:
+            times.append((e0.elapsed_time(e1), e1.elapsed_time(e2), steps))
+    roll = float(np.mean([t[0] for t in times]))
+    upd = float(np.mean([t[1] for t in times]))
+    tot = torch.tensor([roll + upd], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    return {'sps': world * E * T / (total_ms * 1e-3), 'unit': 'learner transitions/s', 'envs_per_gpu': E, 'T': T,
+            'rollout_ms': roll, 'gae_plus_update_ms': upd, 'optimizer_steps': int(times[-1][2]),
+            'update_epochs': cfg['update_epochs'], 'num_minibatches': cfg['num_minibatches'],
+            'kl_early_stop': 'disabled for timing', 'opponent_pool': cfg['pool_size'],
+            'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3)}
+
+
 def fp_peaks(torch, dev):
     """Live FMA-throughput micro-benchmarks: torch has no such kernel, so this
     uses a tiny dependent-chain FMA kernel compiled into librk_b200.so."""
@@ -170,6 +252,9 @@ def main():
     ap.add_argument('--envs', type=int, default=None)
     ap.add_argument('--query', default='culled', choices=['culled', 'exact'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ppo-updates', type=int, default=2,
+                    help='also time N full self-play PPO iterations (rollout + GAE + update); 0 skips')
+    ap.add_argument('--ppo-steps', type=int, default=64, help='rollout length T of the PPO timing')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
@@ -296,6 +381,10 @@ def main():
                'h2d_bytes_per_step': int(vec.h2d_bytes_per_step), 'd2h_bytes_per_step': int(vec.d2h_bytes_per_step),
                'ms_per_step': 1e3 * float(tw.item()) / args.steps}
 
+    ppo = None
+    if args.ppo_updates > 0 and wl['selfplay']:
+        ppo = time_ppo(args, wl, vec, dev, rank, world)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(peaks_path):
@@ -325,11 +414,12 @@ def main():
                            'autoreset': 'next_step', 'actions': 'uniform random, resident in HBM',
                            'opponent': 'frozen MLP snapshot (fused inference kernel)' if wl['selfplay'] else None,
                            'l2': 'flushed between timed steps (256 MiB memset outside the event pair)'},
-                'roofline': roof, 'clocks': clocks, 'gpu_launches': int(launches), 'e2e': e2e}
+                'roofline': roof, 'clocks': clocks, 'gpu_launches': int(launches), 'e2e': e2e, 'ppo': ppo}
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(wl)
         print(json.dumps(line))
-    vec.close()
+    if ppo is None:
+        vec.close()
     if world > 1:
         dist.destroy_process_group()
 

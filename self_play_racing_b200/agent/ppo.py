@@ -25,6 +25,46 @@ from ..backend import flatten_agent, gae as gae_kernel, policy_act
 from ..environment.vec_env import BatchedRacingVecEnv
 
 
+class _SplitKLinearFn(torch.autograd.Function):
+    """y = x W^T + b whose weight/bias gradients are reduced in row chunks.
+
+    A PPO minibatch here has ~10^5 rows and 64 columns, so dW = dY^T X is a
+    64x64 output with a 10^5-long reduction: a plain GEMM maps it onto one or two
+    thread blocks (measured 279 us per layer, profiles/r01_ppo_update_profile.txt).
+    Splitting the rows into chunks turns it into a batched GEMM that fills the
+    GPU, followed by a tiny sum over chunks."""
+    CHUNK = 2048
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        n, m = x.shape[0], _SplitKLinearFn.CHUNK
+        c = n // m
+        xa, dya = x[:c * m].view(c, m, -1), dy[:c * m].view(c, m, -1)
+        dw = torch.bmm(dya.transpose(1, 2), xa).sum(0)
+        db = dya.sum(1).sum(0)
+        if c * m < n:
+            dw = dw + dy[c * m:].t() @ x[c * m:]
+            db = db + dy[c * m:].sum(0)
+        return dx, dw, db
+
+
+class _Linear(nn.Linear):
+    """nn.Linear (same parameters, same state_dict keys) that switches to the
+    chunked-reduction backward for tall training batches."""
+
+    def forward(self, x):
+        if x.dim() == 2 and x.shape[0] >= 4 * _SplitKLinearFn.CHUNK and torch.is_grad_enabled() and self.weight.requires_grad:
+            return _SplitKLinearFn.apply(x, self.weight, self.bias)
+        return super().forward(x)
+
+
 def _ortho(layer, std=np.sqrt(2), bias=0.0):
     torch.nn.init.orthogonal_(layer.weight, std)
     torch.nn.init.constant_(layer.bias, bias)
@@ -41,14 +81,14 @@ class Agent(nn.Module):
         obs_dim = int(np.array(obs_space.shape).prod())
         action_dim = action_space.shape[0]
         self.actor_mu = nn.Sequential(
-            _ortho(nn.Linear(obs_dim, 64)), nn.Tanh(),
-            _ortho(nn.Linear(64, 64)), nn.Tanh(),
-            _ortho(nn.Linear(64, action_dim), std=0.01), nn.Tanh())
+            _ortho(_Linear(obs_dim, 64)), nn.Tanh(),
+            _ortho(_Linear(64, 64)), nn.Tanh(),
+            _ortho(_Linear(64, action_dim), std=0.01), nn.Tanh())
         self.register_buffer('log_std', torch.zeros(action_dim))
         self.critic = nn.Sequential(
-            _ortho(nn.Linear(obs_dim, 64)), nn.Tanh(),
-            _ortho(nn.Linear(64, 64)), nn.Tanh(),
-            _ortho(nn.Linear(64, 1), std=1.0))
+            _ortho(_Linear(obs_dim, 64)), nn.Tanh(),
+            _ortho(_Linear(64, 64)), nn.Tanh(),
+            _ortho(_Linear(64, 1), std=1.0))
 
     def get_value(self, obs):
         return self.critic(obs)

@@ -212,6 +212,23 @@ def test_ppo_update_kl_early_stop():
     assert ppo.ppo_update(adv, returns, values, logp, actions, obs) > 0
 
 
+def test_chunked_linear_backward_equals_plain_linear():
+    from self_play_racing_b200.agent.ppo import _Linear, _SplitKLinearFn
+    torch.manual_seed(0)
+    lin = _Linear(19, 64).double()
+    ref = torch.nn.Linear(19, 64).double()
+    ref.load_state_dict(lin.state_dict())
+    n = 4 * _SplitKLinearFn.CHUNK + 37            # ragged tail exercises the remainder path
+    x = torch.randn(n, 19, dtype=torch.float64, requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    g = torch.randn(n, 64, dtype=torch.float64)
+    lin(x).backward(g)
+    ref(x2).backward(g)
+    torch.testing.assert_close(x.grad, x2.grad)
+    torch.testing.assert_close(lin.weight.grad, ref.weight.grad, rtol=1e-12, atol=1e-10)
+    torch.testing.assert_close(lin.bias.grad, ref.bias.grad, rtol=1e-12, atol=1e-10)
+
+
 # ------------------------------------------------------------------ data parallel, gloo world size 2
 def _dp_worker(rank, world, port, tmp, cfg, n):
     import torch.distributed as dist
