@@ -127,6 +127,20 @@ def test_configs_match_reference_values():
     assert big['batch_size'] == 65536 * 64 and big['minibatch_size'] == big['batch_size'] // 16
 
 
+def test_compat_aliases_resolve_reference_imports():
+    """The import lines of the reference's train.py / evaluate.py resolve to the mirrors."""
+    import subprocess
+    code = ('from self_play_racing_b200.compat import install_as_reference_modules as f; f();'
+            'from environment.racing_env import RacingEnv; from environment.multi_racing_env import MultiRacingEnv;'
+            'from environment.track import gen_tracks; from environment.wrappers import SelfPlayWrapper;'
+            'from agent.ppo import PPO, Agent; from agent.self_play_ppo import SelfPlayPPO;'
+            'from configs.base_config import hyperparams_config as b; from configs.self_play_config import hyperparams_config as s;'
+            'import self_play_racing_b200.environment.racing_env as m; assert RacingEnv is m.RacingEnv; print(s()["pool_size"])')
+    out = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == '5'
+
+
 # ------------------------------------------------------------------ PPO update
 def _fake_ppo(config, seed=3):
     """A PPO object with an Agent but no environment (update math is pure torch)."""
