@@ -95,10 +95,70 @@ class Agent(nn.Module):
 
     def get_action_and_value(self, obs, action=None):
         mu = self.actor_mu(obs)
-        dist = torch.distributions.Normal(mu, torch.exp(self.log_std).expand_as(mu))
+        # validate_args=False: the argument checks synchronise with the host, which CUDA-graph capture forbids
+        dist = torch.distributions.Normal(mu, torch.exp(self.log_std).expand_as(mu), validate_args=False)
         if action is None:
             action = torch.clamp(dist.sample(), -1.0, 1.0)
         return action, dist.log_prob(action).sum(-1), dist.entropy().sum(-1), self.critic(obs)
+
+
+class _GraphedMinibatch:
+    """Static buffers + two captured CUDA graphs for one PPO minibatch step."""
+
+    def __init__(self, ppo, mb, obs_dim):
+        dev, c = ppo.device, ppo.config
+        self.mb = mb
+        z = lambda *shape, dt=torch.float32: torch.zeros(*shape, device=dev, dtype=dt)
+        self.obs, self.act = z(mb, obs_dim), z(mb, 2)
+        self.old_logp, self.adv, self.ret, self.val = z(mb), z(mb), z(mb), z(mb)
+        self.adv_mean, self.adv_std = z(()), torch.ones((), device=dev)
+        self.kl_sum = z((), dt=torch.float64)
+        params = [p for p in ppo.agent.parameters()]
+        self.flat_grad = z(sum(p.numel() for p in params))
+        world = ppo.world
+        opt = ppo.optimizer
+
+        def fwd_bwd():
+            opt.zero_grad(set_to_none=False)
+            loss, kl = ppo._losses(self.obs, self.act, self.old_logp, self.adv, self.ret, self.val,
+                                   self.adv_mean, self.adv_std)
+            self.kl_sum.copy_(kl)
+            loss.backward()
+            if world > 1:
+                torch.cat([p.grad.reshape(-1) for p in params], out=self.flat_grad)
+
+        def clip_step():
+            if world > 1:
+                off = 0
+                for p in params:
+                    p.grad.copy_(self.flat_grad[off:off + p.numel()].view_as(p)).div_(world)
+                    off += p.numel()
+            nn.utils.clip_grad_norm_(params, c['max_grad_norm'], foreach=True)
+            opt.step()
+
+        # warm-up on a side stream (allocates grads and Adam state), then restore the
+        # parameters and the optimizer state IN PLACE so that training is unaffected
+        saved_p = [p.detach().clone() for p in params]
+        had_state = {id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt.state[p].items()}
+                     for p in params if p in opt.state and len(opt.state[p])}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fwd_bwd()
+                clip_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():
+            for p, q in zip(params, saved_p):
+                p.copy_(q)
+                for k, v in opt.state[p].items():
+                    if torch.is_tensor(v):
+                        v.copy_(had_state[id(p)][k]) if id(p) in had_state else v.zero_()
+        self.fwd_bwd, self.clip_step = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd_bwd):
+            fwd_bwd()
+        with torch.cuda.graph(self.clip_step, pool=self.fwd_bwd.pool()):
+            clip_step()
 
 
 def _dist_ready():
@@ -119,9 +179,27 @@ class PPO:
         np.random.seed(config['seed'])
         torch.manual_seed(config['seed'])
         self.agent = Agent(self.envs.single_observation_space, self.envs.single_action_space).to(self.device)
-        self.optimizer = optim.Adam(self.agent.parameters(), lr=config['learning_rate'], eps=1e-5)
+        self.optimizer = self._make_optimizer()
         self._act_counter = 0
         self._perm_gen = None
+        self._graphed = None
+
+    def _make_optimizer(self):
+        """Adam(lr 3e-4, eps 1e-5) as agent/ppo.py:83.  On CUDA it is created
+        capturable with a tensor learning rate so that the minibatch step can be
+        replayed as a CUDA graph while the learning rate is annealed in place."""
+        c = self.config
+        if self.device.type == 'cuda':
+            lr = torch.tensor(float(c['learning_rate']), device=self.device)
+            return optim.Adam(self.agent.parameters(), lr=lr, eps=1e-5, capturable=True, foreach=True)
+        return optim.Adam(self.agent.parameters(), lr=c['learning_rate'], eps=1e-5)
+
+    def _set_lr(self, value):
+        g = self.optimizer.param_groups[0]
+        if isinstance(g['lr'], torch.Tensor):
+            g['lr'].fill_(float(value))
+        else:
+            g['lr'] = float(value)
 
     # ---- env construction (agent/ppo.py:70,85-95) ------------------------------
     def _make_env(self, env_fn, seed, env_idx):
@@ -183,10 +261,27 @@ class PPO:
             self._perm_gen.manual_seed(self.config['seed'] + 12345)
         return torch.randperm(n, device=device, generator=self._perm_gen)
 
+    def _losses(self, mb_obs, mb_act, old_logp, mb_adv, ret, v_old, adv_mean, adv_std):
+        """Clipped surrogate + clipped value loss + entropy bonus of one minibatch
+        (agent/ppo.py:173-204).  Returns (loss, sum(old_logp - new_logp))."""
+        c = self.config
+        _, new_logp, entropy, new_v = self.agent.get_action_and_value(mb_obs, mb_act)
+        logratio = new_logp - old_logp
+        ratio = logratio.exp()
+        adv = (mb_adv - adv_mean) / (adv_std + 1e-8)
+        pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - c['clip_coef'], 1 + c['clip_coef'])).mean()
+        new_v = new_v.flatten()
+        v_clip = v_old + torch.clamp(new_v - v_old, -c['clip_coef'], c['clip_coef'])
+        v_loss = 0.5 * torch.max((new_v - ret) ** 2, (v_clip - ret) ** 2).mean()
+        loss = pg_loss + c['ent_coef'] * (-entropy.mean()) + c['vf_coef'] * v_loss
+        return loss, (-logratio).detach().sum()
+
     def ppo_update(self, advantages, returns, values, logprobs, actions, obs, permutation=None):
         """Flat [B, ...] tensors of THIS rank's share of the batch.  Returns the
         number of optimizer steps taken (the KL early stop aborts the update)."""
         c = self.config
+        if obs.is_cuda and c.get('cuda_graph_update', True):
+            return self._ppo_update_graphed(advantages, returns, values, logprobs, actions, obs, permutation)
         b_obs = obs.reshape(-1, obs.shape[-1])
         b_actions = actions.reshape(-1, actions.shape[-1])
         b_logprobs, b_adv = logprobs.reshape(-1), advantages.reshape(-1)
@@ -240,11 +335,61 @@ class PPO:
                 n_steps += 1
         return n_steps
 
+
+    # ---- the same update with the minibatch step replayed as two CUDA graphs ----------------
+    def _ppo_update_graphed(self, advantages, returns, values, logprobs, actions, obs, permutation=None):
+        """ppo_update for CUDA tensors.  Per minibatch: gather into static buffers and
+        global advantage statistics (eager, a handful of launches), graph 1 = forward +
+        losses + backward, then the KL early-stop test of agent/ppo.py:178-182 on the
+        host (the only synchronisation; the step is NOT applied when it fires, as in
+        the reference), graph 2 = gradient clipping + Adam.  With world > 1 the flat
+        gradient and the KL sum are all-reduced between the two graphs."""
+        c = self.config
+        b_obs = obs.reshape(-1, obs.shape[-1])
+        b_actions = actions.reshape(-1, actions.shape[-1])
+        b_logprobs, b_adv = logprobs.reshape(-1), advantages.reshape(-1)
+        b_returns, b_values = returns.reshape(-1), values.reshape(-1)
+        n_local = b_obs.shape[0]
+        mb = max(n_local // c['num_minibatches'], 1)
+        g = self._graphed
+        if g is None or g.mb != mb or g.obs.shape[1] != b_obs.shape[1]:
+            g = self._graphed = _GraphedMinibatch(self, mb, b_obs.shape[1])
+        n_steps = 0
+        n_glob = float(mb * self.world)
+        for epoch in range(c['update_epochs']):
+            perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
+            for start in range(0, n_local - mb + 1, mb):
+                idx = perm[start:start + mb]
+                torch.index_select(b_obs, 0, idx, out=g.obs)
+                torch.index_select(b_actions, 0, idx, out=g.act)
+                torch.index_select(b_logprobs, 0, idx, out=g.old_logp)
+                torch.index_select(b_adv, 0, idx, out=g.adv)
+                torch.index_select(b_returns, 0, idx, out=g.ret)
+                torch.index_select(b_values, 0, idx, out=g.val)
+                a64 = g.adv.double()
+                stats = torch.stack([a64.sum(), (a64 * a64).sum()])
+                self._all_reduce(stats)
+                mean = stats[0] / n_glob
+                g.adv_mean.copy_(mean)
+                g.adv_std.copy_(((stats[1] - n_glob * mean * mean) / (n_glob - 1)).clamp_min(0).sqrt())
+                g.fwd_bwd.replay()
+                if self.world > 1:
+                    self._all_reduce(g.kl_sum)
+                    self._all_reduce(g.flat_grad)
+                approx_kl = float(g.kl_sum) / n_glob  # host sync: the early-stop test needs the value
+                if approx_kl > c['kl_target']:
+                    if self.rank == 0:
+                        print(f'  Early stopping at epoch {epoch + 1} due to KL divergence: {approx_kl:.4f}')
+                    return n_steps
+                g.clip_step.replay()
+                n_steps += 1
+        return n_steps
+
     # ---- training loop (agent/ppo.py:211-287) ---------------------------------------------
     def _anneal(self, update, num_updates):
         c = self.config
         frac = max(0.0, 1.0 - update / num_updates)
-        self.optimizer.param_groups[0]['lr'] = frac * c['learning_rate']
+        self._set_lr(frac * c['learning_rate'])
         lo, hi = self.LOG_STD_RANGE
         self.agent.log_std.data.fill_(frac * lo + (1 - frac) * hi)
         return frac

@@ -199,3 +199,38 @@ def test_single_ppo_learns_something(pkg):
     assert len(r) >= 8 and np.isfinite(r).all()
     assert np.mean(r[-3:]) > np.mean(r[:3])
     trainer.envs.close()
+
+
+def test_graphed_update_equals_eager_update(pkg):
+    """The CUDA-graph replay of the minibatch step (default on the GPU) gives the
+    same parameters as the eager step-by-step update, and honours the KL stop."""
+    env_mod, agent_mod, configs = pkg
+    results = []
+    for graphed in (False, True):
+        cfg = configs.base_config(num_envs=64, num_steps=64, update_epochs=2, num_minibatches=4, kl_target=1e9,
+                                  cuda_graph_update=graphed)
+        vec = env_mod.BatchedRacingVecEnv.synthetic('single', 64, n_tracks=4, seed=0)
+        tr = agent_mod.PPO(vec, cfg, device='cuda')
+        g = torch.Generator(device='cuda').manual_seed(0)
+        n = cfg['batch_size']
+        obs = torch.rand(n, 15, device='cuda', generator=g) * 2 - 1
+        act = torch.rand(n, 2, device='cuda', generator=g) * 2 - 1
+        adv = torch.randn(n, device='cuda', generator=g)
+        val = torch.randn(n, device='cuda', generator=g)
+        with torch.no_grad():
+            _, logp, _, _ = tr.agent.get_action_and_value(obs, act)
+        logp = logp + 0.05 * torch.randn(n, device='cuda', generator=g)
+        perms = [torch.randperm(n, device='cuda', generator=g) for _ in range(cfg['update_epochs'])]
+        tr._anneal(3, 10)  # exercises the in-place learning-rate tensor
+        steps = tr.ppo_update(adv, val + adv, val, logp, act, obs, permutation=lambda ep: perms[ep])
+        assert steps == 8
+        results.append([p.detach().clone() for p in tr.agent.parameters()])
+        # KL stop: nothing is applied when the very first minibatch exceeds the target
+        tr.config['kl_target'] = 0.015
+        before = [p.detach().clone() for p in tr.agent.parameters()]
+        assert tr.ppo_update(adv, val + adv, val, logp + 1.0, act, obs, permutation=lambda ep: perms[ep]) == 0
+        for a, b in zip(before, tr.agent.parameters()):
+            assert torch.equal(a, b)
+        vec.close()
+    for a, b in zip(*results):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
