@@ -164,9 +164,13 @@ RK_API int rk_gae(const float* rewards, const float* values, const float* dones,
 
 /* Fused policy inference: Agent.get_action_and_value with action=None
  * (agent/ppo.py:43-56) for a batch of B observations of width obs_dim.
- * params: the Agent state_dict flattened in registration order
- *   actor_mu.{0,2,4}.{weight,bias}, log_std, critic.{0,2,4}.{weight,bias}
- * (float32, row-major [out,in] weights as torch stores them).  obs rows are
+ * params: the Agent state_dict packed for the kernel (float32, 16-byte aligned,
+ * rk_policy_param_count(obs_dim) values, zero padded).  Hidden-layer weights are
+ * stored TRANSPOSED, [in][out] row-major (torch stores [out][in]):
+ *   actor_mu.0.weight^T, actor_mu.0.bias, actor_mu.2.weight^T, actor_mu.2.bias,
+ *   actor_mu.4.weight [2][64], actor_mu.4.bias, log_std,
+ *   critic.0.weight^T, critic.0.bias, critic.2.weight^T, critic.2.bias,
+ *   critic.4.weight [64], critic.4.bias.  obs rows are
  * obs_stride floats apart, action rows act_stride floats apart (so a car's
  * slice of an [E,A,*] tensor can be read/written in place).  Normal samples
  * come from Philox(seed, counter).  logprob [B], value [B] and mean [B,2] (the
@@ -177,7 +181,7 @@ RK_API int rk_gae(const float* rewards, const float* values, const float* dones,
 RK_API int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
                   uint64_t seed, uint64_t counter, float* action, int64_t act_stride,
                   float* logprob, float* value, float* mean, void* stream);
-/* number of float32 values in the flattened Agent for a given obs_dim/action_dim=2 */
+/* number of float32 values in the packed Agent block for a given obs_dim (action_dim = 2) */
 RK_API int rk_policy_param_count(int32_t obs_dim);
 
 /* ---- measurement aid --------------------------------------------------------- */

@@ -237,9 +237,21 @@ PARAM_ORDER = ['actor_mu.0.weight', 'actor_mu.0.bias', 'actor_mu.2.weight', 'act
                'critic.4.weight', 'critic.4.bias']
 
 
+_TRANSPOSED = {'actor_mu.0.weight', 'actor_mu.2.weight', 'critic.0.weight', 'critic.2.weight'}
+
+
 def flatten_agent(state_dict, out=None):
-    """Agent state_dict (agent/ppo.py:11-37) -> one float32 vector in PARAM_ORDER."""
-    flat = torch.cat([state_dict[k].detach().reshape(-1).to(torch.float32) for k in PARAM_ORDER])
+    """Agent state_dict (agent/ppo.py:11-37) -> the packed float32 block
+    rk_policy_act expects (see racing_b200.h): PARAM_ORDER, hidden-layer weights
+    transposed to [in][out], zero padded to a multiple of 4 floats."""
+    parts = []
+    for k in PARAM_ORDER:
+        v = state_dict[k].detach().to(torch.float32)
+        parts.append((v.t().contiguous() if k in _TRANSPOSED else v).reshape(-1))
+    flat = torch.cat(parts)
+    pad = (-flat.numel()) % 4
+    if pad:
+        flat = torch.cat([flat, flat.new_zeros(pad)])
     if out is not None:
         out.copy_(flat)
         return out

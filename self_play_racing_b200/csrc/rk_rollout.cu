@@ -5,6 +5,7 @@
 //                        opponent of SelfPlayWrapper.step
 //                        (environment/wrappers.py:29-39)
 #include <math.h>
+#include <stdint.h>
 
 #include "rk_types.cuh"
 
@@ -38,142 +39,153 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
 }
 
 constexpr int kHidden = 64;
-constexpr int kPolicyThreads = 128;
+constexpr int kPolicyThreads = 128;           // threads per CTA
+constexpr int kSamplesPerThread = 2;          // register tile: every weight fetched feeds 2 samples
+constexpr int kPolicyCols = kPolicyThreads * kSamplesPerThread;
 
-// y[j] = b[j] + sum_i Wt[i][j] * x[i], weights transposed in shared memory so
-// that a float4 broadcast load feeds four FMAs.
-// x lives in shared memory, one column per thread (stride kPolicyThreads), so
-// the loop over inputs can stay rolled without dynamic register indexing.
-template <int NIN>
-__device__ __forceinline__ void dense64(const float* __restrict__ wt, const float* __restrict__ b,
-                                        const float* xs, float* y) {
-#pragma unroll
-    for (int j = 0; j < kHidden; ++j) y[j] = b[j];
-#pragma unroll 4
-    for (int i = 0; i < NIN; ++i) {
-        const float xi = xs[i * kPolicyThreads];
-        const float4* row = reinterpret_cast<const float4*>(wt + i * kHidden);
-#pragma unroll
-        for (int j4 = 0; j4 < kHidden / 4; ++j4) {
-            const float4 w = row[j4];
-            y[4 * j4 + 0] = fmaf(w.x, xi, y[4 * j4 + 0]);
-            y[4 * j4 + 1] = fmaf(w.y, xi, y[4 * j4 + 1]);
-            y[4 * j4 + 2] = fmaf(w.z, xi, y[4 * j4 + 2]);
-            y[4 * j4 + 3] = fmaf(w.w, xi, y[4 * j4 + 3]);
-        }
-    }
+// Packed parameter block (floats), produced by backend.flatten_agent(): every weight
+// matrix of a hidden layer is stored TRANSPOSED ([in][out], so one float4 broadcast
+// load feeds four output neurons), padded to a multiple of 4 floats for the bulk copy:
+//   actor : W0t[obs][64] b0[64] W2t[64][64] b2[64] W4[2][64] b4[2] log_std[2]
+//   critic: W0t[obs][64] b0[64] W2t[64][64] b2[64] W4[64] b4[1]  (+ padding)
+__host__ __device__ inline int policy_packed_floats(int obs_dim) {
+    const int n = 2 * (obs_dim * kHidden + kHidden + kHidden * kHidden + kHidden) + (2 * kHidden + 2) + 2 + (kHidden + 1);
+    return (n + 3) / 4 * 4;
 }
 
-// Generic-input first layer (obs_dim is a runtime value, x in registers up to 96 wide)
-__device__ __forceinline__ void dense_in(const float* __restrict__ wt, const float* __restrict__ b, int nin,
-                                         const float* __restrict__ obs_row, float* y) {
+// tanh through ex2.approx + rcp.approx: |error| < 2e-7 absolute, 6 instructions
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+// y[s][j] = b[j] + sum_i Wt[i][j] * x_s[i] for the thread's two samples.  x lives
+// in shared memory, one column per sample (stride kPolicyCols), so the loop over
+// inputs stays rolled with static register indexing of the 2 x 64 accumulators.
+__device__ __forceinline__ void dense2(const float* __restrict__ wt, const float* __restrict__ b, int nin,
+                                       const float* xs, float (&y0)[kHidden], float (&y1)[kHidden]) {
 #pragma unroll
-    for (int j = 0; j < kHidden; ++j) y[j] = b[j];
+    for (int j = 0; j < kHidden; ++j) { y0[j] = b[j]; y1[j] = b[j]; }
+#pragma unroll 2
     for (int i = 0; i < nin; ++i) {
-        const float xi = obs_row[i];
+        const float xa = xs[i * kPolicyCols], xb = xs[i * kPolicyCols + kPolicyThreads];
         const float4* row = reinterpret_cast<const float4*>(wt + i * kHidden);
 #pragma unroll
         for (int j4 = 0; j4 < kHidden / 4; ++j4) {
             const float4 w = row[j4];
-            y[4 * j4 + 0] = fmaf(w.x, xi, y[4 * j4 + 0]);
-            y[4 * j4 + 1] = fmaf(w.y, xi, y[4 * j4 + 1]);
-            y[4 * j4 + 2] = fmaf(w.z, xi, y[4 * j4 + 2]);
-            y[4 * j4 + 3] = fmaf(w.w, xi, y[4 * j4 + 3]);
+            y0[4 * j4 + 0] = fmaf(w.x, xa, y0[4 * j4 + 0]); y1[4 * j4 + 0] = fmaf(w.x, xb, y1[4 * j4 + 0]);
+            y0[4 * j4 + 1] = fmaf(w.y, xa, y0[4 * j4 + 1]); y1[4 * j4 + 1] = fmaf(w.y, xb, y1[4 * j4 + 1]);
+            y0[4 * j4 + 2] = fmaf(w.z, xa, y0[4 * j4 + 2]); y1[4 * j4 + 2] = fmaf(w.z, xb, y1[4 * j4 + 2]);
+            y0[4 * j4 + 3] = fmaf(w.w, xa, y0[4 * j4 + 3]); y1[4 * j4 + 3] = fmaf(w.w, xb, y1[4 * j4 + 3]);
         }
     }
 }
 
-// shared-memory layout (floats): [actor W0t | b0 | W2t | b2 | W4 | b4 | log_std | critic W0t | b0 | W2t | b2 | W4 | b4]
-__global__ void __launch_bounds__(kPolicyThreads)
+__device__ __forceinline__ void stage_obs(float* xs, const float* __restrict__ obs, int64_t obs_stride, int obs_dim,
+                                          int b0, int b1, int B) {
+    for (int i = 0; i < obs_dim; ++i) {
+        xs[i * kPolicyCols] = (b0 < B) ? obs[(size_t)b0 * obs_stride + i] : 0.f;
+        xs[i * kPolicyCols + kPolicyThreads] = (b1 < B) ? obs[(size_t)b1 * obs_stride + i] : 0.f;
+    }
+}
+
+// Fused Agent.get_action_and_value(obs) (agent/ppo.py:43-56).  The packed
+// parameter block arrives in shared memory through ONE bulk asynchronous copy
+// (cp.async.bulk -> mbarrier) while the threads stage their observations.
+__global__ void __launch_bounds__(kPolicyThreads, 2)
 policy_act_kernel(const float* __restrict__ params, int obs_dim, const float* __restrict__ obs, int64_t obs_stride,
                   int B, uint64_t seed, uint64_t counter, float* __restrict__ action, int64_t act_stride,
                   float* __restrict__ logprob, float* __restrict__ value, float* __restrict__ mean) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int n_packed = policy_packed_floats(obs_dim);
     const int n0 = obs_dim * kHidden;
-    float* aW0 = sm;            float* ab0 = aW0 + n0;
-    float* aW2 = ab0 + kHidden; float* ab2 = aW2 + kHidden * kHidden;
-    float* aW4 = ab2 + kHidden; float* ab4 = aW4 + 2 * kHidden;
-    float* lstd = ab4 + 2;
-    float* cW0 = lstd + 2;      float* cb0 = cW0 + n0;
-    float* cW2 = cb0 + kHidden; float* cb2 = cW2 + kHidden * kHidden;
-    float* cW4 = cb2 + kHidden;
-    float* hbuf = cW4 + kHidden + 4 + threadIdx.x;  // [kHidden][kPolicyThreads] activations, column per thread
-    {
-        // global layout: torch [out, in] row-major, in state-dict order (see racing_b200.h)
-        const float* g = params;
-        for (int k = threadIdx.x; k < n0; k += blockDim.x) aW0[(k % obs_dim) * kHidden + k / obs_dim] = g[k];
-        g += n0;
-        for (int k = threadIdx.x; k < kHidden; k += blockDim.x) ab0[k] = g[k];
-        g += kHidden;
-        for (int k = threadIdx.x; k < kHidden * kHidden; k += blockDim.x) aW2[(k % kHidden) * kHidden + k / kHidden] = g[k];
-        g += kHidden * kHidden;
-        for (int k = threadIdx.x; k < kHidden; k += blockDim.x) ab2[k] = g[k];
-        g += kHidden;
-        for (int k = threadIdx.x; k < 2 * kHidden + 2 + 2; k += blockDim.x) aW4[k] = g[k];  // W4, b4, log_std
-        g += 2 * kHidden + 4;
-        if (value != nullptr) {
-            for (int k = threadIdx.x; k < n0; k += blockDim.x) cW0[(k % obs_dim) * kHidden + k / obs_dim] = g[k];
-            g += n0;
-            for (int k = threadIdx.x; k < kHidden; k += blockDim.x) cb0[k] = g[k];
-            g += kHidden;
-            for (int k = threadIdx.x; k < kHidden * kHidden; k += blockDim.x) cW2[(k % kHidden) * kHidden + k / kHidden] = g[k];
-            g += kHidden * kHidden;
-            for (int k = threadIdx.x; k < kHidden; k += blockDim.x) cb2[k] = g[k];
-            g += kHidden;
-            for (int k = threadIdx.x; k < kHidden + 1; k += blockDim.x) cW4[k] = g[k];
-        }
+    const float* aW0 = sm;             const float* ab0 = aW0 + n0;
+    const float* aW2 = ab0 + kHidden;  const float* ab2 = aW2 + kHidden * kHidden;
+    const float* aW4 = ab2 + kHidden;  const float* ab4 = aW4 + 2 * kHidden;
+    const float* lstd = ab4 + 2;
+    const float* cW0 = lstd + 2;       const float* cb0 = cW0 + n0;
+    const float* cW2 = cb0 + kHidden;  const float* cb2 = cW2 + kHidden * kHidden;
+    const float* cW4 = cb2 + kHidden;
+    float* xs = sm + n_packed + threadIdx.x;  // this thread's two activation columns
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)n_packed * 4u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(sm)), "l"(params), "r"(bytes), "r"(bar_addr) : "memory");
     }
-    __syncthreads();
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float* orow = obs + (size_t)b * obs_stride;
-    float h1[kHidden], h2[kHidden];
+    const int b0 = blockIdx.x * kPolicyCols + threadIdx.x, b1 = b0 + kPolicyThreads;
+    stage_obs(xs, obs, obs_stride, obs_dim, b0, b1, B);
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_addr) : "memory");
+    }
+    float y0[kHidden], y1[kHidden];
     // actor: Linear-Tanh-Linear-Tanh-Linear-Tanh (ppo.py:19-26)
-    dense_in(aW0, ab0, obs_dim, orow, h1);
-#pragma unroll
-    for (int j = 0; j < kHidden; ++j) hbuf[j * kPolicyThreads] = tanhf(h1[j]);
-    dense64<kHidden>(aW2, ab2, hbuf, h2);
-    float m0 = ab4[0], m1 = ab4[1];
+    dense2(aW0, ab0, obs_dim, xs, y0, y1);
 #pragma unroll
     for (int j = 0; j < kHidden; ++j) {
-        const float t = tanhf(h2[j]);
-        m0 = fmaf(aW4[j], t, m0);
-        m1 = fmaf(aW4[kHidden + j], t, m1);
+        xs[j * kPolicyCols] = tanh_fast(y0[j]);
+        xs[j * kPolicyCols + kPolicyThreads] = tanh_fast(y1[j]);
     }
-    m0 = tanhf(m0);
-    m1 = tanhf(m1);
-    if (mean != nullptr) {
-        mean[2 * (size_t)b] = m0;
-        mean[2 * (size_t)b + 1] = m1;
+    dense2(aW2, ab2, kHidden, xs, y0, y1);
+    float m[2][2] = {{ab4[0], ab4[1]}, {ab4[0], ab4[1]}};
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) {
+        const float t0 = tanh_fast(y0[j]), t1 = tanh_fast(y1[j]);
+        m[0][0] = fmaf(aW4[j], t0, m[0][0]); m[0][1] = fmaf(aW4[kHidden + j], t0, m[0][1]);
+        m[1][0] = fmaf(aW4[j], t1, m[1][0]); m[1][1] = fmaf(aW4[kHidden + j], t1, m[1][1]);
     }
-    // a ~ N(mu, exp(log_std)) clamped to [-1, 1] (ppo.py:47-54); Box-Muller on Philox
-    uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x706f6c79u};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const float rad = sqrtf(-2.f * logf(u01(c[0])));
-    float sn, cs;
-    sincosf(6.2831853071795865f * u01(c[1]), &sn, &cs);
-    const float s0 = expf(lstd[0]), s1 = expf(lstd[1]);
-    const float a0 = fminf(fmaxf(fmaf(s0, rad * cs, m0), -1.f), 1.f);
-    const float a1 = fminf(fmaxf(fmaf(s1, rad * sn, m1), -1.f), 1.f);
-    action[(size_t)b * act_stride] = a0;
-    action[(size_t)b * act_stride + 1] = a1;
-    if (logprob != nullptr) {
-        // torch Normal.log_prob: -(a-mu)^2 / (2 var) - log_std - log(sqrt(2 pi)), summed (ppo.py:56)
-        const float kLogSqrt2Pi = 0.9189385332046727f;
-        const float l0 = -((a0 - m0) * (a0 - m0)) / (2.f * s0 * s0) - lstd[0] - kLogSqrt2Pi;
-        const float l1 = -((a1 - m1) * (a1 - m1)) / (2.f * s1 * s1) - lstd[1] - kLogSqrt2Pi;
-        logprob[b] = l0 + l1;
+    const float s0 = __expf(lstd[0]), s1 = __expf(lstd[1]);
+#pragma unroll
+    for (int s = 0; s < kSamplesPerThread; ++s) {
+        const int b = s ? b1 : b0;
+        if (b >= B) continue;
+        const float m0 = tanh_fast(m[s][0]), m1 = tanh_fast(m[s][1]);
+        if (mean != nullptr) {
+            mean[2 * (size_t)b] = m0;
+            mean[2 * (size_t)b + 1] = m1;
+        }
+        // a ~ N(mu, exp(log_std)) clamped to [-1, 1] (ppo.py:47-54); Box-Muller on Philox
+        uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x706f6c79u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float rad = sqrtf(-2.f * logf(u01(c[0])));
+        float sn, cs;
+        sincosf(6.2831853071795865f * u01(c[1]), &sn, &cs);
+        const float a0 = fminf(fmaxf(fmaf(s0, rad * cs, m0), -1.f), 1.f);
+        const float a1 = fminf(fmaxf(fmaf(s1, rad * sn, m1), -1.f), 1.f);
+        action[(size_t)b * act_stride] = a0;
+        action[(size_t)b * act_stride + 1] = a1;
+        if (logprob != nullptr) {
+            // torch Normal.log_prob: -(a-mu)^2 / (2 var) - log_std - log(sqrt(2 pi)), summed (ppo.py:56)
+            const float kLogSqrt2Pi = 0.9189385332046727f;
+            const float l0 = -((a0 - m0) * (a0 - m0)) / (2.f * s0 * s0) - lstd[0] - kLogSqrt2Pi;
+            const float l1 = -((a1 - m1) * (a1 - m1)) / (2.f * s1 * s1) - lstd[1] - kLogSqrt2Pi;
+            logprob[b] = l0 + l1;
+        }
     }
     if (value != nullptr) {
-        // critic: Linear-Tanh-Linear-Tanh-Linear (ppo.py:31-37)
-        dense_in(cW0, cb0, obs_dim, orow, h1);
+        // critic: Linear-Tanh-Linear-Tanh-Linear (ppo.py:31-37); the activation columns were
+        // overwritten by the actor, so the observations are staged again (L2 resident)
+        stage_obs(xs, obs, obs_stride, obs_dim, b0, b1, B);
+        dense2(cW0, cb0, obs_dim, xs, y0, y1);
 #pragma unroll
-        for (int j = 0; j < kHidden; ++j) hbuf[j * kPolicyThreads] = tanhf(h1[j]);
-        dense64<kHidden>(cW2, cb2, hbuf, h2);
-        float v = cW4[kHidden];
+        for (int j = 0; j < kHidden; ++j) {
+            xs[j * kPolicyCols] = tanh_fast(y0[j]);
+            xs[j * kPolicyCols + kPolicyThreads] = tanh_fast(y1[j]);
+        }
+        dense2(cW2, cb2, kHidden, xs, y0, y1);
+        float v0 = cW4[kHidden], v1 = cW4[kHidden];
 #pragma unroll
-        for (int j = 0; j < kHidden; ++j) v = fmaf(cW4[j], tanhf(h2[j]), v);
-        value[b] = v;
+        for (int j = 0; j < kHidden; ++j) {
+            v0 = fmaf(cW4[j], tanh_fast(y0[j]), v0);
+            v1 = fmaf(cW4[j], tanh_fast(y1[j]), v1);
+        }
+        if (b0 < B) value[b0] = v0;
+        if (b1 < B) value[b1] = v1;
     }
 }
 
@@ -200,9 +212,7 @@ int launch_gae(const float* rewards, const float* values, const float* dones, co
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int policy_param_count(int obs_dim) {
-    return 2 * (obs_dim * kHidden + kHidden + kHidden * kHidden + kHidden) + (2 * kHidden + 2) + 2 + (kHidden + 1);
-}
+int policy_param_count(int obs_dim) { return policy_packed_floats(obs_dim); }
 
 int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B, uint64_t seed,
                       uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
@@ -213,13 +223,14 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
         count_launch();
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
-    const size_t smem = ((size_t)policy_param_count(obs_dim) + 8 + (size_t)kHidden * kPolicyThreads) * sizeof(float);
+    if ((reinterpret_cast<uintptr_t>(params) & 15u) != 0) return 2;  // the bulk copy needs a 16-byte aligned source
+    const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    policy_act_kernel<<<(B + kPolicyThreads - 1) / kPolicyThreads, kPolicyThreads, smem, stream>>>(
+    policy_act_kernel<<<(B + kPolicyCols - 1) / kPolicyCols, kPolicyThreads, smem, stream>>>(
         params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

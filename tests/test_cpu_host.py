@@ -114,7 +114,8 @@ def test_agent_matches_reference_init_and_forward(golden):
     np.testing.assert_allclose(val.numpy(), g['value'], atol=1e-6)
     assert a.abs().max() <= 1
     flat = flatten_agent(sd)
-    assert flat.numel() == 11077 and set(PARAM_ORDER) == set(sd)
+    assert flat.numel() == 11080 and set(PARAM_ORDER) == set(sd)
+    np.testing.assert_array_equal(flat[:19 * 64].view(19, 64).numpy(), sd['actor_mu.0.weight'].t().numpy())
 
 
 def test_configs_match_reference_values():

@@ -318,7 +318,7 @@ def test_policy_act_matches_torch_agent(B, golden):
     g = golden('agent')
     sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')}
     params = B.flatten_agent(sd).cuda()
-    assert params.numel() == 11077
+    assert params.numel() == 11080  # 11,075 parameters + log_std (2), padded to a multiple of 4
     obs = torch.from_numpy(g['obs']).cuda()
     n = obs.shape[0]
     act = torch.zeros(n, 2, device='cuda'); lp = torch.zeros(n, device='cuda')
