@@ -194,7 +194,8 @@ def time_ppo(args, wl, vec, dev, rank, world):
     from self_play_racing_b200 import configs
     from self_play_racing_b200.agent import SelfPlayPPO
     E, T = wl['E'], args.ppo_steps
-    cfg = configs.self_play_config(num_envs=E, num_steps=T, total_timesteps=10 ** 12, kl_target=1e9)
+    cfg = configs.self_play_config(num_envs=E, num_steps=T, total_timesteps=10 ** 12, kl_target=1e9,
+                                   update_matmul_precision=args.ppo_precision)
     trainer = SelfPlayPPO(vec, cfg, device=str(dev))
     trainer.opponent_pool = [trainer.snapshot_agent() for _ in range(cfg['pool_size'])]  # pool of 5 snapshots
     buf = trainer.alloc_buffers()
@@ -226,6 +227,7 @@ def time_ppo(args, wl, vec, dev, rank, world):
             'rollout_ms': roll, 'gae_plus_update_ms': upd, 'optimizer_steps': int(times[-1][2]),
             'update_epochs': cfg['update_epochs'], 'num_minibatches': cfg['num_minibatches'],
             'kl_early_stop': 'disabled for timing', 'opponent_pool': cfg['pool_size'],
+            'update_matmul_precision': args.ppo_precision,
             'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3)}
 
 
@@ -255,6 +257,8 @@ def main():
     ap.add_argument('--ppo-updates', type=int, default=2,
                     help='also time N full self-play PPO iterations (rollout + GAE + update); 0 skips')
     ap.add_argument('--ppo-steps', type=int, default=64, help='rollout length T of the PPO timing')
+    ap.add_argument('--ppo-precision', default='fp32', choices=['fp32', 'tf32'],
+                    help='matmul precision of the PPO update (rollout kernels are always fp32/fp64)')
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
@@ -396,8 +400,14 @@ def main():
         n_mean = 12 * wl['factor']  # n_ctrl in [10, 15) -> mean 12 control points
         flops_step = alg_flops_per_agent_step(R, 2 * n_mean, A, n_mean) * agent_steps
         ach = bytes_step / (kms * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        ncu_path = os.path.join(ROOT, 'profiles', 'r01_step_kernel_ncu.json')
+        if os.path.exists(ncu_path) and E == WORKLOADS[args.workload]['E']:
+            rec = json.load(open(ncu_path)).get(args.workload)
+            if rec:
+                traffic = rec['dram_bytes_read'] + rec['dram_bytes_write']
         roof = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': 'rk::step_kernel', 'kernel_ms': kms,
+                'traffic': traffic, 'peak_source': peak_src, 'kernel': 'rk::step_kernel', 'kernel_ms': kms,
                 'algorithmic_bytes_per_agent_step': alg_bytes_per_agent_step(D),
                 'note': 'the step kernel is FP32/FP64-pipe bound, not HBM bound (SURVEY 8d); see fp_pipe'}
         fp = fp_peaks(torch, dev)

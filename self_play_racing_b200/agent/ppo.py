@@ -191,7 +191,7 @@ class PPO:
         c = self.config
         if self.device.type == 'cuda':
             lr = torch.tensor(float(c['learning_rate']), device=self.device)
-            return optim.Adam(self.agent.parameters(), lr=lr, eps=1e-5, capturable=True, foreach=True)
+            return optim.Adam(self.agent.parameters(), lr=lr, eps=1e-5, capturable=True, fused=True)
         return optim.Adam(self.agent.parameters(), lr=c['learning_rate'], eps=1e-5)
 
     def _set_lr(self, value):
@@ -281,7 +281,14 @@ class PPO:
         number of optimizer steps taken (the KL early stop aborts the update)."""
         c = self.config
         if obs.is_cuda and c.get('cuda_graph_update', True):
-            return self._ppo_update_graphed(advantages, returns, values, logprobs, actions, obs, permutation)
+            # 'update_matmul_precision': 'fp32' (default, what the reference computes on a GPU) or
+            # 'tf32' (tensor-core GEMMs in the update only; rollout kernels are unaffected)
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = c.get('update_matmul_precision', 'fp32') == 'tf32'
+            try:
+                return self._ppo_update_graphed(advantages, returns, values, logprobs, actions, obs, permutation)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
         b_obs = obs.reshape(-1, obs.shape[-1])
         b_actions = actions.reshape(-1, actions.shape[-1])
         b_logprobs, b_adv = logprobs.reshape(-1), advantages.reshape(-1)
