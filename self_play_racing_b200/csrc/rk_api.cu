@@ -286,6 +286,16 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
             }
             sh[ns++] = INFINITY;
         }
+        // environments per warp: as many as fit (one car per lane) unless that leaves the GPU short of
+        // warps; measured (profiles/r01_epw_sweep.log): one full wave of ~27 warps per SM is the
+        // sweet spot, more environments per warp beyond that only serialises the ray queries
+        // (RK_B200_EPW overrides for tuning)
+        int epw = 32 / h->cfg.num_agents;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+        while (epw > 1 && (h->cfg.num_envs + epw - 1) / epw < 26 * sms) epw >>= 1;
+        if (const char* env = getenv("RK_B200_EPW")) epw = atoi(env);
+        p.epw = epw < 1 ? 1 : (epw > 32 / h->cfg.num_agents ? 32 / h->cfg.num_agents : epw);
         p.n_shells = ns;
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }

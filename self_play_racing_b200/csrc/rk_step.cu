@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = p.A, R = p.R, D = p.D;
-    const int epw = 32 / A;                                       // environments per warp
+    const int epw = p.epw;                                        // environments per warp (<= 32 / A)
     const int e_base = (blockIdx.x * kWarpsPerCta + warp) * epw;
     if (e_base >= p.E) return;
     const int n_env = min(epw, p.E - e_base);
@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
 }  // namespace
 
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
-    const int epw = 32 / p.A;
+    const int epw = p.epw;
     const int warps = (p.E + epw - 1) / epw;
     const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R);
