@@ -234,3 +234,54 @@ def test_graphed_update_equals_eager_update(pkg):
         vec.close()
     for a, b in zip(*results):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
+
+
+def test_batched_evaluation_protocol(pkg):
+    """evaluate.py's tracks x runs protocol as one batch: result keys of
+    evaluate.py:51-64 / utils/metrics.py, reproducible, and -- with a (nearly)
+    deterministic policy -- equal to the per-environment loop of utils/metrics.py
+    run against the single-env facade."""
+    env_mod, agent_mod, _ = pkg
+    from self_play_racing_b200.evaluation import evaluate_batched
+    np.random.seed(42)
+    pool = env_mod.gen_tracks(num_tracks=3, seed=42)
+    widths = [int(np.random.RandomState(42 + i).randint(4, 10)) for i in range(3)]
+    torch.manual_seed(3)
+    proto = env_mod.RacingEnv(num_sensors=11)
+    agent = agent_mod.Agent(proto.observation_space, proto.action_space).cuda()
+    agent.log_std.data.fill_(-18.0)  # sigma ~ 1.5e-8: sampling is numerically deterministic
+    res = evaluate_batched('single', agent, pool, widths, num_tracks=3, num_runs=2, max_steps=80)
+    assert set(res) == {'num_episodes', 'num_successful', 'success_rate', 'crash_rate', 'avg_steps', 'avg_reward',
+                        'avg_progress', 'avg_speed', 'avg_distance', 'avg_steps_per_progress', 'all_episodes'}
+    assert res['num_episodes'] == 6 and 0 <= res['crash_rate'] <= 1
+    res2 = evaluate_batched('single', agent, pool, widths, num_tracks=3, num_runs=2, max_steps=80)
+    assert res['all_episodes'] == res2['all_episodes']
+    # the reference's per-env loop (utils/metrics.py:39-78) against the facade
+    for t in range(3):
+        for r in range(2):
+            env = env_mod.RacingEnv(num_sensors=11, track_pool=pool, track_id=t, track_width=widths[r])
+            obs, _ = env.reset()
+            total, prev, dist = 0.0, None, 0.0
+            for step in range(80):
+                with torch.no_grad():
+                    a = agent.get_action_and_value(torch.from_numpy(obs).float().unsqueeze(0).cuda())[0].cpu().numpy()[0]
+                obs, rew, term, trunc, info = env.step(a)
+                total += rew
+                if prev is not None:
+                    dist += float(np.hypot(info['position'][0] - prev[0], info['position'][1] - prev[1]))
+                prev = info['position']
+                if term or trunc:
+                    break
+            m = res['all_episodes'][t * 2 + r]
+            assert m['steps'] == step + 1 and m['crashed'] == info['crashed'] and m['finished'] == info['finished']
+            assert abs(m['total_reward'] - total) < 1e-2 * max(1.0, abs(total))
+            assert abs(m['total_distance'] - dist) < 1e-3 * max(1.0, dist)
+            assert abs(m['progress'] - info['progress']) < 1e-9
+            env.close()
+    # 2-car protocol: both cars driven by the same policy
+    magent = agent_mod.Agent(env_mod.MultiRacingEnv(2, 11).observation_space['0'], proto.action_space).cuda()
+    magent.log_std.data.fill_(-0.3)
+    mres = evaluate_batched('multi', magent, pool, [8, 9], num_tracks=3, num_runs=2, max_steps=400)
+    assert mres['num_episodes'] == 6
+    for m in mres['all_episodes']:
+        assert 1 <= m['steps'] <= 400 and ('placement' in m) and 0 <= m['progress'] <= 1
