@@ -361,3 +361,66 @@ def test_policy_act_matches_torch_agent(B, golden):
     r = act3[:, 1].cpu().numpy()
     assert (r[:, 0] >= -1).all() and (r[:, 0] <= 1).all() and (r[:, 1] >= 0).all() and (r[:, 1] <= 1).all()
     assert r[:, 0].std() > 0.4
+
+
+@pytest.mark.parametrize('query', QUERY_MODES)
+def test_sweep_shape_64_rays_4_cars_vs_oracle(B, query):
+    """BASELINE config 5 shape (4 cars, 64 rays, obs 80-dim) at a size the oracle
+    finishes in seconds; E = 21 is deliberately not a multiple of the 8 envs a warp holds."""
+    cps, widths = _pool(3, seed=31)
+    widths = [w + 3 for w in widths]
+    tracks = O.make_pool(cps, widths)
+    E, A, R = 21, 4, 64
+    e2t = np.arange(E) % 3
+    orc = O.OracleVecEnv(tracks, e2t, kind='multi', num_agents=A, num_sensors=R, seed=2)
+    be = B.RacingBackend(E, kind='multi', num_agents=A, num_sensors=R, query=query)
+    assert be.D == 80
+    be.set_tracks_from_waypoints([t.waypoints for t in tracks], widths, env_to_track=e2t)
+    rs = np.random.RandomState(4)
+    so = orc._draw_start_order(E)
+    oobs, _ = orc.reset(start_order=so)
+    gobs = be.reset(start_slot=torch.from_numpy(so.astype(np.int32)).cuda()).cpu().numpy()
+    np.testing.assert_allclose(gobs, oobs, rtol=0, atol=OBS_ATOL)
+    for k in range(60):
+        a = rs.uniform(-1, 1, size=(E, A, 2)).astype(np.float32)
+        a[..., 1] = np.abs(a[..., 1])
+        so = orc._draw_start_order(E)
+        oobs, orew, ote, otr, _ = orc.step(a, start_order=so)
+        be.actions.copy_(torch.from_numpy(a))
+        be.step(start_slot=torch.from_numpy(so.astype(np.int32)).cuda())
+        np.testing.assert_array_equal(be.terminated.cpu().numpy().astype(bool), ote, err_msg=f'step {k}')
+        np.testing.assert_allclose(be.obs.cpu().numpy(), oobs, rtol=0, atol=OBS_ATOL, err_msg=f'step {k}')
+        np.testing.assert_allclose(be.reward64.cpu().numpy(), orew, rtol=0, atol=STATE_ATOL, err_msg=f'step {k}')
+    be.close()
+
+
+def test_step_invariants_at_scale(B):
+    """Size-independent properties at the full benchmark size (65,536 two-car
+    envs, device-generated pool): both query modes agree bit for bit on every
+    discrete output and to 1e-6 on observations over a free-running rollout;
+    readings stay in [0, 1]; episode bookkeeping is consistent."""
+    E = 65536
+    outs = []
+    for query in QUERY_MODES:
+        be = B.RacingBackend(E, kind='multi', num_agents=2, num_sensors=11, query=query, seed=5)
+        be.generate_tracks(seed=9, n_tracks=16)
+        be.reset()
+        g = torch.Generator(device='cuda').manual_seed(1)
+        term_count = torch.zeros((), dtype=torch.int64, device='cuda')
+        for k in range(40):
+            be.actions.copy_(torch.rand(be.actions.shape, device='cuda', generator=g) * 2 - 1)
+            be.actions[..., 1].abs_()
+            be.step()
+            term_count += be.done.sum()
+        assert float(be.obs[..., :11].min()) >= 0.0 and float(be.obs[..., :11].max()) <= 1.0
+        assert float(be.obs.abs().max()) <= 1.0
+        assert int(be.ep_stats[2]) == int(term_count) > 1000
+        st = be.get_state()
+        outs.append((be.obs.clone(), be.reward64.clone(), st['car_i32'].copy(), st['car_f64'].copy(), int(term_count)))
+        be.close()
+    (o0, r0, i0, f0, n0), (o1, r1, i1, f1, n1) = outs
+    assert n0 == n1
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(f0, f1)               # float64 state is bit-identical between the query modes
+    assert torch.equal(r0, r1)
+    assert float((o0 - o1).abs().max()) <= 1e-6
