@@ -42,7 +42,22 @@ constexpr double kMaxRange = 50.0;      // racing_env.py:15
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// Out of line on purpose: IEEE double division and double sincos each expand to a few hundred bytes of SASS,
+// and the step kernel has dozens of call sites (ncu: 13 % of stalls were instruction-fetch misses at 130 KB).
+#ifndef RK_OUTLINE
+#define RK_OUTLINE 0
+#endif
+#if RK_OUTLINE
+#define RK_MAYBE_NOINLINE __noinline__
+#else
+#define RK_MAYBE_NOINLINE __forceinline__
+#endif
+__device__ RK_MAYBE_NOINLINE double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ RK_MAYBE_NOINLINE double2 sincos_d(double a) {  // returns (sin, cos) by value: no locals forced to the stack
+    double s, c;
+    sincos(a, &s, &c);
+    return make_double2(s, c);
+}
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
@@ -51,6 +66,8 @@ __device__ __forceinline__ double warp_min_d(double v) {
     for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
     return v;
 }
+// sqrt for culling bounds only (2 instructions; every use adds slack far above its ~2 ulp error)
+__device__ __forceinline__ float sqrt_fast(float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; }
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, m));
@@ -157,6 +174,22 @@ __device__ __forceinline__ void raycast_walls_exact(const TrackPool& tp, const T
     }
 }
 
+// One ray against all walls, exact: the rare re-scan of the culled path.
+__device__ RK_MAYBE_NOINLINE double raycast_wall_exact_one(const TrackPool& tp, const TrackMeta& tm, double ox, double oy,
+                                                      double v3x, double v3y, int lane) {
+    const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
+    const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
+    const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
+    const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
+    double best = INFINITY;
+    for (int i = lane; i < 2 * tm.n_wp; i += 32) {
+        const double ax = v2x[i], ay = v2y[i];
+        const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
+        best = fmin(best, ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot));
+    }
+    return warp_min_d(best);
+}
+
 // The four edges of every other car (multi_track.py:10-24), exact, for ONE ray.
 __device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int A, double ox, double oy,
                                                     double v3x, double v3y) {
@@ -165,7 +198,7 @@ __device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int
         const int l = base + oc;
         const double ddx = dsub(S.x[l], ox), ddy = dsub(S.y[l], oy);
         if (sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5) continue;  // multi_track.py:13 (the car itself)
-#pragma unroll
+#pragma unroll 1
         for (int ed = 0; ed < 4; ++ed) {
             const double ex0 = S.cx[ed][l], ey0 = S.cy[ed][l];
             const double ax = dsub(S.cx[(ed + 1) & 3][l], ex0), ay = dsub(S.cy[(ed + 1) & 3][l], ey0);
@@ -198,12 +231,13 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     const float cx0 = (float)(qx[0] - tm.org_x), cy0 = (float)(qy[0] - tm.org_y);
     const int nwc = tm.n_wchunk;
     float U = INFINITY;
+#pragma unroll 1
     for (int c0 = 0; c0 < nwc; c0 += 32) {
         const int ci = c0 + lane;
         if (ci < nwc) {
             const float4 cc = wch[ci];
             const float dx = cc.x - cx0, dy = cc.y - cy0;
-            U = fminf(U, sqrtf(dx * dx + dy * dy) + cc.z);
+            U = fminf(U, sqrt_fast(dx * dx + dy * dy) + cc.z);
         }
     }
     // the nearest waypoint of the centre is within U; every corner is within kHalfDiag of
@@ -212,13 +246,14 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     const float thr = warp_min_f(U) + 2.f * kHalfDiag + 2e-2f;
     int count = 0;
     const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
     for (int c0 = 0; c0 < nwc; c0 += 32) {
         const int ci = c0 + lane;
         bool keep = false;
         if (ci < nwc) {
             const float4 cc = wch[ci];
             const float dx = cc.x - cx0, dy = cc.y - cy0;
-            keep = sqrtf(dx * dx + dy * dy) - cc.z <= thr;
+            keep = sqrt_fast(dx * dx + dy * dy) - cc.z <= thr;
         }
         const unsigned m = __ballot_sync(kFull, keep);
         if (keep) list[count + __popc(m & lt)] = (unsigned short)ci;
@@ -232,6 +267,7 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     const double* wx = tp.wx + tm.wp_off;
     const double* wy = tp.wy + tm.wp_off;
     const int half = lane >> 4, j = lane & 15;
+#pragma unroll 1
     for (int it = 0; it < count; it += 2) {
         const int my = it + half;
         if (my < count) {
@@ -316,6 +352,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
         if (!(hi > lo)) break;
         // ---- level 1 ----
         int count = 0;
+#pragma unroll 1
         for (int c0 = 0; c0 < nb; c0 += 32) {
             const int ci = c0 + lane;
             bool keep = false;
@@ -323,7 +360,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 const float4 cc = bch[ci];
                 const float rx = cc.x - ox, ry = cc.y - oy, rr = cc.z;
                 const float lx = rx * hc + ry * hs, ly = ry * hc - rx * hs;  // car frame
-                const float dc = sqrtf(rx * rx + ry * ry), dmin = dc - rr;   // no point of the chunk is closer than dmin
+                const float dc = sqrt_fast(rx * rx + ry * ry), dmin = dc - rr;   // no point of the chunk is closer than dmin
                 keep = (p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr) &&   // circle reaches into the cone |angle| <= H
                        dmin > lo && dmin <= hi;
                 if (keep && pass > 0 && dc > rr) {
@@ -346,6 +383,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
         }
         __syncwarp();
         // ---- level 2 ----
+#pragma unroll 1
         for (int it = 0; it < count; it += 2) {
             const int my = it + half;
             const bool act = my < count;
@@ -488,7 +526,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 na = fmod(na, kTwoPi);                                // car.py:56 (python modulo)
                 if (na != 0.0) { if (na < 0.0) na = dadd(na, kTwoPi); } else na = 0.0;
                 ang = na;
-                sincos(ang, &sn, &cs);
+                { const double2 sc = sincos_d(ang); sn = sc.x; cs = sc.y; }
                 double vf = dadd(dmul(vx, cs), dmul(vy, sn));            // car.py:59
                 double vl = dadd(dmul(vx, -sn), dmul(vy, cs));           // car.py:60
                 vf = dmul(dadd(vf, dmul(dmul(thr, 10.0), kDt)), 0.985);  // car.py:61-62
@@ -505,7 +543,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 y = dadd(y, dmul(vy, kDt));
             }
         }
-        if (!moving) sincos(ang, &sn, &cs);
+        if (!moving) { const double2 sc = sincos_d(ang); sn = sc.x; cs = sc.y; }
         // publish pose and corners (car.py:26-43) for the cooperative phases
         S.x[lane] = x; S.y[lane] = y;
         {
@@ -561,7 +599,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (o == a) continue;
                 const int li = base + min(a, o), lj = base + max(a, o);  // the reference's (i, j), i < j
                 bool hit = true;  // multi_car.py:16-43: 4 axes, strict separation test
-#pragma unroll
+#pragma unroll 1
                 for (int ax = 0; ax < 4; ++ax) {
                     const int lo = (ax < 2) ? li : lj, k0 = ax & 1;
                     const double ex = dsub(S.cx[k0 + 1][lo], S.cx[k0][lo]), ey = dsub(S.cy[k0 + 1][lo], S.cy[k0][lo]);
@@ -745,7 +783,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     const bool want_obs = is_car && (p.mode != 1 || resetting);
 
     // ---- observations (racing_env.py:44-75 / multi_racing_env.py:48-105) ------------------
-    sincos(ang, &sn, &cs);
+    { const double2 sc = sincos_d(ang); sn = sc.x; cs = sc.y; }
     __syncwarp();
     S.x[lane] = x; S.y[lane] = y; S.c[lane] = cs; S.s[lane] = sn; S.vx[lane] = vx; S.vy[lane] = vy;
     {
@@ -838,11 +876,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     fb &= fb - 1;
                     const int bs = s0 + b, ba = bs / R;
                     const double2 d = cv.dir64[bs];
-                    double bx[kRayBlock], by[kRayBlock], bt[kRayBlock];
-#pragma unroll
-                    for (int k = 0; k < kRayBlock; ++k) { bx[k] = -d.y; by[k] = d.x; bt[k] = INFINITY; }
-                    raycast_walls_exact(tp, tm, S.x[gbase + ba], S.y[gbase + ba], bx, by, 1, lane, bt);
-                    const double t = warp_min_d(bt[0]);
+                    const double t = raycast_wall_exact_one(tp, tm, S.x[gbase + ba], S.y[gbase + ba], -d.y, d.x, lane);
                     if (lane == b) wall = t;
                 }
                 if (live) {
@@ -869,7 +903,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     for (int k = 0; k < kRayBlock; ++k) {
                         // lane k computes ray r0+k's direction, then it is broadcast
                         double dsn = 0.0, dcs = 1.0;
-                        if (lane == k && k < nr) sincos(dadd(oang, p.sensor_angles[r0 + k]), &dsn, &dcs);
+                        if (lane == k && k < nr) { const double2 sc = sincos_d(dadd(oang, p.sensor_angles[r0 + k])); dsn = sc.x; dcs = sc.y; }
                         v3x[k] = -__shfl_sync(kFull, dsn, k);  // track.py:178 v3 = (-dir_y, dir_x)
                         v3y[k] = __shfl_sync(kFull, dcs, k);
                         best[k] = INFINITY;
