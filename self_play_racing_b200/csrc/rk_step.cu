@@ -85,6 +85,10 @@ __device__ __forceinline__ int warp_argmin_d(double d, int idx) {
     return (int)__reduce_min_sync(kFull, (hi == mh && lo == ml) ? (unsigned)idx : 0xffffffffu);
 }
 
+#ifndef RK_L2_UNROLL
+#define RK_L2_UNROLL 1
+#endif
+constexpr int kLevel2Unroll = RK_L2_UNROLL;
 constexpr int kListCap = 512;  // chunk work items per warp batch
 
 // Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
@@ -383,7 +387,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
         }
         __syncwarp();
         // ---- level 2 ----
-#pragma unroll 1
+#pragma unroll kLevel2Unroll
         for (int it = 0; it < count; it += 2) {
             const int my = it + half;
             const bool act = my < count;
@@ -451,7 +455,7 @@ __device__ __forceinline__ int philox_start_slot(uint64_t seed, int e, uint32_t 
 
 // ---------------------------------------------------------------------------
 #ifndef RK_STEP_MIN_BLOCKS
-#define RK_STEP_MIN_BLOCKS 8
+#define RK_STEP_MIN_BLOCKS 7
 #endif
 template <int KIND, int QUERY>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_kernel(const StepParams p) {

@@ -10,7 +10,10 @@ namespace rk {
 constexpr int kChunk = 16;          // waypoints per bounding-circle chunk
 constexpr int kRaySegs = 15;        // boundary segments per chunk (16 points: one half-warp, lane j+1 holds lane j's end point)
 constexpr int kMaxKnots = 130;      // n_ctrl + 1 <= kMaxKnots
-constexpr int kWarpsPerCta = 4;
+#ifndef RK_WARPS
+#define RK_WARPS 4
+#endif
+constexpr int kWarpsPerCta = RK_WARPS;
 
 // flags word of a car
 enum : int { F_CRASHED = 1, F_FINISHED = 2, F_CP25 = 4, F_CP50 = 8, F_CP75 = 16, F_HAS_CRASHED = 32 };
