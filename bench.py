@@ -252,6 +252,7 @@ def main():
     ap.add_argument('--workload', default='multi2_selfplay_65536', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=None)
+    ap.add_argument('--tracks', type=int, default=None, help='size of the procedural track pool (default 16)')
     ap.add_argument('--query', default='culled', choices=['culled', 'exact'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ppo-updates', type=int, default=2,
@@ -263,6 +264,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
         wl['E'] = args.envs
+    if args.tracks:
+        wl['tracks'] = args.tracks
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))

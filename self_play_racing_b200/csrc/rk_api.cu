@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -38,6 +39,10 @@ struct rk_env_s {
     PoolBuffers* pool = nullptr;
     EnvState st{};
     double* sensor_angles = nullptr;  // [3R]: angles, cos, sin
+    int epw = 1;                       // environments per warp of the step kernel
+    // staged launch plan (environments grouped by track); null when not applicable
+    int32_t *group_env = nullptr, *group_count = nullptr, *cta_track = nullptr;
+    int n_ctas = 0, stage_bytes = 0;
     std::vector<void*> owned;
     char err[512] = {0};
 };
@@ -136,6 +141,17 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
         ang[2 * R + k] = sin(ang[k]);
     }
     cudaMemcpy(h->sensor_angles, ang.data(), 3 * R * sizeof(double), cudaMemcpyHostToDevice);
+    {
+        // environments per warp: as many as fit (one car per lane) unless that leaves the GPU short of
+        // warps; measured (profiles/r01_epw_sweep.log): one full wave of ~27 warps per SM is the
+        // sweet spot, more environments per warp beyond that only serialises the ray queries
+        // (RK_B200_EPW overrides for tuning)
+        int epw = 32 / A, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        while (epw > 1 && (E + epw - 1) / epw < 26 * sms) epw >>= 1;
+        if (const char* env = getenv("RK_B200_EPW")) epw = atoi(env);
+        h->epw = epw < 1 ? 1 : (epw > 32 / A ? 32 / A : epw);
+    }
     *out = h;
     return 0;
 }
@@ -144,8 +160,66 @@ int rk_destroy(rk_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     for (void* p : h->owned) cudaFree(p);
+    for (void* p : {(void*)h->group_env, (void*)h->group_count, (void*)h->cta_track})
+        if (p) cudaFree(p);
     if (h->pool) pool_delete(h->pool);
     delete h;
+    return 0;
+}
+
+// Group the environments by track so that every CTA of the step kernel works on ONE
+// track and can stage its search tables in shared memory.  Each track's environments
+// are cut into warp groups of `epw`; a track's group count is padded to whole CTAs.
+// Opt-in (RK_B200_STAGED=1): measured on B200 the staged launch is within 1 % of the plain
+// one for pools of 16..1024 tracks (profiles/r01_staged_vs_plain.log) -- once a warp's
+// environments share a track the tables are L1 hits anyway -- so the plain launch stays
+// the default.  Also skipped when the padding would waste more than a quarter of the warps
+// (e.g. a distinct track per environment).
+static int plan_staged_launch(rk_handle h, const int32_t* e2t_in) {
+    for (int32_t** p : {&h->group_env, &h->group_count, &h->cta_track}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    h->n_ctas = 0;
+    const char* env = getenv("RK_B200_STAGED");
+    if (!env || atoi(env) == 0 || h->cfg.query_mode != RK_QUERY_CULLED) return 0;
+    const int E = h->cfg.num_envs, epw = h->epw, nt = pool_num_tracks(h->pool);
+    std::vector<std::vector<int32_t>> per_track(nt);
+    for (int e = 0; e < E; ++e) per_track[e2t_in ? e2t_in[e] : e % nt].push_back(e);
+    std::vector<int32_t> genv, gcount, ctrack;
+    int stage = 0;
+    for (int t = 0; t < nt; ++t) {
+        const auto& v = per_track[t];
+        if (v.empty()) continue;
+        const TrackMeta& m = *pool_host_meta(h->pool, t);
+        stage = std::max(stage, 16 * (m.n_wp + 1) + 16 * m.n_bchunk + 16 * m.n_wchunk);
+        const int groups = ((int)v.size() + epw - 1) / epw;
+        const int ctas = (groups + kWarpsPerCta - 1) / kWarpsPerCta;
+        for (int c = 0; c < ctas; ++c) {
+            ctrack.push_back(t);
+            for (int w = 0; w < kWarpsPerCta; ++w) {
+                const int g = c * kWarpsPerCta + w;
+                int cnt = 0;
+                for (int k = 0; k < epw; ++k) {
+                    const size_t i = (size_t)g * epw + k;
+                    const bool ok = g < groups && i < v.size();
+                    genv.push_back(ok ? v[i] : -1);
+                    cnt += ok;
+                }
+                gcount.push_back(cnt);
+            }
+        }
+    }
+    const size_t plain_warps = ((size_t)E + epw - 1) / epw;
+    if (gcount.size() > plain_warps + plain_warps / 4 + kWarpsPerCta) return 0;  // too much padding: plain launch
+    H_CUDA(h, cudaMalloc(&h->group_env, genv.size() * sizeof(int32_t)));
+    H_CUDA(h, cudaMalloc(&h->group_count, gcount.size() * sizeof(int32_t)));
+    H_CUDA(h, cudaMalloc(&h->cta_track, ctrack.size() * sizeof(int32_t)));
+    H_CUDA(h, cudaMemcpy(h->group_env, genv.data(), genv.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    H_CUDA(h, cudaMemcpy(h->group_count, gcount.data(), gcount.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    H_CUDA(h, cudaMemcpy(h->cta_track, ctrack.data(), ctrack.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->n_ctas = (int)ctrack.size();
+    h->stage_bytes = (stage + 15) / 16 * 16;
     return 0;
 }
 
@@ -173,8 +247,10 @@ static int set_tracks_common(rk_handle h, const double* ctrl, const int32_t* n_c
             n_wp[t] = n_wp_in[t];
         }
     }
-    return build_pool(*h->pool, n_tracks, ctrl ? n_ctrl : nullptr, ctrl ? off.data() : nullptr, total_ctrl, ctrl,
-                      n_wp.data(), wp, widths, e2t, h->cfg.num_envs, h->err, sizeof(h->err));
+    if (build_pool(*h->pool, n_tracks, ctrl ? n_ctrl : nullptr, ctrl ? off.data() : nullptr, total_ctrl, ctrl,
+                   n_wp.data(), wp, widths, e2t, h->cfg.num_envs, h->err, sizeof(h->err)))
+        return 1;
+    return plan_staged_launch(h, e2t);
 }
 
 int rk_set_tracks_from_control_points(rk_handle h, const double* host_ctrl_xy, const int32_t* host_n_ctrl,
@@ -286,16 +362,12 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
             }
             sh[ns++] = INFINITY;
         }
-        // environments per warp: as many as fit (one car per lane) unless that leaves the GPU short of
-        // warps; measured (profiles/r01_epw_sweep.log): one full wave of ~27 warps per SM is the
-        // sweet spot, more environments per warp beyond that only serialises the ray queries
-        // (RK_B200_EPW overrides for tuning)
-        int epw = 32 / h->cfg.num_agents;
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-        while (epw > 1 && (h->cfg.num_envs + epw - 1) / epw < 26 * sms) epw >>= 1;
-        if (const char* env = getenv("RK_B200_EPW")) epw = atoi(env);
-        p.epw = epw < 1 ? 1 : (epw > 32 / h->cfg.num_agents ? 32 / h->cfg.num_agents : epw);
+        p.epw = h->epw;
+        p.group_env = h->group_env;
+        p.group_count = h->group_count;
+        p.cta_track = h->cta_track;
+        p.n_ctas = h->n_ctas;
+        p.stage_bytes = h->stage_bytes;
         p.n_shells = ns;
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }

@@ -457,15 +457,53 @@ __device__ __forceinline__ int philox_start_slot(uint64_t seed, int e, uint32_t 
 #ifndef RK_STEP_MIN_BLOCKS
 #define RK_STEP_MIN_BLOCKS 7
 #endif
-template <int KIND, int QUERY>
+// STAGED: the CTA's environments all run on ONE track (the host groups them, see
+// rk_api.cu), whose fp32 search tables -- closed boundary rows, ray-chunk and
+// waypoint-chunk circles -- are brought into shared memory with bulk asynchronous
+// copies (TMA, cp.async.bulk -> mbarrier) while the warps integrate the dynamics.
+template <int KIND, int QUERY, bool STAGED>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long stage_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = p.A, R = p.R, D = p.D;
     const int epw = p.epw;                                        // environments per warp (<= 32 / A)
-    const int e_base = (blockIdx.x * kWarpsPerCta + warp) * epw;
-    if (e_base >= p.E) return;
-    const int n_env = min(epw, p.E - e_base);
+    const int gwarp = blockIdx.x * kWarpsPerCta + warp;           // this warp's group of environments
+    TrackPool tp = p.trk;
+    TrackMeta stm;                                                // STAGED: the CTA's track, offsets re-based to shared memory
+    if (STAGED) {
+        stm = tp.meta[p.cta_track[blockIdx.x]];
+        unsigned char* stage = smem_raw + (size_t)kWarpsPerCta * warp_smem_bytes(A, R);
+        const unsigned b_bpt = 16u * (unsigned)(stm.n_wp + 1), b_bch = 16u * (unsigned)stm.n_bchunk,
+                       b_wch = 16u * (unsigned)stm.n_wchunk;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bpt + b_bch + b_wch) : "memory");
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(tp.bpt + stm.bpt_off), "r"(b_bpt), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + b_bpt), "l"(tp.bchunk + stm.bchunk_off), "r"(b_bch), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + b_bpt + b_bch), "l"(tp.wchunk + stm.wchunk_off), "r"(b_wch), "r"(bar) : "memory");
+        }
+        tp.bpt = reinterpret_cast<const float2*>(stage);
+        tp.bchunk = reinterpret_cast<const float4*>(stage + b_bpt);
+        tp.wchunk = reinterpret_cast<const float4*>(stage + b_bpt + b_bch);
+        stm.bpt_off = 0; stm.bchunk_off = 0; stm.wchunk_off = 0;
+        __syncthreads();  // the barrier is initialised before any warp polls it (every thread reaches this point)
+    }
+    int e_base = gwarp * epw, n_env;
+    if (STAGED) {
+        n_env = p.group_count[gwarp];
+        if (n_env == 0) return;
+    } else {
+        if (e_base >= p.E) return;
+        n_env = min(epw, p.E - e_base);
+    }
+    const int* genv = STAGED ? p.group_env + (size_t)gwarp * epw : nullptr;
     unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
     CarS& S = *reinterpret_cast<CarS*>(wbase);
     CullView cv;
@@ -474,19 +512,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     cv.ray_key = reinterpret_cast<unsigned long long*>(cv.dir64 + A * R);
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(cv.dir32 + A * R);
-    const TrackPool& tp = p.trk;
 
     // ---- lane = one car -------------------------------------------------------
     const int g = lane / A, a = lane - g * A;     // environment within the warp, car within the environment
     const bool is_car = g < n_env;
-    const int e = e_base + (is_car ? g : 0);
+    const int e = STAGED ? genv[is_car ? g : 0] : e_base + (is_car ? g : 0);
     const int base = g * A;                       // first lane of this car's environment
     const bool lead = is_car && a == 0;           // writes the per-environment outputs
     const int c = e * A + a;                      // state index
     const bool agent_major = p.io.layout == RK_LAYOUT_AGENT_MAJOR;
     const size_t ci = agent_major ? (size_t)a * p.E + e : (size_t)c;  // index in the caller's per-car arrays
     const int tid = tp.env_to_track[e];
-    const TrackMeta* tmp = tp.meta + tid;
+    const TrackMeta* tmp = tp.meta + tid;  // (scalar fields only: start pose, width, N)
     const int n_wp = tmp->n_wp;
     const double Nd = (double)n_wp;
 
@@ -560,6 +597,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         }
         __syncwarp();
 
+        if (STAGED) {  // the staged tables are needed from here on
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar) : "memory");
+        }
         // ---- W: closest waypoint of the centre and the 4 corners, one car at a time,
         //         all lanes cooperating (track.py:150-152) ---------------------------
         int cidx1 = 0, cidx2 = 0, cidx3 = 0, cidx4 = 0;
@@ -567,7 +611,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1;
-            const TrackMeta tm = tp.meta[__shfl_sync(kFull, tid, l)];
+            const TrackMeta tm = STAGED ? stm : tp.meta[__shfl_sync(kFull, tid, l)];
             double qx[5], qy[5];
             qx[0] = S.x[l]; qy[0] = S.y[l];
 #pragma unroll
@@ -824,14 +868,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         }
     }
 
+    if (STAGED && p.mode != 0) {  // reset / observe launches did not pass the wait above
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
     // rays: the warp walks over its environments, all lanes cooperating on one
     const unsigned obs_envs = __ballot_sync(kFull, want_obs && a == 0);
     const int nslot = A * R;
     for (int gg = 0; gg < n_env; ++gg) {
         const int gbase = gg * A;
         if (!((obs_envs >> gbase) & 1u)) continue;
-        const int ee = e_base + gg;
-        const TrackMeta tm = tp.meta[__shfl_sync(kFull, tid, gbase)];
+        const int ee = STAGED ? genv[gg] : e_base + gg;
+        const TrackMeta tm = STAGED ? stm : tp.meta[__shfl_sync(kFull, tid, gbase)];
         if (QUERY == RK_QUERY_CULLED) {
             // ray directions by angle addition from the car's (cos, sin): one lane per (car, ray) slot
             for (int s0 = 0; s0 < nslot; s0 += 32) {
@@ -933,20 +984,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
 }  // namespace
 
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
+    const bool staged = p.group_env != nullptr;
     const int epw = p.epw;
     const int warps = (p.E + epw - 1) / epw;
-    const int grid = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R);
+    const int grid = staged ? p.n_ctas : (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R) + (staged ? (size_t)p.stage_bytes : 0);
     using Kern = void (*)(const StepParams);
+    const bool single = env_kind == RK_ENV_SINGLE, culled = query_mode == RK_QUERY_CULLED;
     Kern k;
-    if (env_kind == RK_ENV_SINGLE)
-        k = (query_mode == RK_QUERY_CULLED) ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED>
-                                            : step_kernel<RK_ENV_SINGLE, RK_QUERY_EXACT_F64>;
+    if (staged && culled)
+        k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED, true> : step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED, true>;
+    else if (culled)
+        k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED, false> : step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED, false>;
     else
-        k = (query_mode == RK_QUERY_CULLED) ? step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED>
-                                            : step_kernel<RK_ENV_MULTI, RK_QUERY_EXACT_F64>;
+        k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_EXACT_F64, false> : step_kernel<RK_ENV_MULTI, RK_QUERY_EXACT_F64, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(p);
+    StepParams q = p;
+    if (!(staged && culled)) q.group_env = nullptr;
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(q);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

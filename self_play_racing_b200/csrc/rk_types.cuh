@@ -73,6 +73,11 @@ struct StepParams {
     const double *sensor_cos, *sensor_sin;  // [R] cos / sin of the above
     float inv_dphi;    // (R-1) / (2H): ray-index units per radian (H = half cone: pi/3 single, pi/2 multi)
     float cone_half, cone_sin, cone_cos;  // H plus a small margin, and its sine / cosine
+    // staged launch (environments grouped by track, tables staged in shared memory); null = plain launch
+    const int32_t* group_env;    // [n_ctas * kWarpsPerCta * epw] environment ids, -1 padded
+    const int32_t* group_count;  // [n_ctas * kWarpsPerCta] environments in each warp's group
+    const int32_t* cta_track;    // [n_ctas]
+    int32_t n_ctas, stage_bytes;
     int32_t epw;       // environments per warp (<= 32 / A): fewer means more warps for the cooperative queries
     int32_t n_shells;  // distance shells of the ray sweep: (-inf, shell[0]], (shell[0], shell[1]], ...
     float shell[4];

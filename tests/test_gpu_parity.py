@@ -193,11 +193,14 @@ def _pool(n_tracks, seed):
     return cps, widths
 
 
-@pytest.mark.parametrize('query', QUERY_MODES)
+@pytest.mark.parametrize('query', QUERY_MODES + ['culled-staged'])
 @pytest.mark.parametrize('kind,A,E,steps', [('single', 1, 192, 260), ('multi', 2, 160, 260), ('multi', 4, 48, 120)])
-def test_batched_lockstep_vs_oracle(B, kind, A, E, steps, query):
+def test_batched_lockstep_vs_oracle(B, kind, A, E, steps, query, monkeypatch):
     """E envs over 6 procedural tracks, free-running against the oracle on the
     same seeded actions and injected start slots; ragged N (300..420)."""
+    if query == 'culled-staged':  # the opt-in launch that stages each CTA's track tables with bulk async copies
+        monkeypatch.setenv('RK_B200_STAGED', '1')
+        query = 'culled'
     cps, widths = _pool(6, seed=21 + A)
     if A == 4:
         widths = [w + 3 for w in widths]  # 4 cars abreast need width >= 8 (SURVEY 8d config 5)
