@@ -96,8 +96,7 @@ class BatchedRacingVecEnv:
                   query='culled', autoreset='next_step', seed=0, copy=True, factor=30, width_lo=6.0, width_mod=4,
                   want_info=False):
         """E environments over a device-generated procedural pool (BASELINE
-        configs 2-5): the envs are split evenly over the n_tracks tracks (blocked), widths
-        width_lo + (t % width_mod)."""
+        configs 2-5): env e runs on track e % n_tracks, widths width_lo + (t % width_mod)."""
         self = cls.__new__(cls)
         self.kind = kind
         self.num_envs = int(num_envs)
@@ -105,13 +104,13 @@ class BatchedRacingVecEnv:
         self.selfplay = bool(selfplay) and kind == 'multi' and self.num_agents == 2
         self.copy = copy
         self._specs = None
-        # blocked assignment (envs of a track are contiguous): warps of the staged step kernel then
-        # touch contiguous state; RK_B200_INTERLEAVE=1 gives e % n_tracks instead (tuning)
+        # env e runs on track e % n_tracks; RK_B200_BLOCKED=1 assigns contiguous
+        # blocks of environments to each track instead (what the opt-in staged launch prefers)
         import os
-        if os.environ.get('RK_B200_INTERLEAVE') == '1':
-            self.env_to_track = (np.arange(self.num_envs) % n_tracks).astype(np.int32)
-        else:
+        if os.environ.get('RK_B200_BLOCKED') == '1':
             self.env_to_track = (np.arange(self.num_envs, dtype=np.int64) * n_tracks // self.num_envs).astype(np.int32)
+        else:
+            self.env_to_track = (np.arange(self.num_envs) % n_tracks).astype(np.int32)
         self.be = RacingBackend(self.num_envs, kind=kind, num_agents=self.num_agents, num_sensors=num_sensors,
                                 device=device, autoreset=autoreset, query=query, seed=seed, want_info=want_info,
                                 agent_major=True)
