@@ -202,6 +202,9 @@ __device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int
         const int l = base + oc;
         const double ddx = dsub(S.x[l], ox), ddy = dsub(S.y[l], oy);
         if (sqrt(dadd(dmul(ddx, ddx), dmul(ddy, ddy))) < 0.5) continue;  // multi_track.py:13 (the car itself)
+        // all four edges lie within sqrt(5) of the car's centre: a ray whose line passes farther from the
+        // centre, or that points away from it, can not hit any of them (no effect on results)
+        if (fabs(ddx * v3x + ddy * v3y) > 2.23606797750 + 1e-6 || ddx * v3y - ddy * v3x < -(2.23606797750 + 1e-6)) continue;
 #pragma unroll 1
         for (int ed = 0; ed < 4; ++ed) {
             const double ex0 = S.cx[ed][l], ey0 = S.cy[ed][l];
