@@ -184,6 +184,22 @@ RK_API int rk_policy_act(const float* params, int32_t obs_dim, const float* obs,
 /* number of float32 values in the packed Agent block for a given obs_dim (action_dim = 2) */
 RK_API int rk_policy_param_count(int32_t obs_dim);
 
+/* ---- PPO update helpers: PPO.ppo_update (agent/ppo.py:156-209) -------------------- */
+/* Gather one minibatch: dst[k] = src[idx[k]] for obs [.,obs_dim], actions [.,2], old
+ * log-probs, advantages, returns, values (ppo.py:170-195's fancy indexing).  idx: int64 [n]. */
+RK_API int rk_gather_minibatch(const int64_t* idx, int32_t n, int32_t obs_dim, const float* obs, const float* act,
+                               const float* logp, const float* adv, const float* ret, const float* val,
+                               float* o_obs, float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val,
+                               void* stream);
+/* Gradients of the clipped-surrogate + clipped-value loss (ppo.py:173-204) with respect to
+ * the network outputs mu [n,2] and v [n], with torch.maximum / torch.clamp tie conventions;
+ * the entropy bonus has no gradient because log_std is a buffer.  adv_mean/adv_std are the
+ * (global) minibatch statistics as device scalars; *kl_sum += sum(logp_old - logp_new). */
+RK_API int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, const float* old_logp, const float* adv,
+                            const float* ret, const float* v_old, const float* log_std, const float* adv_mean,
+                            const float* adv_std, int32_t n, float clip_coef, float vf_coef, float* dmu, float* dv,
+                            double* kl_sum, void* stream);
+
 /* ---- measurement aid --------------------------------------------------------- */
 /* Sustained FMA throughput of the current device in TFLOP/s (fp32, or fp64 when
  * use_fp64 != 0): the non-tensor roofline denominator bench.py reports the step

@@ -67,6 +67,9 @@ SIGNATURES = {
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'rk_policy_param_count': (C.c_int, [C.c_int32]),
     'rk_fma_peak': (C.c_double, [C.c_int32, C.c_int32]),
+    'rk_gather_minibatch': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 13),
+    'rk_ppo_loss_grad': (C.c_int, [C.c_void_p] * 10 + [C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
-from ..backend import flatten_agent, gae as gae_kernel, policy_act
+from ..backend import flatten_agent, gae as gae_kernel, gather_minibatch, policy_act, ppo_loss_grad
 from ..environment.vec_env import BatchedRacingVecEnv
 
 
@@ -118,12 +118,26 @@ class _GraphedMinibatch:
         world = ppo.world
         opt = ppo.optimizer
 
+        fused = c.get('fused_update_kernels', True)
+        self.dmu, self.dv = z(mb, 2), z(mb)
+        agent = ppo.agent
+
         def fwd_bwd():
             opt.zero_grad(set_to_none=False)
-            loss, kl = ppo._losses(self.obs, self.act, self.old_logp, self.adv, self.ret, self.val,
-                                   self.adv_mean, self.adv_std)
-            self.kl_sum.copy_(kl)
-            loss.backward()
+            if fused:
+                # network outputs -> one kernel for d(loss)/d(mu, v) and the KL sum -> autograd through the MLPs only
+                mu = agent.actor_mu(self.obs)
+                v = agent.critic(self.obs).flatten()
+                self.kl_sum.zero_()
+                ppo_loss_grad(mu.detach(), v.detach(), self.act, self.old_logp, self.adv, self.ret, self.val,
+                              agent.log_std, self.adv_mean, self.adv_std, c['clip_coef'], c['vf_coef'],
+                              self.dmu, self.dv, self.kl_sum)
+                torch.autograd.backward([mu, v], [self.dmu, self.dv])
+            else:
+                loss, kl = ppo._losses(self.obs, self.act, self.old_logp, self.adv, self.ret, self.val,
+                                       self.adv_mean, self.adv_std)
+                self.kl_sum.copy_(kl)
+                loss.backward()
             if world > 1:
                 torch.cat([p.grad.reshape(-1) for p in params], out=self.flat_grad)
 
@@ -352,12 +366,13 @@ class PPO:
         the reference), graph 2 = gradient clipping + Adam.  With world > 1 the flat
         gradient and the KL sum are all-reduced between the two graphs."""
         c = self.config
-        b_obs = obs.reshape(-1, obs.shape[-1])
-        b_actions = actions.reshape(-1, actions.shape[-1])
-        b_logprobs, b_adv = logprobs.reshape(-1), advantages.reshape(-1)
-        b_returns, b_values = returns.reshape(-1), values.reshape(-1)
+        b_obs = obs.reshape(-1, obs.shape[-1]).contiguous()
+        b_actions = actions.reshape(-1, actions.shape[-1]).contiguous()
+        b_logprobs, b_adv = logprobs.reshape(-1).contiguous(), advantages.reshape(-1).contiguous()
+        b_returns, b_values = returns.reshape(-1).contiguous(), values.reshape(-1).contiguous()
         n_local = b_obs.shape[0]
         mb = max(n_local // c['num_minibatches'], 1)
+        fused = c.get('fused_update_kernels', True)
         g = self._graphed
         if g is None or g.mb != mb or g.obs.shape[1] != b_obs.shape[1]:
             g = self._graphed = _GraphedMinibatch(self, mb, b_obs.shape[1])
@@ -367,12 +382,16 @@ class PPO:
             perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
             for start in range(0, n_local - mb + 1, mb):
                 idx = perm[start:start + mb]
-                torch.index_select(b_obs, 0, idx, out=g.obs)
-                torch.index_select(b_actions, 0, idx, out=g.act)
-                torch.index_select(b_logprobs, 0, idx, out=g.old_logp)
-                torch.index_select(b_adv, 0, idx, out=g.adv)
-                torch.index_select(b_returns, 0, idx, out=g.ret)
-                torch.index_select(b_values, 0, idx, out=g.val)
+                if fused:
+                    gather_minibatch(idx, (b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values),
+                                     (g.obs, g.act, g.old_logp, g.adv, g.ret, g.val))
+                else:
+                    torch.index_select(b_obs, 0, idx, out=g.obs)
+                    torch.index_select(b_actions, 0, idx, out=g.act)
+                    torch.index_select(b_logprobs, 0, idx, out=g.old_logp)
+                    torch.index_select(b_adv, 0, idx, out=g.adv)
+                    torch.index_select(b_returns, 0, idx, out=g.ret)
+                    torch.index_select(b_values, 0, idx, out=g.val)
                 a64 = g.adv.double()
                 stats = torch.stack([a64.sum(), (a64 * a64).sum()])
                 self._all_reduce(stats)

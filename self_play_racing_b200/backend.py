@@ -275,3 +275,25 @@ def policy_act(params, obs, action_out, seed, counter, logprob=None, value=None,
     _lib.check(lib.rk_policy_act(_ptr(params), obs_dim, obs_ptr, obs_stride, B, int(seed), int(counter),
                                  _ptr(action_out), action_out.stride(0), _ptr(logprob), _ptr(value), _ptr(mean),
                                  stream), None, 'rk_policy_act')
+
+
+def gather_minibatch(idx, src, dst):
+    """dst[k] = src[idx[k]] for the six per-sample arrays of a PPO minibatch, one
+    launch.  src/dst: (obs [.,D], actions [.,2], logprobs, advantages, returns,
+    values), contiguous float32 CUDA tensors; idx: int64 [n]."""
+    lib = _lib.load()
+    obs = src[0]
+    stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+    _lib.check(lib.rk_gather_minibatch(_ptr(idx), idx.numel(), obs.shape[1], *[_ptr(t) for t in src],
+                                       *[_ptr(t) for t in dst], stream), None, 'rk_gather_minibatch')
+
+
+def ppo_loss_grad(mu, v, act, old_logp, adv, ret, v_old, log_std, adv_mean, adv_std, clip_coef, vf_coef, dmu, dv,
+                  kl_sum):
+    """Fused d(loss)/d(mu, v) of the PPO minibatch loss + KL-sum accumulation."""
+    lib = _lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream(mu.device).cuda_stream)
+    _lib.check(lib.rk_ppo_loss_grad(_ptr(mu), _ptr(v), _ptr(act), _ptr(old_logp), _ptr(adv), _ptr(ret), _ptr(v_old),
+                                    _ptr(log_std), _ptr(adv_mean), _ptr(adv_std), mu.shape[0], float(clip_coef),
+                                    float(vf_coef), _ptr(dmu), _ptr(dv), _ptr(kl_sum), stream), None,
+               'rk_ppo_loss_grad')

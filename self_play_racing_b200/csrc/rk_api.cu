@@ -531,6 +531,31 @@ int rk_gae(const float* rewards, const float* values, const float* dones, const 
 
 int rk_policy_param_count(int32_t obs_dim) { return policy_param_count(obs_dim); }
 
+int rk_gather_minibatch(const int64_t* idx, int32_t n, int32_t obs_dim, const float* obs, const float* act,
+                        const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,
+                        float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val, void* stream) {
+    if (!idx || n <= 0 || !obs || !act || !logp || !adv || !ret || !val || !o_obs || !o_act || !o_logp || !o_adv ||
+        !o_ret || !o_val) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_gather_minibatch: invalid arguments");
+        return 1;
+    }
+    return launch_gather_minibatch(idx, n, obs_dim, obs, act, logp, adv, ret, val, o_obs, o_act, o_logp, o_adv, o_ret,
+                                   o_val, (cudaStream_t)stream);
+}
+
+int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, const float* old_logp, const float* adv,
+                     const float* ret, const float* v_old, const float* log_std, const float* adv_mean,
+                     const float* adv_std, int32_t n, float clip_coef, float vf_coef, float* dmu, float* dv,
+                     double* kl_sum, void* stream) {
+    if (!mu || !v || !act || !old_logp || !adv || !ret || !v_old || !log_std || !adv_mean || !adv_std || n <= 0 ||
+        !dmu || !dv || !kl_sum) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_loss_grad: invalid arguments");
+        return 1;
+    }
+    return launch_ppo_loss_grad(mu, v, act, old_logp, adv, ret, v_old, log_std, adv_mean, adv_std, n, clip_coef,
+                                vf_coef, dmu, dv, kl_sum, (cudaStream_t)stream);
+}
+
 int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
                   uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
                   float* mean, void* stream) {

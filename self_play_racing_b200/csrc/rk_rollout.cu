@@ -189,6 +189,87 @@ policy_act_kernel(const float* __restrict__ params, int obs_dim, const float* __
     }
 }
 
+// ---------------------------------------------------------------------------
+// PPO update helpers (reference agent/ppo.py:156-209): one launch gathers a
+// minibatch, one launch turns the network outputs into the loss gradients.
+// ---------------------------------------------------------------------------
+// dst[k] = src[idx[k]] for the six per-sample arrays of a minibatch (ppo.py:170-176,187-195)
+__global__ void gather_minibatch_kernel(const int64_t* __restrict__ idx, int n, int obs_dim,
+                                        const float* __restrict__ obs, const float* __restrict__ act,
+                                        const float* __restrict__ logp, const float* __restrict__ adv,
+                                        const float* __restrict__ ret, const float* __restrict__ val,
+                                        float* __restrict__ o_obs, float* __restrict__ o_act, float* __restrict__ o_logp,
+                                        float* __restrict__ o_adv, float* __restrict__ o_ret, float* __restrict__ o_val) {
+    // one warp per sample row: lanes copy the obs_dim observation floats, lanes 0..5 the scalars
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const int64_t src = idx[row];
+    for (int k = lane; k < obs_dim; k += 32) o_obs[(size_t)row * obs_dim + k] = obs[(size_t)src * obs_dim + k];
+    if (lane == 0) o_act[2 * (size_t)row] = act[2 * (size_t)src];
+    if (lane == 1) o_act[2 * (size_t)row + 1] = act[2 * (size_t)src + 1];
+    if (lane == 2) o_logp[row] = logp[src];
+    if (lane == 3) o_adv[row] = adv[src];
+    if (lane == 4) o_ret[row] = ret[src];
+    if (lane == 5) o_val[row] = val[src];
+}
+
+// Gradients of  loss = pg_loss + vf_coef * v_loss  (+ an entropy term that is constant in
+// the parameters because log_std is a buffer) with respect to the network outputs mu [n,2]
+// and v [n], exactly as autograd derives them from ppo.py:173-204:
+//   ratio = exp(logp_new - logp_old); pg = mean(max(-A ratio, -A clamp(ratio, 1-c, 1+c)))
+//   v_loss = 0.5 mean(max((v - R)^2, (clamp(v - v_old, -c, c) + v_old - R)^2))
+// torch.maximum splits the gradient evenly on ties and clamp passes it on its closed
+// interval; both conventions are reproduced.  Also accumulates sum(logp_old - logp_new).
+__global__ void ppo_loss_grad_kernel(const float* __restrict__ mu, const float* __restrict__ v,
+                                     const float* __restrict__ act, const float* __restrict__ old_logp,
+                                     const float* __restrict__ adv_raw, const float* __restrict__ ret,
+                                     const float* __restrict__ v_old, const float* __restrict__ log_std,
+                                     const float* __restrict__ adv_mean, const float* __restrict__ adv_std, int n,
+                                     float clip, float vf_coef, float* __restrict__ dmu, float* __restrict__ dv,
+                                     double* __restrict__ kl_sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float kl = 0.f;
+    if (i < n) {
+        const float ls0 = log_std[0], ls1 = log_std[1];
+        const float s0 = expf(ls0), s1 = expf(ls1);
+        const float m0 = mu[2 * (size_t)i], m1 = mu[2 * (size_t)i + 1];
+        const float a0 = act[2 * (size_t)i], a1 = act[2 * (size_t)i + 1];
+        const float kLogSqrt2Pi = 0.9189385332046727f;
+        const float d0 = a0 - m0, d1 = a1 - m1;
+        const float lp = (-(d0 * d0) / (2.f * s0 * s0) - ls0 - kLogSqrt2Pi) + (-(d1 * d1) / (2.f * s1 * s1) - ls1 - kLogSqrt2Pi);
+        const float logratio = lp - old_logp[i];
+        kl = -logratio;
+        const float ratio = expf(logratio);
+        const float A = (adv_raw[i] - adv_mean[0]) / (adv_std[0] + 1e-8f);
+        const float lo = 1.f - clip, hi = 1.f + clip;
+        const float rc = fminf(fmaxf(ratio, lo), hi);
+        const float pg1 = -A * ratio, pg2 = -A * rc;
+        const bool inside = ratio >= lo && ratio <= hi;
+        float w1 = pg1 > pg2 ? 1.f : (pg1 == pg2 ? 0.5f : 0.f);   // share of the max() gradient going to pg1
+        float dratio = w1 * (-A) + (1.f - w1) * (inside ? -A : 0.f);
+        const float g_lp = dratio * ratio / (float)n;              // d loss / d logp_new
+        dmu[2 * (size_t)i] = g_lp * d0 / (s0 * s0);
+        dmu[2 * (size_t)i + 1] = g_lp * d1 / (s1 * s1);
+        const float vi = v[i], R = ret[i], vo = v_old[i];
+        const float dvv = vi - vo;
+        const float vclip = vo + fminf(fmaxf(dvv, -clip), clip);
+        const float l1 = (vi - R) * (vi - R), l2 = (vclip - R) * (vclip - R);
+        const float g1 = 2.f * (vi - R), g2 = (dvv >= -clip && dvv <= clip) ? 2.f * (vclip - R) : 0.f;
+        const float u1 = l1 > l2 ? 1.f : (l1 == l2 ? 0.5f : 0.f);
+        dv[i] = vf_coef * 0.5f * (u1 * g1 + (1.f - u1) * g2) / (float)n;
+    }
+    // block sum of (logp_old - logp_new) -> one atomic per block
+    __shared__ float red[32];
+    for (int m = 16; m > 0; m >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = kl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+        if (threadIdx.x == 0) atomicAdd(kl_sum, (double)t);
+    }
+}
+
 // Pool-empty opponent: Box([-1,0],[1,1]).sample() (wrappers.py:30-32, multi_racing_env.py:28-35)
 __global__ void random_act_kernel(int B, uint64_t seed, uint64_t counter, float* __restrict__ action,
                                   int64_t act_stride) {
@@ -213,6 +294,26 @@ int launch_gae(const float* rewards, const float* values, const float* dones, co
 }
 
 int policy_param_count(int obs_dim) { return policy_packed_floats(obs_dim); }
+
+int launch_gather_minibatch(const int64_t* idx, int n, int obs_dim, const float* obs, const float* act,
+                            const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,
+                            float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val, cudaStream_t stream) {
+    const int rows_per_block = 8;
+    gather_minibatch_kernel<<<(n + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+        idx, n, obs_dim, obs, act, logp, adv, ret, val, o_obs, o_act, o_logp, o_adv, o_ret, o_val);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, const float* old_logp, const float* adv,
+                         const float* ret, const float* v_old, const float* log_std, const float* adv_mean,
+                         const float* adv_std, int n, float clip, float vf_coef, float* dmu, float* dv,
+                         double* kl_sum, cudaStream_t stream) {
+    ppo_loss_grad_kernel<<<(n + 255) / 256, 256, 0, stream>>>(mu, v, act, old_logp, adv, ret, v_old, log_std, adv_mean,
+                                                              adv_std, n, clip, vf_coef, dmu, dv, kl_sum);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B, uint64_t seed,
                       uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,

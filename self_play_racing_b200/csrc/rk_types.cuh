@@ -121,5 +121,12 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
                       uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob,
                       float* value, float* mean, cudaStream_t stream);
 int policy_param_count(int obs_dim);
+int launch_gather_minibatch(const int64_t* idx, int n, int obs_dim, const float* obs, const float* act,
+                            const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,
+                            float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val, cudaStream_t stream);
+int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, const float* old_logp, const float* adv,
+                         const float* ret, const float* v_old, const float* log_std, const float* adv_mean,
+                         const float* adv_std, int n, float clip, float vf_coef, float* dmu, float* dv,
+                         double* kl_sum, cudaStream_t stream);
 
 }  // namespace rk

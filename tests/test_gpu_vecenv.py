@@ -206,9 +206,9 @@ def test_graphed_update_equals_eager_update(pkg):
     same parameters as the eager step-by-step update, and honours the KL stop."""
     env_mod, agent_mod, configs = pkg
     results = []
-    for graphed in (False, True):
+    for graphed, fused in ((False, False), (True, False), (True, True)):
         cfg = configs.base_config(num_envs=64, num_steps=64, update_epochs=2, num_minibatches=4, kl_target=1e9,
-                                  cuda_graph_update=graphed)
+                                  cuda_graph_update=graphed, fused_update_kernels=fused)
         vec = env_mod.BatchedRacingVecEnv.synthetic('single', 64, n_tracks=4, seed=0)
         tr = agent_mod.PPO(vec, cfg, device='cuda')
         g = torch.Generator(device='cuda').manual_seed(0)
@@ -232,8 +232,9 @@ def test_graphed_update_equals_eager_update(pkg):
         for a, b in zip(before, tr.agent.parameters()):
             assert torch.equal(a, b)
         vec.close()
-    for a, b in zip(*results):
-        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
+    for other in results[1:]:  # eager autograd == graphed autograd == graphed with the fused loss-gradient kernel
+        for a, b in zip(results[0], other):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
 
 
 def test_batched_evaluation_protocol(pkg):
