@@ -427,3 +427,57 @@ def test_step_invariants_at_scale(B):
     np.testing.assert_array_equal(f0, f1)               # float64 state is bit-identical between the query modes
     assert torch.equal(r0, r1)
     assert float((o0 - o1).abs().max()) <= 1e-6
+
+
+def test_error_behaviour_through_the_abi(B):
+    """Errors never throw across the C ABI: non-zero status + rk_last_error text,
+    surfaced as RuntimeError by the Python layer."""
+    be = B.RacingBackend(8, kind='multi', num_agents=2)
+    with pytest.raises(RuntimeError, match='no tracks set'):
+        be.step()
+    with pytest.raises(RuntimeError, match='no tracks set'):
+        be.reset()
+    with pytest.raises(RuntimeError, match='control points'):
+        be.set_tracks_from_control_points([np.zeros((2, 2))], [6.0])          # fewer than 3 control points
+    with pytest.raises(RuntimeError, match='out of range'):
+        cps, widths = _pool(2, seed=1)
+        be.set_tracks_from_control_points(cps, widths, env_to_track=np.full(8, 5))
+    cps, widths = _pool(2, seed=1)
+    be.set_tracks_from_control_points(cps, widths)
+    with pytest.raises(RuntimeError, match='out of range'):
+        be.get_track(7)
+    be.reset()
+    be.step()                                                                 # and it still works afterwards
+    be.close()
+    with pytest.raises(RuntimeError, match='invalid config'):
+        B.RacingBackend(8, kind='single', num_sensors=65)                     # RK_MAX_SENSORS = 64
+    with pytest.raises(RuntimeError, match='invalid config'):
+        B.RacingBackend(8, kind='multi', num_agents=9)                        # RK_MAX_AGENTS = 8
+
+
+def test_extreme_track_shapes(B):
+    """Smallest (3 control points) and a long (60 control points, 1800 waypoints,
+    3600 segments) track, one env each, against the oracle in both query modes."""
+    th = np.linspace(0, 2 * np.pi, 60, endpoint=False)
+    big = np.column_stack([(90 + 12 * np.sin(5 * th)) * np.cos(th), (70 + 9 * np.cos(3 * th)) * np.sin(th)])
+    tri = np.array([[0.0, 0.0], [80.0, 0.0], [40.0, 70.0]])
+    cps, widths = [tri, big], [7.0, 8.0]
+    tracks = O.make_pool(cps, widths)
+    rs = np.random.RandomState(0)
+    for query in QUERY_MODES:
+        orc = O.OracleVecEnv(tracks, [0, 1, 0, 1], kind='single', num_sensors=11)
+        be = B.RacingBackend(4, kind='single', num_sensors=11, query=query)
+        be.set_tracks_from_control_points(cps, widths, env_to_track=[0, 1, 0, 1])
+        for i in range(2):
+            np.testing.assert_allclose(be.get_track(i)['waypoints'], tracks[i].waypoints, rtol=0, atol=1e-10)
+        oobs, _ = orc.reset()
+        np.testing.assert_allclose(be.reset().cpu().numpy(), oobs, atol=OBS_ATOL)
+        for k in range(150):
+            a = rs.uniform([-0.4, 0.3], [0.4, 1.0], size=(4, 1, 2)).astype(np.float32)
+            oobs, orew, ote, otr, _ = orc.step(a)
+            be.actions.copy_(torch.from_numpy(a))
+            be.step()
+            np.testing.assert_array_equal(be.terminated.cpu().numpy().astype(bool), ote, err_msg=f'step {k}')
+            np.testing.assert_allclose(be.obs.cpu().numpy(), oobs, rtol=0, atol=OBS_ATOL, err_msg=f'step {k}')
+            np.testing.assert_allclose(be.reward64.cpu().numpy(), orew, rtol=0, atol=STATE_ATOL, err_msg=f'step {k}')
+        be.close()
