@@ -138,6 +138,10 @@ typedef struct rk_step_io {
     /* running totals over finished episodes, accumulated atomically: {sum of
      * returns, sum of lengths, count} -- what PPO.train averages (agent/ppo.py:272-276) */
     double* ep_stats;            /* inout [3] or NULL */
+    /* Step only environments [env_begin, env_begin + env_count) (env_count <= 0: all).  Lets a
+     * caller split one logical step into chunks on several streams so that the device->host
+     * copy of one chunk overlaps the kernel of the next (BatchedRacingVecEnv.step does). */
+    int32_t env_begin, env_count;
 } rk_step_io;
 RK_API int rk_step(rk_handle h, const rk_step_io* io, void* stream);
 

@@ -37,7 +37,7 @@ class RkStepIO(C.Structure):
                 ('terminated', C.c_void_p), ('truncated', C.c_void_p), ('done', C.c_void_p),
                 ('done_f32', C.c_void_p), ('ep_mask', C.c_void_p), ('ep_return', C.c_void_p),
                 ('ep_length', C.c_void_p), ('info_f64', C.c_void_p), ('info_i32', C.c_void_p),
-                ('ep_stats', C.c_void_p)]
+                ('ep_stats', C.c_void_p), ('env_begin', C.c_int32), ('env_count', C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/racing_b200.h declares

@@ -183,10 +183,12 @@ class RacingBackend:
                                      self._stream()), self.h, 'rk_reset')
         return self.obs
 
-    def step(self, start_slot=None):
-        """One step of all environments on self.actions; outputs land in the
-        pre-allocated tensors (obs, reward, terminated, truncated, done, ep_*)."""
+    def step(self, start_slot=None, env_range=None):
+        """One step of all environments (or of env_range = (begin, end)) on
+        self.actions; outputs land in the pre-allocated tensors (obs, reward,
+        terminated, truncated, done, ep_*)."""
         self._io.start_slot = start_slot.data_ptr() if start_slot is not None else None
+        self._io.env_begin, self._io.env_count = (env_range[0], env_range[1] - env_range[0]) if env_range else (0, 0)
         _lib.check(self.lib.rk_step(self.h, C.byref(self._io), self._stream()), self.h, 'rk_step')
 
     def observe(self):

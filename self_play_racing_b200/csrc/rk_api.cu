@@ -372,6 +372,8 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
+    p.env_begin = 0;
+    p.env_end = h->cfg.num_envs;
     p.autoreset = h->cfg.autoreset_mode;
     p.max_steps = h->cfg.max_episode_steps;
     p.speed_weight = h->cfg.speed_weight;
@@ -410,6 +412,16 @@ int rk_step(rk_handle h, const rk_step_io* io, void* stream) {
     if (fill_params(h, p, "rk_step")) return 1;
     p.mode = 0;
     p.io = *io;
+    if (io->env_count > 0) {
+        if (io->env_begin < 0 || io->env_begin + io->env_count > h->cfg.num_envs) {
+            snprintf(h->err, sizeof(h->err), "rk_step: environment range [%d, %d) out of bounds", io->env_begin,
+                     io->env_begin + io->env_count);
+            return 1;
+        }
+        p.env_begin = io->env_begin;
+        p.env_end = io->env_begin + io->env_count;
+        p.group_env = nullptr;  // a sub-range is always a plain launch
+    }
     if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, (cudaStream_t)stream)) {
         snprintf(h->err, sizeof(h->err), "rk_step: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;

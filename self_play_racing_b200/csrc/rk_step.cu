@@ -498,13 +498,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         stm.bpt_off = 0; stm.bchunk_off = 0; stm.wchunk_off = 0;
         __syncthreads();  // the barrier is initialised before any warp polls it (every thread reaches this point)
     }
-    int e_base = gwarp * epw, n_env;
+    int e_base = p.env_begin + gwarp * epw, n_env;
     if (STAGED) {
         n_env = p.group_count[gwarp];
         if (n_env == 0) return;
     } else {
-        if (e_base >= p.E) return;
-        n_env = min(epw, p.E - e_base);
+        if (e_base >= p.env_end) return;
+        n_env = min(epw, p.env_end - e_base);
     }
     const int* genv = STAGED ? p.group_env + (size_t)gwarp * epw : nullptr;
     unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
@@ -989,8 +989,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream) {
     const bool staged = p.group_env != nullptr;
     const int epw = p.epw;
-    const int warps = (p.E + epw - 1) / epw;
+    const int warps = (p.env_end - p.env_begin + epw - 1) / epw;
     const int grid = staged ? p.n_ctas : (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid <= 0) return 0;
     const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R) + (staged ? (size_t)p.stage_bytes : 0);
     using Kern = void (*)(const StepParams);
     const bool single = env_kind == RK_ENV_SINGLE, culled = query_mode == RK_QUERY_CULLED;

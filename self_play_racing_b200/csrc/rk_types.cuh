@@ -82,6 +82,7 @@ struct StepParams {
     int32_t n_shells;  // distance shells of the ray sweep: (-inf, shell[0]], (shell[0], shell[1]], ...
     float shell[4];
     int32_t E, A, R, D;
+    int32_t env_begin, env_end;  // environments stepped by this launch (plain launch only)
     int32_t autoreset, max_steps;
     double speed_weight;
     uint64_t seed;

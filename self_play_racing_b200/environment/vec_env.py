@@ -54,7 +54,8 @@ class _EnvProxy:
 
 class BatchedRacingVecEnv:
     def __init__(self, env_fns, device=None, query='culled', autoreset='next_step', seed=0, copy=True,
-                 want_info=False):
+                 want_info=False, pipeline_chunks=None):
+        self.pipeline_chunks = pipeline_chunks
         envs = [fn() if callable(fn) else fn for fn in env_fns]
         if not envs:
             raise ValueError('need at least one environment')
@@ -94,10 +95,11 @@ class BatchedRacingVecEnv:
     @classmethod
     def synthetic(cls, kind, num_envs, n_tracks=16, num_agents=2, num_sensors=11, selfplay=True, device=None,
                   query='culled', autoreset='next_step', seed=0, copy=True, factor=30, width_lo=6.0, width_mod=4,
-                  want_info=False):
+                  want_info=False, pipeline_chunks=None):
         """E environments over a device-generated procedural pool (BASELINE
         configs 2-5): env e runs on track e % n_tracks, widths width_lo + (t % width_mod)."""
         self = cls.__new__(cls)
+        self.pipeline_chunks = pipeline_chunks
         self.kind = kind
         self.num_envs = int(num_envs)
         self.num_agents = 1 if kind == 'single' else int(num_agents)
@@ -148,6 +150,15 @@ class BatchedRacingVecEnv:
         self._np_truncated = a[o['truncated']:o['truncated'] + E].view(np.bool_)
         self._np_ep_mask = a[o['ep_mask']:o['ep_mask'] + E].view(np.bool_)
         self._np_reward = a[o['reward64']:o['reward64'] + 8 * E].view(np.float64)
+        # Optional Gymnasium-face pipeline: the batch is stepped in chunks on side streams so that the
+        # device->host copy of one chunk's observations overlaps the kernel of the next.  Measured on
+        # B200 (profiles/r01_e2e_pipeline.log) the extra launches cost more than the overlap wins at
+        # 65,536 envs, so the default is a single chunk.
+        if self.pipeline_chunks is None:
+            import os
+            self.pipeline_chunks = int(os.environ.get('RK_B200_PIPELINE_CHUNKS', 1))
+        self._streams = [torch.cuda.Stream(device=be.device) for _ in range(self.pipeline_chunks)] \
+            if self.pipeline_chunks > 1 else []
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
@@ -250,16 +261,19 @@ class BatchedRacingVecEnv:
         step; by default they come from the backend's Philox stream."""
         be = self.be
         self._h_actions.numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
-        be.actions[0].copy_(self._h_actions, non_blocking=True)
-        if self.selfplay:
-            self._opponent_act()
-        if start_slot is not None:
-            start_slot = torch.as_tensor(np.ascontiguousarray(start_slot, dtype=np.int32)).to(be.device)
-        be.step(start_slot=start_slot)
+        if self.pipeline_chunks > 1 and start_slot is None:
+            self._step_pipelined()
+        else:
+            be.actions[0].copy_(self._h_actions, non_blocking=True)
+            if self.selfplay:
+                self._opponent_act()
+            if start_slot is not None:
+                start_slot = torch.as_tensor(np.ascontiguousarray(start_slot, dtype=np.int32)).to(be.device)
+            be.step(start_slot=start_slot)
+            self._h_obs.copy_(be.obs[0], non_blocking=True)
+            self._h_arena.copy_(be.arena[:be.arena_host_bytes], non_blocking=True)
+            torch.cuda.current_stream(be.device).synchronize()
         self._obs_cur = be.obs
-        self._h_obs.copy_(be.obs[0], non_blocking=True)
-        self._h_arena.copy_(be.arena[:be.arena_host_bytes], non_blocking=True)
-        torch.cuda.current_stream(be.device).synchronize()
         obs, rew = self._h_obs.numpy(), self._np_reward
         term, trunc = self._np_terminated, self._np_truncated
         if self.selfplay:  # wrappers.py:52: the wrapper reports dones["__all__"] as `terminated`
@@ -271,6 +285,33 @@ class BatchedRacingVecEnv:
         if self.copy:
             return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
         return obs, rew, term, trunc, infos
+
+    def _step_pipelined(self):
+        # One logical step as `pipeline_chunks` range launches on side streams: chunk i's
+        # host->device actions, opponent inference, step kernel and device->host observation
+        # copy are ordered on stream i; the small per-env results follow once on the last one.
+        be, E = self.be, self.num_envs
+        cur = torch.cuda.current_stream(be.device)
+        n = self.pipeline_chunks
+        bounds = [E * i // n for i in range(n + 1)]
+        self._opp_counter += 1
+        for i, s in enumerate(self._streams):
+            lo, hi = bounds[i], bounds[i + 1]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                be.actions[0, lo:hi].copy_(self._h_actions[lo:hi], non_blocking=True)
+                if self.selfplay:
+                    policy_act(self._opp_params, be.obs[1, lo:hi] if self._opp_params is not None else None,
+                               be.actions[1, lo:hi], seed=self.seed ^ 0x5eed0bb, counter=self._opp_counter * 64 + i)
+                be.step(env_range=(lo, hi))
+                self._h_obs[lo:hi].copy_(be.obs[0, lo:hi], non_blocking=True)
+        last = self._streams[-1]
+        for s in self._streams[:-1]:
+            last.wait_stream(s)
+        with torch.cuda.stream(last):
+            self._h_arena.copy_(be.arena[:be.arena_host_bytes], non_blocking=True)
+        last.synchronize()
+        cur.wait_stream(last)
 
     def close(self):
         if getattr(self, 'be', None) is not None:

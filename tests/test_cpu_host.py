@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f'{n} has no ctypes signature in _lib.py'
     assert set(_lib.SIGNATURES) == set(names)
     assert lib.rk_abi_version() == 1
-    assert ctypes.sizeof(_lib.RkConfig) == 56 and ctypes.sizeof(_lib.RkStepIO) == 8 + 15 * 8
+    assert ctypes.sizeof(_lib.RkConfig) == 56 and ctypes.sizeof(_lib.RkStepIO) == 8 + 15 * 8 + 8
 
 
 def test_no_cpu_fallback_without_a_device():
