@@ -253,6 +253,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=None)
     ap.add_argument('--tracks', type=int, default=None, help='size of the procedural track pool (default 16)')
+    ap.add_argument('--factor', type=int, default=None, help='waypoints per control point (reference: 30); S = 2 * n_ctrl * factor')
     ap.add_argument('--query', default='culled', choices=['culled', 'exact'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ppo-updates', type=int, default=2,
@@ -266,6 +267,8 @@ def main():
         wl['E'] = args.envs
     if args.tracks:
         wl['tracks'] = args.tracks
+    if args.factor:
+        wl['factor'] = args.factor
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -423,7 +426,7 @@ def main():
                 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f64 state + f32 candidate search', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'envs_per_gpu': E, 'cars_per_env': A, 'rays': R,
-                           'tracks': wl['tracks'], 'waypoints_per_track': '300-420', 'query': args.query,
+                           'tracks': wl['tracks'], 'waypoints_per_track': f"{10 * wl['factor']}-{14 * wl['factor']}", 'query': args.query,
                            'autoreset': 'next_step', 'actions': 'uniform random, resident in HBM',
                            'opponent': 'frozen MLP snapshot (fused inference kernel)' if wl['selfplay'] else None,
                            'l2': 'flushed between timed steps (256 MiB memset outside the event pair)'},
