@@ -247,7 +247,7 @@ def fp_peaks(torch, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=500)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--workload', default='multi2_selfplay_65536', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
