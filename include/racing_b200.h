@@ -145,6 +145,29 @@ typedef struct rk_step_io {
 } rk_step_io;
 RK_API int rk_step(rk_handle h, const rk_step_io* io, void* stream);
 
+/* One step with HOST buffers -- the call SyncVectorEnv.step(actions) -> (obs, rewards, ...)
+ * maps to (agent/ppo.py:114-120).  `io` names the caller's DEVICE buffers exactly as for
+ * rk_step and must use RK_LAYOUT_AGENT_MAJOR; `host` names the host side.  The batch is cut
+ * into n_chunks environment ranges, each on its own internal stream: host->device copy of the
+ * learner's actions, (self-play) the opponent's inference, the step kernel over that range,
+ * device->host copy of car 0's observations -- so the copies of one chunk overlap the kernels
+ * of the others; the small per-environment results (arena_*) follow in one copy.  Returns
+ * when every host output is complete.  Host buffers should be page-locked. */
+typedef struct rk_host_io {
+    int32_t struct_size;
+    int32_t n_chunks;             /* 1..8                                                        */
+    const float* actions;         /* host in  [E,2]: car 0's actions                             */
+    float* obs;                   /* host out [E,D]: car 0's observations                        */
+    void* arena_host;             /* host out: arena_bytes copied from arena_dev (or NULL)       */
+    const void* arena_dev;        /* device: contiguous block holding the small per-env results  */
+    int64_t arena_bytes;
+    int32_t selfplay;             /* != 0: car 1 is driven here (SelfPlayWrapper, wrappers.py:29-45) */
+    int32_t reserved0;
+    const float* opponent_params; /* device, packed Agent (see rk_policy_act) or NULL = uniform Box samples */
+    uint64_t seed, counter;       /* Philox stream of the opponent's sampling                    */
+} rk_host_io;
+RK_API int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream);
+
 /* RacingEnv.speed_weight (racing_env.py:26; annealed by agent/ppo.py:256-258) */
 RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
 

@@ -40,6 +40,13 @@ class RkStepIO(C.Structure):
                 ('ep_stats', C.c_void_p), ('env_begin', C.c_int32), ('env_count', C.c_int32)]
 
 
+class RkHostIO(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('n_chunks', C.c_int32), ('actions', C.c_void_p), ('obs', C.c_void_p),
+                ('arena_host', C.c_void_p), ('arena_dev', C.c_void_p), ('arena_bytes', C.c_int64),
+                ('selfplay', C.c_int32), ('reserved0', C.c_int32), ('opponent_params', C.c_void_p),
+                ('seed', C.c_uint64), ('counter', C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol include/racing_b200.h declares
 SIGNATURES = {
     'rk_create': (C.c_int, [C.POINTER(RkConfig), C.POINTER(C.c_void_p)]),
@@ -57,6 +64,7 @@ SIGNATURES = {
     'rk_get_track': (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
     'rk_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'rk_step': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.c_void_p]),
+    'rk_step_host': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.POINTER(RkHostIO), C.c_void_p]),
     'rk_set_speed_weight': (C.c_int, [C.c_void_p, C.c_double]),
     'rk_get_state': (C.c_int, [C.c_void_p] * 5),
     'rk_set_state': (C.c_int, [C.c_void_p] * 5),

@@ -43,6 +43,9 @@ struct rk_env_s {
     // staged launch plan (environments grouped by track); null when not applicable
     int32_t *group_env = nullptr, *group_count = nullptr, *cta_track = nullptr;
     int n_ctas = 0, stage_bytes = 0;
+    // internal streams / events of rk_step_host
+    cudaStream_t hstream[8] = {nullptr};
+    cudaEvent_t hevent[9] = {nullptr};
     std::vector<void*> owned;
     char err[512] = {0};
 };
@@ -159,6 +162,10 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
 int rk_destroy(rk_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
+    for (cudaStream_t st : h->hstream)
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : h->hevent)
+        if (ev) cudaEventDestroy(ev);
     for (void* p : h->owned) cudaFree(p);
     for (void* p : {(void*)h->group_env, (void*)h->group_count, (void*)h->cta_track})
         if (p) cudaFree(p);
@@ -426,6 +433,69 @@ int rk_step(rk_handle h, const rk_step_io* io, void* stream) {
         snprintf(h->err, sizeof(h->err), "rk_step: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
     }
+    return 0;
+}
+
+int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream) {
+    if (!h) return 1;
+    if (!io || io->struct_size != (int32_t)sizeof(rk_step_io) || !host ||
+        host->struct_size != (int32_t)sizeof(rk_host_io)) {
+        snprintf(h->err, sizeof(h->err), "rk_step_host: bad io structs (struct_size mismatch)");
+        return 1;
+    }
+    const int E = h->cfg.num_envs, A = h->cfg.num_agents, D = h->D;
+    if (!io->actions || !io->obs || !io->terminated || !io->truncated || !host->actions || !host->obs ||
+        io->layout != RK_LAYOUT_AGENT_MAJOR || (host->selfplay && A != 2)) {
+        snprintf(h->err, sizeof(h->err),
+                 "rk_step_host: needs device actions/obs/terminated/truncated, host actions/obs, agent-major "
+                 "layout (and 2 cars for self-play)");
+        return 1;
+    }
+    StepParams p;
+    if (fill_params(h, p, "rk_step_host")) return 1;
+    p.mode = 0;
+    p.io = *io;
+    p.group_env = nullptr;  // range launches are plain launches
+    const int n = host->n_chunks < 1 ? 1 : (host->n_chunks > 8 ? 8 : host->n_chunks);
+    cudaSetDevice(h->cfg.device);
+    for (int c = 0; c < n; ++c)
+        if (!h->hstream[c]) H_CUDA(h, cudaStreamCreateWithFlags(&h->hstream[c], cudaStreamNonBlocking));
+    for (int c = 0; c <= 8; ++c)
+        if (!h->hevent[c]) H_CUDA(h, cudaEventCreateWithFlags(&h->hevent[c], cudaEventDisableTiming));
+    // order the internal streams after whatever the caller has queued
+    H_CUDA(h, cudaEventRecord(h->hevent[8], (cudaStream_t)caller_stream));
+    float* dev_act = const_cast<float*>(io->actions);
+    for (int c = 0; c < n; ++c) {
+        cudaStream_t st = h->hstream[c];
+        const int lo = (int)((int64_t)E * c / n), hi = (int)((int64_t)E * (c + 1) / n), m = hi - lo;
+        if (m <= 0) continue;
+        H_CUDA(h, cudaStreamWaitEvent(st, h->hevent[8], 0));
+        H_CUDA(h, cudaMemcpyAsync(dev_act + 2 * (size_t)lo, host->actions + 2 * (size_t)lo, (size_t)m * 2 * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+        if (host->selfplay) {  // car 1: obs block [E + lo, E + hi), action block likewise (agent-major)
+            if (launch_policy_act(host->opponent_params, D, io->obs + ((size_t)E + lo) * D, D, m, host->seed,
+                                  host->counter * 64 + (uint64_t)c, dev_act + 2 * ((size_t)E + lo), 2, nullptr, nullptr,
+                                  nullptr, st)) {
+                snprintf(h->err, sizeof(h->err), "rk_step_host: opponent inference launch failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        p.env_begin = lo;
+        p.env_end = hi;
+        if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, st)) {
+            snprintf(h->err, sizeof(h->err), "rk_step_host: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        H_CUDA(h, cudaMemcpyAsync(host->obs + (size_t)lo * D, io->obs + (size_t)lo * D, (size_t)m * D * sizeof(float),
+                                  cudaMemcpyDeviceToHost, st));
+        H_CUDA(h, cudaEventRecord(h->hevent[c], st));
+    }
+    cudaStream_t last = h->hstream[n - 1];
+    for (int c = 0; c < n - 1; ++c) H_CUDA(h, cudaStreamWaitEvent(last, h->hevent[c], 0));
+    if (host->arena_host && host->arena_dev && host->arena_bytes > 0)
+        H_CUDA(h, cudaMemcpyAsync(host->arena_host, host->arena_dev, (size_t)host->arena_bytes, cudaMemcpyDeviceToHost, last));
+    H_CUDA(h, cudaStreamSynchronize(last));
     return 0;
 }
 

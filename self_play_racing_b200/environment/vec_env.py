@@ -159,6 +159,17 @@ class BatchedRacingVecEnv:
             self.pipeline_chunks = int(os.environ.get('RK_B200_PIPELINE_CHUNKS', 1))
         self._streams = [torch.cuda.Stream(device=be.device) for _ in range(self.pipeline_chunks)] \
             if self.pipeline_chunks > 1 else []
+        # default Gymnasium-face path: one C call per step with host buffers (rk_step_host), the batch cut
+        # into `host_chunks` ranges so that copies overlap kernels; 0 falls back to the torch-level path
+        import ctypes as C
+        import os as _os
+        from .. import _lib
+        self.host_chunks = int(_os.environ.get('RK_B200_HOST_CHUNKS', 4 if E >= 16384 else 1))
+        self._host_io = _lib.RkHostIO(struct_size=C.sizeof(_lib.RkHostIO), n_chunks=max(self.host_chunks, 1),
+                                      actions=self._h_actions.data_ptr(), obs=self._h_obs.data_ptr(),
+                                      arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
+                                      arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
+                                      reserved0=0, opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
@@ -261,7 +272,9 @@ class BatchedRacingVecEnv:
         step; by default they come from the backend's Philox stream."""
         be = self.be
         self._h_actions.numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
-        if self.pipeline_chunks > 1 and start_slot is None:
+        if self.host_chunks > 0:
+            self._step_host(start_slot)
+        elif self.pipeline_chunks > 1 and start_slot is None:
             self._step_pipelined()
         else:
             be.actions[0].copy_(self._h_actions, non_blocking=True)
@@ -285,6 +298,23 @@ class BatchedRacingVecEnv:
         if self.copy:
             return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
         return obs, rew, term, trunc, infos
+
+    def _step_host(self, start_slot=None):
+        # The whole Gymnasium-face step as ONE C call (rk_step_host): chunked host->device copy of the
+        # actions, opponent inference, step kernel and device->host copy of the observations on the
+        # library's internal streams, then the small per-env results; returns when the host buffers are ready.
+        import ctypes as C
+        from .. import _lib
+        be = self.be
+        self._opp_counter += 1
+        if start_slot is not None:
+            start_slot = torch.as_tensor(np.ascontiguousarray(start_slot, dtype=np.int32)).to(be.device)
+        be._io.start_slot = start_slot.data_ptr() if start_slot is not None else None
+        be._io.env_begin, be._io.env_count = 0, 0
+        h = self._host_io
+        h.counter = self._opp_counter
+        h.opponent_params = self._opp_params.data_ptr() if self._opp_params is not None else None
+        _lib.check(be.lib.rk_step_host(be.h, C.byref(be._io), C.byref(h), be._stream()), be.h, 'rk_step_host')
 
     def _step_pipelined(self):
         # One logical step as `pipeline_chunks` range launches on side streams: chunk i's

@@ -88,8 +88,12 @@ def test_vec_env_gym_face_matches_reference_vector_golden(pkg, golden):
     widths = [int(w) for w in g['widths']]
     fns = [(lambda i=i: env_mod.RacingEnv(num_sensors=11, track_pool=cps, track_id=i, track_width=widths[i]))
            for i in range(4)]
-    for query, chunks in (('exact', 1), ('culled', 1), ('culled', 3)):  # 3: the chunked multi-stream pipeline
+    # host_chunks: rk_step_host (one C call per step, chunked over internal streams); 0 = torch-level path,
+    # optionally with the torch-level chunked pipeline
+    for query, chunks, host_chunks in (('exact', 1, 1), ('culled', 1, 0), ('culled', 3, 0), ('culled', 1, 3)):
         vec = env_mod.BatchedRacingVecEnv(fns, query=query, pipeline_chunks=chunks)
+        vec.host_chunks = host_chunks
+        vec._host_io.n_chunks = max(host_chunks, 1)
         assert vec.single_observation_space.shape == (15,) and vec.single_action_space.shape == (2,)
         obs, infos = vec.reset()
         assert obs.dtype == np.float32 and infos == {}
