@@ -24,16 +24,35 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
     float running = 0.f;
     float nnt = __fsub_rn(1.f, next_done[e]);  // ppo.py:141-143
     float nv = next_value[e];
-    for (int t = T - 1; t >= 0; --t) {
+    constexpr int kBatch = 8;  // loads of kBatch time steps are issued together: the recurrence is serial, the loads are not
+    int t = T - 1;
+    for (; t >= kBatch - 1; t -= kBatch) {
+        float r[kBatch], v[kBatch], d[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const size_t i = (size_t)(t - k) * E + e;
+            r[k] = rewards[i]; v[k] = values[i]; d[k] = dones[i];
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const size_t i = (size_t)(t - k) * E + e;
+            // ppo.py:149: delta = r + gamma * nnt * V' - V (left to right); ppo.py:151: A = delta + (gamma*lambda) * nnt * A'
+            const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(gamma, nnt), nv)), v[k]);
+            running = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), running));
+            adv[i] = running;
+            ret[i] = __fadd_rn(running, v[k]);  // ppo.py:152
+            nnt = __fsub_rn(1.f, d[k]);         // ppo.py:145-146 for the next (earlier) step
+            nv = v[k];
+        }
+    }
+    for (; t >= 0; --t) {
         const size_t i = (size_t)t * E + e;
         const float v = values[i];
-        // ppo.py:149: delta = r + gamma * nnt * V' - V        (left to right)
         const float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(__fmul_rn(gamma, nnt), nv)), v);
-        // ppo.py:151: A = delta + (gamma*lambda) * nnt * A'
         running = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), running));
         adv[i] = running;
-        ret[i] = __fadd_rn(running, v);  // ppo.py:152
-        nnt = __fsub_rn(1.f, dones[i]);  // ppo.py:145-146 for the next (earlier) step
+        ret[i] = __fadd_rn(running, v);
+        nnt = __fsub_rn(1.f, dones[i]);
         nv = v;
     }
 }
@@ -200,17 +219,34 @@ __global__ void gather_minibatch_kernel(const int64_t* __restrict__ idx, int n, 
                                         const float* __restrict__ ret, const float* __restrict__ val,
                                         float* __restrict__ o_obs, float* __restrict__ o_act, float* __restrict__ o_logp,
                                         float* __restrict__ o_adv, float* __restrict__ o_ret, float* __restrict__ o_val) {
-    // one warp per sample row: lanes copy the obs_dim observation floats, lanes 0..5 the scalars
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= n) return;
-    const int64_t src = idx[row];
-    for (int k = lane; k < obs_dim; k += 32) o_obs[(size_t)row * obs_dim + k] = obs[(size_t)src * obs_dim + k];
-    if (lane == 0) o_act[2 * (size_t)row] = act[2 * (size_t)src];
-    if (lane == 1) o_act[2 * (size_t)row + 1] = act[2 * (size_t)src + 1];
-    if (lane == 2) o_logp[row] = logp[src];
-    if (lane == 3) o_adv[row] = adv[src];
-    if (lane == 4) o_ret[row] = ret[src];
-    if (lane == 5) o_val[row] = val[src];
+    // a warp handles kRows sample rows at once (their random-row loads are all in flight
+    // together): lanes copy the obs_dim observation floats, lanes 0..5 the scalars
+    constexpr int kRows = 4;
+    const int lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRows;
+    if (row0 >= n) return;
+    int64_t src[kRows];
+    float o[kRows], sc[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) src[k] = idx[min(row0 + k, n - 1)];
+    const float* scal = lane == 2 ? logp : lane == 3 ? adv : lane == 4 ? ret : val;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        o[k] = lane < obs_dim ? obs[(size_t)src[k] * obs_dim + lane] : 0.f;
+        sc[k] = lane < 2 ? act[2 * (size_t)src[k] + lane] : (lane < 6 ? scal[src[k]] : 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const int row = row0 + k;
+        if (row >= n) break;
+        if (lane < obs_dim) o_obs[(size_t)row * obs_dim + lane] = o[k];
+        for (int j = lane + 32; j < obs_dim; j += 32) o_obs[(size_t)row * obs_dim + j] = obs[(size_t)src[k] * obs_dim + j];
+        if (lane < 2) o_act[2 * (size_t)row + lane] = sc[k];
+        if (lane == 2) o_logp[row] = sc[k];
+        if (lane == 3) o_adv[row] = sc[k];
+        if (lane == 4) o_ret[row] = sc[k];
+        if (lane == 5) o_val[row] = sc[k];
+    }
 }
 
 // Gradients of  loss = pg_loss + vf_coef * v_loss  (+ an entropy term that is constant in
@@ -298,8 +334,8 @@ int policy_param_count(int obs_dim) { return policy_packed_floats(obs_dim); }
 int launch_gather_minibatch(const int64_t* idx, int n, int obs_dim, const float* obs, const float* act,
                             const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,
                             float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val, cudaStream_t stream) {
-    const int rows_per_block = 8;
-    gather_minibatch_kernel<<<(n + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+    const int rows_per_block = 8 * 4;  // 8 warps x 4 rows
+    gather_minibatch_kernel<<<(n + rows_per_block - 1) / rows_per_block, 8 * 32, 0, stream>>>(
         idx, n, obs_dim, obs, act, logp, adv, ret, val, o_obs, o_act, o_logp, o_adv, o_ret, o_val);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
