@@ -227,6 +227,47 @@ RK_API int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, c
                             const float* adv_std, int32_t n, float clip_coef, float vf_coef, float* dmu, float* dv,
                             double* kl_sum, void* stream);
 
+/* ---- fused minibatch gradient: forward + loss + backward of PPO.ppo_update --------
+ * (agent/ppo.py:170-206 up to and including loss.backward(); gradient clipping and
+ * Adam stay with the caller's optimizer).  The Agent's two 64-64 tanh MLPs
+ * (agent/ppo.py:11-37) are evaluated, differentiated and their weight gradients
+ * reduced over the minibatch by ONE kernel, fp32 throughout; nothing of size
+ * [minibatch, 64] ever reaches HBM.  obs_dim <= RK_PPO_MAX_OBS_DIM. */
+#define RK_ADV_STAT_BLOCKS 64
+#define RK_PPO_MAX_OBS_DIM 20
+/* partial (sum, sum of squares) in float64 of the minibatch's advantages adv[idx[k]],
+ * k < n (idx NULL: adv[k]); part: double [RK_ADV_STAT_BLOCKS][2].  With several ranks
+ * the caller all-reduces `part` so that every rank normalises with the statistics of
+ * the GLOBAL minibatch (ppo.py:187 `mb_adv.mean()`, `mb_adv.std()` unbiased). */
+RK_API int rk_ppo_adv_stats(const int64_t* idx, const float* adv, int32_t n, double* part, void* stream);
+
+typedef struct rk_ppo_grad_io {
+    int32_t struct_size;       /* sizeof(rk_ppo_grad_io) */
+    int32_t obs_dim;
+    int32_t n;                 /* rows of this rank's minibatch */
+    int32_t reserved0;
+    double n_global;           /* rows of the global minibatch (n * world size) */
+    /* parameters in torch layout [out][in]: actor_mu.{0,2,4}.{weight,bias} then critic.{0,2,4}.{weight,bias} */
+    const float* params[12];
+    const float* log_std;      /* [2] */
+    /* the flat rollout buffers (agent/ppo.py:158-165) and the minibatch's row indices into them */
+    const float* obs;          /* [B, obs_dim] */
+    const float* act;          /* [B, 2] */
+    const float* old_logp;     /* [B] */
+    const float* adv;          /* [B] raw advantages; normalised inside with `adv_part` */
+    const float* ret;          /* [B] */
+    const float* val;          /* [B] */
+    const int64_t* idx;        /* [n] or NULL for rows 0..n-1 */
+    const double* adv_part;    /* [RK_ADV_STAT_BLOCKS][2] from rk_ppo_adv_stats (summed over ranks) */
+    float clip_coef, vf_coef;
+    void* workspace;           /* device scratch of rk_ppo_grad_workspace_bytes() bytes */
+    uint64_t workspace_bytes;
+    float* flat_grad;          /* out: d loss / d params, concatenated in the order of `params` */
+    double* kl_sum;            /* out: sum over the n rows of (logp_old - logp_new)  (ppo.py:178-182) */
+} rk_ppo_grad_io;
+RK_API uint64_t rk_ppo_grad_workspace_bytes(void);
+RK_API int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream);
+
 /* ---- measurement aid --------------------------------------------------------- */
 /* Sustained FMA throughput of the current device in TFLOP/s (fp32, or fp64 when
  * use_fp64 != 0): the non-tensor roofline denominator bench.py reports the step

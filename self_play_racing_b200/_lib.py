@@ -40,6 +40,15 @@ class RkStepIO(C.Structure):
                 ('ep_stats', C.c_void_p), ('env_begin', C.c_int32), ('env_count', C.c_int32)]
 
 
+class RkPpoGradIO(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('obs_dim', C.c_int32), ('n', C.c_int32), ('reserved0', C.c_int32),
+                ('n_global', C.c_double), ('params', C.c_void_p * 12), ('log_std', C.c_void_p),
+                ('obs', C.c_void_p), ('act', C.c_void_p), ('old_logp', C.c_void_p), ('adv', C.c_void_p),
+                ('ret', C.c_void_p), ('val', C.c_void_p), ('idx', C.c_void_p), ('adv_part', C.c_void_p),
+                ('clip_coef', C.c_float), ('vf_coef', C.c_float), ('workspace', C.c_void_p),
+                ('workspace_bytes', C.c_uint64), ('flat_grad', C.c_void_p), ('kl_sum', C.c_void_p)]
+
+
 class RkHostIO(C.Structure):
     _fields_ = [('struct_size', C.c_int32), ('n_chunks', C.c_int32), ('actions', C.c_void_p), ('obs', C.c_void_p),
                 ('arena_host', C.c_void_p), ('arena_dev', C.c_void_p), ('arena_bytes', C.c_int64),
@@ -76,6 +85,9 @@ SIGNATURES = {
     'rk_policy_param_count': (C.c_int, [C.c_int32]),
     'rk_fma_peak': (C.c_double, [C.c_int32, C.c_int32]),
     'rk_gather_minibatch': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 13),
+    'rk_ppo_adv_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'rk_ppo_grad_workspace_bytes': (C.c_uint64, []),
+    'rk_ppo_minibatch_grad': (C.c_int, [C.POINTER(RkPpoGradIO), C.c_void_p]),
     'rk_ppo_loss_grad': (C.c_int, [C.c_void_p] * 10 + [C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 import torch.optim as optim
 
-from ..backend import flatten_agent, gae as gae_kernel, gather_minibatch, policy_act, ppo_loss_grad
+from ..backend import (PPO_MAX_OBS_DIM, PpoMinibatchGrad, flatten_agent, gae as gae_kernel, gather_minibatch,
+                       policy_act, ppo_loss_grad)
 from ..environment.vec_env import BatchedRacingVecEnv
 
 
@@ -119,8 +120,17 @@ class _GraphedMinibatch:
         opt = ppo.optimizer
 
         fused = c.get('fused_update_kernels', True)
+        # 'fused_mlp_update': forward + loss + backward of both MLPs as ONE kernel reading the rollout
+        # buffers through the minibatch indices (rk_ppo_minibatch_grad); only clip + Adam stay a graph
+        self.fused_mlp = bool(fused and c.get('fused_mlp_update', True) and obs_dim <= PPO_MAX_OBS_DIM
+                              and len(params) == 12)
         self.dmu, self.dv = z(mb, 2), z(mb)
         agent = ppo.agent
+        if self.fused_mlp:
+            self.grad = PpoMinibatchGrad(params, agent.log_std, obs_dim, c['clip_coef'], c['vf_coef'])
+            self.flat_grad, self.kl_sum = self.grad.flat_grad, self.grad.kl_sum
+            for p, gview in zip(params, self.grad.grad_views()):
+                p.grad = gview                      # the kernel writes the gradients where Adam reads them
 
         def fwd_bwd():
             opt.zero_grad(set_to_none=False)
@@ -142,7 +152,10 @@ class _GraphedMinibatch:
                 torch.cat([p.grad.reshape(-1) for p in params], out=self.flat_grad)
 
         def clip_step():
-            if world > 1:
+            if self.fused_mlp:
+                if world > 1:
+                    self.flat_grad.div_(world)
+            elif world > 1:
                 off = 0
                 for p in params:
                     p.grad.copy_(self.flat_grad[off:off + p.numel()].view_as(p)).div_(world)
@@ -159,7 +172,8 @@ class _GraphedMinibatch:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(3):
-                fwd_bwd()
+                if not self.fused_mlp:
+                    fwd_bwd()
                 clip_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         with torch.no_grad():
@@ -169,6 +183,10 @@ class _GraphedMinibatch:
                     if torch.is_tensor(v):
                         v.copy_(had_state[id(p)][k]) if id(p) in had_state else v.zero_()
         self.fwd_bwd, self.clip_step = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        if self.fused_mlp:
+            with torch.cuda.graph(self.clip_step):
+                clip_step()
+            return
         with torch.cuda.graph(self.fwd_bwd):
             fwd_bwd()
         with torch.cuda.graph(self.clip_step, pool=self.fwd_bwd.pool()):
@@ -382,6 +400,21 @@ class PPO:
             perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
             for start in range(0, n_local - mb + 1, mb):
                 idx = perm[start:start + mb]
+                if g.fused_mlp:
+                    part = g.grad.stats(idx, b_adv)
+                    self._all_reduce(part)
+                    g.grad(idx, b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values, n_global=n_glob)
+                    if self.world > 1:
+                        self._all_reduce(g.kl_sum)
+                        self._all_reduce(g.flat_grad)
+                    approx_kl = float(g.kl_sum) / n_glob  # host sync: the early-stop test needs the value
+                    if approx_kl > c['kl_target']:
+                        if self.rank == 0:
+                            print(f'  Early stopping at epoch {epoch + 1} due to KL divergence: {approx_kl:.4f}')
+                        return n_steps
+                    g.clip_step.replay()
+                    n_steps += 1
+                    continue
                 if fused:
                     gather_minibatch(idx, (b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values),
                                      (g.obs, g.act, g.old_logp, g.adv, g.ret, g.val))

@@ -299,3 +299,76 @@ def ppo_loss_grad(mu, v, act, old_logp, adv, ret, v_old, log_std, adv_mean, adv_
                                     _ptr(log_std), _ptr(adv_mean), _ptr(adv_std), mu.shape[0], float(clip_coef),
                                     float(vf_coef), _ptr(dmu), _ptr(dv), _ptr(kl_sum), stream), None,
                'rk_ppo_loss_grad')
+
+
+ADV_STAT_BLOCKS = 64     # RK_ADV_STAT_BLOCKS
+PPO_MAX_OBS_DIM = 20     # RK_PPO_MAX_OBS_DIM
+
+
+def ppo_adv_stats(idx, adv, part):
+    """part[b] = (sum, sum of squares) in float64 of block b's share of adv[idx]
+    (idx None: adv itself); part: float64 [ADV_STAT_BLOCKS, 2]."""
+    lib = _lib.load()
+    n = adv.numel() if idx is None else idx.numel()
+    stream = C.c_void_p(torch.cuda.current_stream(adv.device).cuda_stream)
+    _lib.check(lib.rk_ppo_adv_stats(_ptr(idx), _ptr(adv), n, _ptr(part), stream), None, 'rk_ppo_adv_stats')
+
+
+class PpoMinibatchGrad:
+    """Forward + PPO loss + backward of the Agent's two MLPs as one kernel
+    (rk_ppo_minibatch_grad).  Holds the argument block, the scratch buffer and the
+    flat gradient; `params` are the twelve weight/bias tensors in
+    `Agent.parameters()` order (actor_mu.{0,2,4}, critic.{0,2,4}), read in place."""
+
+    def __init__(self, params, log_std, obs_dim, clip_coef, vf_coef):
+        lib = _lib.load()
+        params = list(params)
+        if len(params) != 12 or obs_dim > PPO_MAX_OBS_DIM:
+            raise ValueError('PpoMinibatchGrad: needs the 12 Agent parameters and obs_dim <= %d' % PPO_MAX_OBS_DIM)
+        dev = params[0].device
+        self._keep = (params, log_std)
+        self.device = dev
+        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+        self.kl_sum = torch.zeros((), device=dev, dtype=torch.float64)
+        self.adv_part = torch.zeros(ADV_STAT_BLOCKS, 2, device=dev, dtype=torch.float64)
+        nbytes = int(lib.rk_ppo_grad_workspace_bytes())
+        self.workspace = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        io = _lib.RkPpoGradIO()
+        io.struct_size = C.sizeof(_lib.RkPpoGradIO)
+        io.obs_dim = int(obs_dim)
+        for k, p in enumerate(params):
+            if not (p.is_cuda and p.is_contiguous() and p.dtype == torch.float32):
+                raise ValueError('PpoMinibatchGrad: parameters must be contiguous float32 CUDA tensors')
+            io.params[k] = p.data_ptr()
+        io.log_std = log_std.data_ptr()
+        io.adv_part = self.adv_part.data_ptr()
+        io.clip_coef, io.vf_coef = float(clip_coef), float(vf_coef)
+        io.workspace, io.workspace_bytes = self.workspace.data_ptr(), nbytes
+        io.flat_grad, io.kl_sum = self.flat_grad.data_ptr(), self.kl_sum.data_ptr()
+        self.io = io
+
+    def grad_views(self):
+        """Views of flat_grad shaped like the parameters (to be installed as .grad)."""
+        out, off = [], 0
+        for p in self._keep[0]:
+            out.append(self.flat_grad[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return out
+
+    def stats(self, idx, adv):
+        ppo_adv_stats(idx, adv, self.adv_part)
+        return self.adv_part
+
+    def __call__(self, idx, obs, act, old_logp, adv, ret, val, n_global=None):
+        """flat_grad, kl_sum <- gradient of the minibatch rows idx (None: all rows);
+        the advantage statistics must already be in self.adv_part (`stats`)."""
+        lib = _lib.load()
+        io = self.io
+        io.n = int(obs.shape[0] if idx is None else idx.numel())
+        io.n_global = float(n_global if n_global is not None else io.n)
+        io.obs, io.act, io.old_logp = obs.data_ptr(), act.data_ptr(), old_logp.data_ptr()
+        io.adv, io.ret, io.val = adv.data_ptr(), ret.data_ptr(), val.data_ptr()
+        io.idx = None if idx is None else idx.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(lib.rk_ppo_minibatch_grad(C.byref(io), stream), None, 'rk_ppo_minibatch_grad')
+        return self.flat_grad, self.kl_sum

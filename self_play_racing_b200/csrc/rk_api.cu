@@ -638,6 +638,45 @@ int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, const fl
                                 vf_coef, dmu, dv, kl_sum, (cudaStream_t)stream);
 }
 
+int rk_ppo_adv_stats(const int64_t* idx, const float* adv, int32_t n, double* part, void* stream) {
+    if (!adv || !part || n <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adv_stats: invalid arguments");
+        return 1;
+    }
+    return launch_adv_stats(idx, adv, n, part, (cudaStream_t)stream);
+}
+
+uint64_t rk_ppo_grad_workspace_bytes(void) { return (uint64_t)ppo_grad_workspace_bytes(); }
+
+int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
+    if (!io || io->struct_size != (int32_t)sizeof(rk_ppo_grad_io)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_minibatch_grad: io->struct_size mismatch");
+        return 1;
+    }
+    bool ok = io->n > 0 && io->obs_dim > 0 && io->obs_dim <= RK_PPO_MAX_OBS_DIM && io->n_global >= 2.0 && io->log_std &&
+              io->obs && io->act && io->old_logp && io->adv && io->ret && io->val && io->adv_part && io->workspace &&
+              io->flat_grad && io->kl_sum;
+    for (int k = 0; k < 12; ++k) ok = ok && io->params[k] != nullptr;
+    if (!ok) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "rk_ppo_minibatch_grad: invalid arguments (obs_dim must be 1..%d, no NULL pointers except idx)",
+                 RK_PPO_MAX_OBS_DIM);
+        return 1;
+    }
+    PpoGradIO g;
+    g.obs_dim = io->obs_dim; g.n = io->n; g.n_global = io->n_global;
+    for (int k = 0; k < 12; ++k) g.params[k] = io->params[k];
+    g.log_std = io->log_std;
+    g.obs = io->obs; g.act = io->act; g.old_logp = io->old_logp; g.adv = io->adv; g.ret = io->ret; g.val = io->val;
+    g.idx = io->idx; g.adv_part = io->adv_part; g.clip = io->clip_coef; g.vf_coef = io->vf_coef;
+    g.workspace = io->workspace; g.workspace_bytes = (size_t)io->workspace_bytes;
+    g.flat_grad = io->flat_grad; g.kl_sum = io->kl_sum;
+    const int rc = launch_ppo_minibatch_grad(g, (cudaStream_t)stream);
+    if (rc) snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_minibatch_grad: %s",
+                     rc == 3 ? "workspace too small" : rc == 2 ? "unsupported shape" : cudaGetErrorString(cudaGetLastError()));
+    return rc ? 1 : 0;
+}
+
 int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
                   uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
                   float* mean, void* stream) {

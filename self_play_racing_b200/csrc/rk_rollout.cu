@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "rk_types.cuh"
+#include "rk_ppo_loss.cuh"
 
 namespace rk {
 
@@ -266,33 +267,12 @@ __global__ void ppo_loss_grad_kernel(const float* __restrict__ mu, const float* 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float kl = 0.f;
     if (i < n) {
-        const float ls0 = log_std[0], ls1 = log_std[1];
-        const float s0 = expf(ls0), s1 = expf(ls1);
-        const float m0 = mu[2 * (size_t)i], m1 = mu[2 * (size_t)i + 1];
-        const float a0 = act[2 * (size_t)i], a1 = act[2 * (size_t)i + 1];
-        const float kLogSqrt2Pi = 0.9189385332046727f;
-        const float d0 = a0 - m0, d1 = a1 - m1;
-        const float lp = (-(d0 * d0) / (2.f * s0 * s0) - ls0 - kLogSqrt2Pi) + (-(d1 * d1) / (2.f * s1 * s1) - ls1 - kLogSqrt2Pi);
-        const float logratio = lp - old_logp[i];
-        kl = -logratio;
-        const float ratio = expf(logratio);
-        const float A = (adv_raw[i] - adv_mean[0]) / (adv_std[0] + 1e-8f);
-        const float lo = 1.f - clip, hi = 1.f + clip;
-        const float rc = fminf(fmaxf(ratio, lo), hi);
-        const float pg1 = -A * ratio, pg2 = -A * rc;
-        const bool inside = ratio >= lo && ratio <= hi;
-        float w1 = pg1 > pg2 ? 1.f : (pg1 == pg2 ? 0.5f : 0.f);   // share of the max() gradient going to pg1
-        float dratio = w1 * (-A) + (1.f - w1) * (inside ? -A : 0.f);
-        const float g_lp = dratio * ratio / (float)n;              // d loss / d logp_new
-        dmu[2 * (size_t)i] = g_lp * d0 / (s0 * s0);
-        dmu[2 * (size_t)i + 1] = g_lp * d1 / (s1 * s1);
-        const float vi = v[i], R = ret[i], vo = v_old[i];
-        const float dvv = vi - vo;
-        const float vclip = vo + fminf(fmaxf(dvv, -clip), clip);
-        const float l1 = (vi - R) * (vi - R), l2 = (vclip - R) * (vclip - R);
-        const float g1 = 2.f * (vi - R), g2 = (dvv >= -clip && dvv <= clip) ? 2.f * (vclip - R) : 0.f;
-        const float u1 = l1 > l2 ? 1.f : (l1 == l2 ? 0.5f : 0.f);
-        dv[i] = vf_coef * 0.5f * (u1 * g1 + (1.f - u1) * g2) / (float)n;
+        float d0, d1;
+        ppo_policy_grad(mu[2 * (size_t)i], mu[2 * (size_t)i + 1], act[2 * (size_t)i], act[2 * (size_t)i + 1], old_logp[i],
+                        adv_raw[i], adv_mean[0], adv_std[0], log_std[0], log_std[1], clip, n, d0, d1, kl);
+        dmu[2 * (size_t)i] = d0;
+        dmu[2 * (size_t)i + 1] = d1;
+        dv[i] = ppo_value_grad(v[i], ret[i], v_old[i], clip, vf_coef, n);
     }
     // block sum of (logp_old - logp_new) -> one atomic per block
     __shared__ float red[32];

@@ -1,0 +1,486 @@
+// Fused PPO minibatch gradient: PPO.ppo_update's forward + loss + backward
+// (reference agent/ppo.py:170-206) for the Agent's two 64-64 tanh MLPs
+// (agent/ppo.py:11-37) as ONE kernel.
+//
+// One CTA owns one network (blockIdx.y: 0 actor_mu, 1 critic) and walks over
+// 128-sample tiles of the minibatch.  Per tile everything stays in shared
+// memory: the gathered observation rows X[D][128], the hidden activations
+// H1, H2 [64][128] (overwritten in place by their pre-activation gradients),
+// the weights (transposed copies for the forward pass).  The three 64-wide
+// products per tile (layer 1, layer 2, d h1 = d z2 . W2) run as 8x8 register
+// tiles fed by 128-bit shared-memory loads; the weight gradients
+// dW2 += H1^T dZ2, dW1 += X^T dZ1, dW3 += H2^T dOut are outer-product
+// accumulations whose registers PERSIST across all tiles of the CTA, so each
+// CTA writes its partial gradient once; a second small kernel sums the partials
+// in a fixed order (deterministic, no atomics) into torch's parameter order.
+// Arithmetic is fp32 FFMA throughout (what the reference computes on a GPU).
+#include "rk_types.cuh"
+#include "rk_ppo_loss.cuh"
+
+namespace rk {
+namespace {
+
+constexpr int kH = 64;          // hidden width (agent/ppo.py:18-22)
+constexpr int kTS = 128;        // samples per tile
+constexpr int kNT = 128;        // threads per CTA
+constexpr int kLD = kTS + 4;    // activation row stride: rows 4 banks apart, 16-byte aligned
+constexpr int kWLD = kH + 4;    // W2^T row stride (column reads in the backward product stay conflict-free)
+constexpr int kMaxD = 20;       // observation width supported by the register tile of dW1
+constexpr int kNetStride = 5632;  // floats per CTA partial (>= 64*20 + 64 + 4096 + 64 + 128 + 2)
+
+struct NetPtrs { const float *W1, *b1, *W2, *b2, *W3, *b3; };
+struct GradArgs {
+    NetPtrs net[2];
+    const float* log_std;
+    const float *obs, *act, *old_logp, *adv, *ret, *val;
+    const int64_t* idx;
+    const double* adv_part;  // [kAdvBlocks][2] partial (sum, sum of squares) of the minibatch advantages
+    double n_global;
+    int n, D;
+    float clip, vf_coef;
+    float* partial;       // [2][gridDim.x][kNetStride]
+    double* kl_partial;   // [gridDim.x]
+};
+
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// acc[m][n] += sum_k A[k][s_m] * W[k][j_n]; s_m = ty*4 + (m&3) + 64*(m>>2), j_n = tx*4 + (n&3) + 32*(n>>2)
+__device__ __forceinline__ void tile_product(const float* __restrict__ A, const float* __restrict__ W, int wld, int K,
+                                             int ty, int tx, float (&acc)[8][8]) {
+    const float* a = A + ty * 4;
+    const float* w = W + tx * 4;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float4 a0 = ld4(a + k * kLD), a1 = ld4(a + k * kLD + 64);
+        const float4 w0 = ld4(w + k * wld), w1 = ld4(w + k * wld + 32);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(av[m], wv[n], acc[m][n]);
+    }
+}
+
+template <int OUT>
+__device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, float* smem) {
+    constexpr bool kActor = OUT == 2;
+    const int tid = threadIdx.x, D = g.D;
+    const int tx = tid & 7, ty = tid >> 3;
+    // shared-memory carve-up
+    float* W1t = smem;                   // [D][64]      W1t[i][j] = W1[j][i]
+    float* W2t = W1t + kMaxD * kH;       // [64][kWLD]   W2t[i][j] = W2[j][i]
+    float* sb1 = W2t + kH * kWLD;        // [64]
+    float* sb2 = sb1 + kH;               // [64]
+    float* sW3 = sb2 + kH;               // [OUT][64]
+    float* X = sW3 + 2 * kH;             // [D][kLD]
+    float* H1 = X + kMaxD * kLD;         // [64][kLD]  h1, then dz1
+    float* H2 = H1 + kH * kLD;           // [64][kLD]  h2, then dz2
+    float* DO = H2 + kH * kLD;           // [2][kLD]   d loss / d (pre-activation output)
+    float* red = DO + 2 * kLD;           // [16]
+
+    for (int q = tid; q < kH * D; q += kNT) { const int j = q / D, i = q - j * D; W1t[i * kH + j] = P.W1[q]; }
+    for (int q = tid; q < kH * kH; q += kNT) { const int j = q >> 6, i = q & 63; W2t[i * kWLD + j] = P.W2[q]; }
+    for (int q = tid; q < kH; q += kNT) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
+    for (int q = tid; q < OUT * kH; q += kNT) sW3[q] = P.W3[q];
+    float b3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) b3[o] = P.b3[o];
+
+    // minibatch advantage statistics (ppo.py:187, unbiased std), summed in a fixed order
+    float adv_mean = 0.f, adv_std = 1.f;
+    if (kActor) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int b = 0; b < kAdvBlocks; ++b) { s1 += g.adv_part[2 * b]; s2 += g.adv_part[2 * b + 1]; }
+        const double mean = s1 / g.n_global;
+        const double var = (s2 - g.n_global * mean * mean) / (g.n_global - 1.0);
+        adv_mean = (float)mean;
+        adv_std = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    const float ls0 = kActor ? g.log_std[0] : 0.f, ls1 = kActor ? g.log_std[1] : 0.f;
+
+    // accumulators that live across all tiles of this CTA
+    const int kg = tid >> 6, u = tid & 63, ti = u >> 3, tj = u & 7;
+    float gW2[8][8], gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        gb2[m] = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) gW2[m][n] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxD; ++i) gW1[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
+    __syncthreads();
+
+    const int ntiles = (g.n + kTS - 1) / kTS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- gather the tile: thread <-> sample ----
+        const int gi = tile * kTS + tid;
+        const bool valid = gi < g.n;
+        const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
+        {
+            const float* src = g.obs + row * D;
+            for (int i = 0; i < D; ++i) X[i * kLD + tid] = valid ? src[i] : 0.f;
+        }
+        float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
+        if (valid) {
+            if (kActor) {
+                const float2 a = *reinterpret_cast<const float2*>(g.act + 2 * row);
+                d_a0 = a.x; d_a1 = a.y; d_lp = g.old_logp[row]; d_adv = g.adv[row];
+            } else {
+                d_ret = g.ret[row]; d_val = g.val[row];
+            }
+        }
+        __syncthreads();
+        float acc[8][8];
+        // ---- layer 1: H1 = tanh(X W1^T + b1) ----
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float b = sb1[tx * 4 + (n & 3) + 32 * (n >> 2)];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m][n] = b;
+        }
+        tile_product(X, W1t, kH, D, ty, tx, acc);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            float* h = H1 + (tx * 4 + (n & 3) + 32 * (n >> 2)) * kLD + ty * 4;
+            st4(h, make_float4(tanh_fast(acc[0][n]), tanh_fast(acc[1][n]), tanh_fast(acc[2][n]), tanh_fast(acc[3][n])));
+            st4(h + 64, make_float4(tanh_fast(acc[4][n]), tanh_fast(acc[5][n]), tanh_fast(acc[6][n]), tanh_fast(acc[7][n])));
+        }
+        __syncthreads();
+        // ---- layer 2: H2 = tanh(H1 W2^T + b2) ----
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float b = sb2[tx * 4 + (n & 3) + 32 * (n >> 2)];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[m][n] = b;
+        }
+        tile_product(H1, W2t, kWLD, kH, ty, tx, acc);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            float* h = H2 + (tx * 4 + (n & 3) + 32 * (n >> 2)) * kLD + ty * 4;
+            st4(h, make_float4(tanh_fast(acc[0][n]), tanh_fast(acc[1][n]), tanh_fast(acc[2][n]), tanh_fast(acc[3][n])));
+            st4(h + 64, make_float4(tanh_fast(acc[4][n]), tanh_fast(acc[5][n]), tanh_fast(acc[6][n]), tanh_fast(acc[7][n])));
+        }
+        __syncthreads();
+        // ---- output layer + loss gradient: thread <-> sample ----
+        {
+            float out[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) out[o] = b3[o];
+#pragma unroll 4
+            for (int j = 0; j < kH; j += 4) {
+                const float h0 = H2[j * kLD + tid], h1 = H2[(j + 1) * kLD + tid], h2 = H2[(j + 2) * kLD + tid],
+                            h3 = H2[(j + 3) * kLD + tid];
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) {
+                    const float4 w = ld4(sW3 + o * kH + j);
+                    out[o] = fmaf(h0, w.x, out[o]); out[o] = fmaf(h1, w.y, out[o]);
+                    out[o] = fmaf(h2, w.z, out[o]); out[o] = fmaf(h3, w.w, out[o]);
+                }
+            }
+            float dpre[OUT];
+            if (kActor) {
+                const float mu0 = tanh_fast(out[0]), mu1 = tanh_fast(out[1]);  // actor_mu ends in nn.Tanh (ppo.py:19)
+                float dmu0 = 0.f, dmu1 = 0.f, klv = 0.f;
+                if (valid)
+                    ppo_policy_grad(mu0, mu1, d_a0, d_a1, d_lp, d_adv, adv_mean, adv_std, ls0, ls1, g.clip, g.n, dmu0,
+                                    dmu1, klv);
+                kl += klv;
+                dpre[0] = dmu0 * (1.f - mu0 * mu0);
+                dpre[OUT - 1] = dmu1 * (1.f - mu1 * mu1);
+            } else {
+                dpre[0] = valid ? ppo_value_grad(out[0], d_ret, d_val, g.clip, g.vf_coef, g.n) : 0.f;
+            }
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { DO[o * kLD + tid] = dpre[o]; gb3[o] += dpre[o]; }
+        }
+        __syncthreads();
+        // ---- dW3 += H2^T dOut (thread <-> (o, j) or (sample half, j)) ----
+        {
+            const int o = kActor ? kg : 0;
+            const int s0 = kActor ? 0 : kg * 64, s1 = kActor ? kTS : s0 + 64;
+            const float* h = H2 + u * kLD;
+            const float* d = DO + o * kLD;
+            float a = 0.f;
+#pragma unroll 4
+            for (int s = s0; s < s1; s += 4) {
+                const float4 hv = ld4(h + s), dv = ld4(d + s);
+                a = fmaf(hv.x, dv.x, a); a = fmaf(hv.y, dv.y, a); a = fmaf(hv.z, dv.z, a); a = fmaf(hv.w, dv.w, a);
+            }
+            gW3 += a;
+        }
+        __syncthreads();
+        // ---- dZ2 = (dOut W3) * (1 - H2^2), in place ----
+        {
+            float4 d0[OUT], d1[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { d0[o] = ld4(DO + o * kLD + ty * 4); d1[o] = ld4(DO + o * kLD + 64 + ty * 4); }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int j = tx * 4 + (n & 3) + 32 * (n >> 2);
+                float* h = H2 + j * kLD + ty * 4;
+                const float4 ha = ld4(h), hb = ld4(h + 64);
+                float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) {
+                    const float w = sW3[o * kH + j];
+                    za.x = fmaf(d0[o].x, w, za.x); za.y = fmaf(d0[o].y, w, za.y); za.z = fmaf(d0[o].z, w, za.z); za.w = fmaf(d0[o].w, w, za.w);
+                    zb.x = fmaf(d1[o].x, w, zb.x); zb.y = fmaf(d1[o].y, w, zb.y); zb.z = fmaf(d1[o].z, w, zb.z); zb.w = fmaf(d1[o].w, w, zb.w);
+                }
+                za.x *= 1.f - ha.x * ha.x; za.y *= 1.f - ha.y * ha.y; za.z *= 1.f - ha.z * ha.z; za.w *= 1.f - ha.w * ha.w;
+                zb.x *= 1.f - hb.x * hb.x; zb.y *= 1.f - hb.y * hb.y; zb.z *= 1.f - hb.z * hb.z; zb.w *= 1.f - hb.w * hb.w;
+                st4(h, za); st4(h + 64, zb);
+            }
+        }
+        __syncthreads();
+        // ---- dW2 += H1^T dZ2, db2 += sum dZ2: thread <-> 8 inputs x 8 outputs over its half of the samples ----
+        {
+            const float* ha = H1 + ti * kLD + kg * 64;
+            const float* zb = H2 + tj * kLD + kg * 64;
+#pragma unroll 1
+            for (int s = 0; s < 64; s += 4) {
+                float4 a[8], b[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) { a[m] = ld4(ha + 8 * m * kLD + s); b[m] = ld4(zb + 8 * m * kLD + s); }
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    gb2[m] += (b[m].x + b[m].y) + (b[m].z + b[m].w);
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        float t = gW2[m][n];
+                        t = fmaf(a[m].x, b[n].x, t); t = fmaf(a[m].y, b[n].y, t);
+                        t = fmaf(a[m].z, b[n].z, t); t = fmaf(a[m].w, b[n].w, t);
+                        gW2[m][n] = t;
+                    }
+                }
+            }
+        }
+        // ---- dH1 = dZ2 W2 (outputs i = tx + 8 n), then dZ1 = dH1 * (1 - H1^2) in place ----
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
+        {
+            const float* a = H2 + ty * 4;
+            const float* w = W2t + tx * kWLD;
+#pragma unroll 2
+            for (int k = 0; k < kH; ++k) {
+                const float4 a0 = ld4(a + k * kLD), a1 = ld4(a + k * kLD + 64);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float wv[8];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) wv[n] = w[8 * n * kWLD + k];
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(av[m], wv[n], acc[m][n]);
+            }
+        }
+        __syncthreads();  // every thread has finished reading H1 (dW2) before it is overwritten
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            float* h = H1 + (tx + 8 * n) * kLD + ty * 4;
+            const float4 ha = ld4(h), hb = ld4(h + 64);
+            st4(h, make_float4(acc[0][n] * (1.f - ha.x * ha.x), acc[1][n] * (1.f - ha.y * ha.y),
+                               acc[2][n] * (1.f - ha.z * ha.z), acc[3][n] * (1.f - ha.w * ha.w)));
+            st4(h + 64, make_float4(acc[4][n] * (1.f - hb.x * hb.x), acc[5][n] * (1.f - hb.y * hb.y),
+                                    acc[6][n] * (1.f - hb.z * hb.z), acc[7][n] * (1.f - hb.w * hb.w)));
+        }
+        __syncthreads();
+        // ---- dW1 += X^T dZ1, db1 += sum dZ1: thread <-> output j over its half of the samples ----
+        {
+            const float* z = H1 + u * kLD + kg * 64;
+            const float* x = X + kg * 64;
+#pragma unroll 2
+            for (int s = 0; s < 64; s += 4) {
+                const float4 zv = ld4(z + s);
+                gb1 += (zv.x + zv.y) + (zv.z + zv.w);
+#pragma unroll
+                for (int i = 0; i < kMaxD; ++i) {
+                    if (i < D) {
+                        const float4 xv = ld4(x + i * kLD + s);
+                        float t = gW1[i];
+                        t = fmaf(xv.x, zv.x, t); t = fmaf(xv.y, zv.y, t); t = fmaf(xv.z, zv.z, t); t = fmaf(xv.w, zv.w, t);
+                        gW1[i] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // X, H1, H2 are rewritten by the next tile
+    }
+
+    // ---- combine the two sample halves and write this CTA's partial gradient ----
+    // layout = torch's parameter order of one Sequential: W1 [64][D], b1, W2 [64][64], b2, W3 [OUT][64], b3
+    float* stage = H1;  // >= kNetStride floats (H1 and H2 are contiguous)
+    const int oW1 = 0, ob1 = kH * D, oW2 = ob1 + kH, ob2 = oW2 + kH * kH, oW3 = ob2 + kH, ob3 = oW3 + OUT * kH;
+    for (int pass = 1; pass >= 0; --pass) {
+        if (kg == pass) {
+            const bool add = pass == 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    float* d = stage + oW2 + (tj + 8 * n) * kH + (ti + 8 * m);
+                    *d = add ? *d + gW2[m][n] : gW2[m][n];
+                }
+            if (ti == 0) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    float* d = stage + ob2 + tj + 8 * n;
+                    *d = add ? *d + gb2[n] : gb2[n];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i)
+                if (i < D) {
+                    float* d = stage + oW1 + u * D + i;
+                    *d = add ? *d + gW1[i] : gW1[i];
+                }
+            {
+                float* d = stage + ob1 + u;
+                *d = add ? *d + gb1 : gb1;
+            }
+            if (kActor) {
+                stage[oW3 + kg * kH + u] = gW3;          // kg is the output index for the actor
+            } else {
+                float* d = stage + oW3 + u;
+                *d = add ? *d + gW3 : gW3;
+            }
+        }
+        __syncthreads();
+    }
+    // db3 and the KL sum: fixed-order block reduction
+    float r[OUT + 1];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) r[o] = gb3[o];
+    r[OUT] = kl;
+#pragma unroll
+    for (int o = 0; o <= OUT; ++o) {
+        for (int m = 16; m > 0; m >>= 1) r[o] += __shfl_xor_sync(0xffffffffu, r[o], m);
+        if ((tid & 31) == 0) red[o * 4 + (tid >> 5)] = r[o];
+    }
+    __syncthreads();
+    if (tid < OUT) stage[ob3 + tid] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+    if (kActor && tid == 0)
+        g.kl_partial[blockIdx.x] = (double)((red[OUT * 4] + red[OUT * 4 + 1]) + (red[OUT * 4 + 2] + red[OUT * 4 + 3]));
+    __syncthreads();
+    float* dst = g.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kNetStride;
+    const int np = ob3 + OUT;
+    for (int q = tid; q < np; q += kNT) dst[q] = stage[q];
+}
+
+__global__ void __launch_bounds__(kNT, 2) ppo_mlp_grad_kernel(const GradArgs g) {
+    extern __shared__ __align__(16) float train_smem[];
+    if (blockIdx.y == 0) net_body<2>(g, g.net[0], train_smem);
+    else net_body<1>(g, g.net[1], train_smem);
+}
+
+// flat_grad[q] = sum over CTAs of partial[net][cta][q'] in a fixed order; *kl_sum = sum kl_partial
+__global__ void ppo_grad_reduce_kernel(const float* __restrict__ partial, const double* __restrict__ kl_partial,
+                                       int ncta, int n_actor, int n_total, float* __restrict__ flat_grad,
+                                       double* __restrict__ kl_sum) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_total) {
+        const int net = q >= n_actor, local = net ? q - n_actor : q;
+        const float* src = partial + (size_t)net * ncta * kNetStride + local;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int c = 0;
+        for (; c + 4 <= ncta; c += 4) {
+            s0 += src[(size_t)c * kNetStride]; s1 += src[(size_t)(c + 1) * kNetStride];
+            s2 += src[(size_t)(c + 2) * kNetStride]; s3 += src[(size_t)(c + 3) * kNetStride];
+        }
+        for (; c < ncta; ++c) s0 += src[(size_t)c * kNetStride];
+        flat_grad[q] = (s0 + s1) + (s2 + s3);
+    }
+    if (q == 0) {
+        double s = 0.0;
+        for (int c = 0; c < ncta; ++c) s += kl_partial[c];
+        *kl_sum = s;
+    }
+}
+
+// partial (sum, sum of squares) of adv[idx[k]] in float64: kAdvBlocks blocks, fixed order inside each
+__global__ void adv_stats_kernel(const int64_t* __restrict__ idx, const float* __restrict__ adv, int n,
+                                 double* __restrict__ part) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double a = (double)adv[idx ? idx[k] : (int64_t)k];
+        s1 += a; s2 += a * a;
+    }
+    __shared__ double r1[8], r2[8];
+    for (int m = 16; m > 0; m >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, m); s2 += __shfl_xor_sync(0xffffffffu, s2, m); }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r1[w]; b += r2[w]; }
+        part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+}
+
+constexpr size_t kTrainSmemFloats = (size_t)kMaxD * kH + (size_t)kH * kWLD + 2 * kH + 2 * kH + (size_t)kMaxD * kLD +
+                                    2 * (size_t)kH * kLD + 2 * kLD + 16;
+static_assert(2 * (size_t)kH * kLD >= (size_t)kNetStride, "the staging area must hold one partial gradient");
+static_assert((kMaxD * kH) % 4 == 0 && (kH * kWLD) % 4 == 0 && (kMaxD * kLD) % 4 == 0, "16-byte aligned carve-up");
+
+int train_grid(int n) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (n + kTS - 1) / kTS;
+    return ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms;
+}
+
+}  // namespace
+
+size_t ppo_grad_workspace_bytes() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * (size_t)sms * kNetStride * sizeof(float) + (size_t)sms * sizeof(double);
+}
+
+int launch_adv_stats(const int64_t* idx, const float* adv, int n, double* part, cudaStream_t stream) {
+    adv_stats_kernel<<<kAdvBlocks, 256, 0, stream>>>(idx, adv, n, part);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
+    if (io.obs_dim < 1 || io.obs_dim > kMaxD) return 2;
+    if (io.n <= 0) return 2;
+    GradArgs g;
+    for (int k = 0; k < 2; ++k)
+        g.net[k] = NetPtrs{io.params[6 * k], io.params[6 * k + 1], io.params[6 * k + 2], io.params[6 * k + 3],
+                           io.params[6 * k + 4], io.params[6 * k + 5]};
+    g.log_std = io.log_std;
+    g.obs = io.obs; g.act = io.act; g.old_logp = io.old_logp; g.adv = io.adv; g.ret = io.ret; g.val = io.val;
+    g.idx = io.idx; g.adv_part = io.adv_part; g.n_global = io.n_global; g.n = io.n; g.D = io.obs_dim;
+    g.clip = io.clip; g.vf_coef = io.vf_coef;
+    const int ncta = train_grid(io.n);
+    if (io.workspace_bytes < 2 * (size_t)ncta * kNetStride * sizeof(float) + (size_t)ncta * sizeof(double)) return 3;
+    g.kl_partial = reinterpret_cast<double*>(io.workspace);
+    g.partial = reinterpret_cast<float*>(g.kl_partial + ((ncta + 1) & ~1));
+    if ((size_t)((ncta + 1) & ~1) * sizeof(double) + 2 * (size_t)ncta * kNetStride * sizeof(float) > io.workspace_bytes) return 3;
+    const size_t smem = kTrainSmemFloats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ppo_mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    ppo_mlp_grad_kernel<<<dim3(ncta, 2), kNT, smem, stream>>>(g);
+    count_launch();
+    const int n_actor = kH * io.obs_dim + kH + kH * kH + kH + 2 * kH + 2;
+    const int n_total = n_actor + kH * io.obs_dim + kH + kH * kH + kH + kH + 1;
+    ppo_grad_reduce_kernel<<<(n_total + 127) / 128, 128, 0, stream>>>(g.partial, g.kl_partial, ncta, n_actor, n_total,
+                                                                       io.flat_grad, io.kl_sum);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace rk

@@ -130,4 +130,24 @@ int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, cons
                          const float* adv_std, int n, float clip, float vf_coef, float* dmu, float* dv,
                          double* kl_sum, cudaStream_t stream);
 
+// fused PPO minibatch gradient (rk_train.cu)
+constexpr int kAdvBlocks = 64;  // partial sums produced by launch_adv_stats ([kAdvBlocks][2] doubles)
+struct PpoGradIO {
+    int obs_dim, n;
+    double n_global;
+    const float* params[12];  // actor W1,b1,W2,b2,W3,b3 then critic, torch layouts [out][in]
+    const float* log_std;
+    const float *obs, *act, *old_logp, *adv, *ret, *val;
+    const int64_t* idx;
+    const double* adv_part;
+    float clip, vf_coef;
+    void* workspace;
+    size_t workspace_bytes;
+    float* flat_grad;
+    double* kl_sum;
+};
+size_t ppo_grad_workspace_bytes();
+int launch_adv_stats(const int64_t* idx, const float* adv, int n, double* part, cudaStream_t stream);
+int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream);
+
 }  // namespace rk

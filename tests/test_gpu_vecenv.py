@@ -210,9 +210,11 @@ def test_graphed_update_equals_eager_update(pkg):
     same parameters as the eager step-by-step update, and honours the KL stop."""
     env_mod, agent_mod, configs = pkg
     results = []
-    for graphed, fused in ((False, False), (True, False), (True, True)):
+    for graphed, fused, fused_mlp in ((False, False, False), (True, False, False), (True, True, False),
+                                      (True, True, True)):
         cfg = configs.base_config(num_envs=64, num_steps=64, update_epochs=2, num_minibatches=4, kl_target=1e9,
-                                  cuda_graph_update=graphed, fused_update_kernels=fused)
+                                  cuda_graph_update=graphed, fused_update_kernels=fused,
+                                  fused_mlp_update=fused_mlp)
         vec = env_mod.BatchedRacingVecEnv.synthetic('single', 64, n_tracks=4, seed=0)
         tr = agent_mod.PPO(vec, cfg, device='cuda')
         g = torch.Generator(device='cuda').manual_seed(0)
@@ -236,9 +238,73 @@ def test_graphed_update_equals_eager_update(pkg):
         for a, b in zip(before, tr.agent.parameters()):
             assert torch.equal(a, b)
         vec.close()
-    for other in results[1:]:  # eager autograd == graphed autograd == graphed with the fused loss-gradient kernel
+    # eager autograd == graphed autograd == graphed + fused loss-gradient kernel == one-kernel forward/loss/backward
+    for other in results[1:]:
         for a, b in zip(results[0], other):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize('n,obs_dim,use_idx', [(1000, 19, True), (128, 15, False), (5000, 19, True), (77, 7, True)])
+def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
+    """rk_ppo_minibatch_grad (forward + PPO loss + backward of both MLPs in one
+    kernel, rows gathered through the minibatch indices) against torch autograd of
+    the reference's loss expression (agent/ppo.py:173-204): fp32 autograd within
+    rtol 1e-3, and no farther from a float64 evaluation than fp32 autograd is."""
+    _, agent_mod, configs = pkg
+    import copy
+    from self_play_racing_b200 import spaces
+    from self_play_racing_b200.backend import PpoMinibatchGrad
+    torch.manual_seed(n)
+    agent = agent_mod.Agent(spaces.Box(-1, 1, (obs_dim,)), spaces.Box(-1, 1, (2,))).cuda()
+    with torch.no_grad():
+        for p in agent.parameters():
+            p.add_(0.2 * torch.randn_like(p))      # away from the 0.01-gain output layer: every term matters
+        agent.log_std.fill_(-0.7)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    B = 3 * n
+    obs = torch.rand(B, obs_dim, device='cuda', generator=g) * 2 - 1
+    act = torch.rand(B, 2, device='cuda', generator=g) * 2 - 1
+    adv = torch.randn(B, device='cuda', generator=g) * 3 + 0.5
+    val = torch.randn(B, device='cuda', generator=g)
+    ret = val + 0.3 * torch.randn(B, device='cuda', generator=g)
+    with torch.no_grad():
+        _, logp, _, _ = agent.get_action_and_value(obs, act)
+    logp = logp + 0.15 * torch.randn(B, device='cuda', generator=g)   # ratios on both sides of the clip range
+    idx = torch.randperm(B, device='cuda', generator=g)[:n] if use_idx else None
+    clip, vf = 0.2, 0.5
+
+    def reference(net, dtype):
+        sel = (lambda t: t[idx]) if use_idx else (lambda t: t[:n])
+        o, a, lp, ad, rt, vl = (sel(t).to(dtype) for t in (obs, act, logp, adv, ret, val))
+        net.zero_grad()
+        _, new_lp, _, new_v = net.get_action_and_value(o, a)
+        logratio = new_lp - lp
+        ratio = logratio.exp()
+        adn = (ad - ad.mean()) / (ad.std() + 1e-8)
+        pg = torch.max(-adn * ratio, -adn * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+        new_v = new_v.flatten()
+        vclip = vl + torch.clamp(new_v - vl, -clip, clip)
+        vloss = 0.5 * torch.max((new_v - rt) ** 2, (vclip - rt) ** 2).mean()
+        (pg + vf * vloss).backward()
+        return torch.cat([p.grad.reshape(-1) for p in net.parameters()]), float((-logratio).sum())
+
+    g32, kl32 = reference(agent, torch.float32)
+    g64, kl64 = reference(copy.deepcopy(agent).double(), torch.float64)
+    fused = PpoMinibatchGrad(list(agent.parameters()), agent.log_std, obs_dim, clip, vf)
+    src = (obs, act, logp, adv, ret, val) if use_idx else tuple(t[:n].contiguous() for t in (obs, act, logp, adv, ret, val))
+    fused.stats(idx, src[3])
+    flat, kl = fused(idx, *src)
+    torch.cuda.synchronize()
+    assert flat.shape == g32.shape
+    torch.testing.assert_close(flat, g32, rtol=1e-3, atol=2e-6)
+    err_fused = float((flat.double() - g64).abs().max())
+    err_torch = float((g32.double() - g64).abs().max())
+    assert err_fused <= 4 * err_torch + 1e-7, (err_fused, err_torch)
+    assert abs(float(kl) - kl64) <= 1e-5 * max(1.0, abs(kl64)) + 1e-3
+    # replay: deterministic (fixed-order reductions)
+    first = flat.clone()
+    fused(idx, *src)
+    assert torch.equal(first, fused.flat_grad)
 
 
 def test_batched_evaluation_protocol(pkg):
