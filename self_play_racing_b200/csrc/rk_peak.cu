@@ -22,8 +22,32 @@ __global__ void __launch_bounds__(256) fma_chain_kernel(T* out, int iters, T a, 
     if (s == (T)123456789) out[0] = s;  // never true; keeps the chains alive
 }
 
+// the same with Blackwell's packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): 8 independent
+// 64-bit chains per thread, two FMAs per instruction
+__global__ void __launch_bounds__(256) fma2_chain_kernel(float* out, int iters, float a, float b) {
+    unsigned long long x[8], aa, bb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) asm("mov.b64 %0, {%1, %2};" : "=l"(x[u]) : "f"((float)threadIdx.x + u), "f"((float)u));
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[u]) : "l"(aa), "l"(bb));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[u]));
+        s += lo + hi;
+    }
+    if (s == 123456789.f) out[0] = s;
+}
+
 template <typename T>
-double measure(int iters) {
+double measure(int iters, bool packed = false) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -36,7 +60,8 @@ double measure(int iters) {
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        fma_chain_kernel<T><<<grid, block>>>(out, iters, (T)1.0000001, (T)1e-7);
+        if (packed) fma2_chain_kernel<<<grid, block>>>((float*)out, iters, 1.0000001f, 1e-7f);
+        else fma_chain_kernel<T><<<grid, block>>>(out, iters, (T)1.0000001, (T)1e-7);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         count_launch();
@@ -56,5 +81,6 @@ double measure(int iters) {
 
 extern "C" RK_API double rk_fma_peak(int32_t use_fp64, int32_t iters) {
     if (iters <= 0) iters = 1024;
+    if (use_fp64 == 2) return rk::measure<float>(iters, true);  // packed fp32 (FFMA2), same 64 FMAs per thread-iteration
     return use_fp64 ? rk::measure<double>(iters) : rk::measure<float>(iters);
 }

@@ -46,22 +46,50 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Blackwell's packed fp32 FMA (SASS FFMA2): two IEEE fp32 FMAs per issue slot, so the
+// 8x8 register tiles below cost 32 instead of 64 instructions per step
+typedef float2 u64;  // one packed register pair
+__device__ __forceinline__ u64 pack2(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { lo = v.x; hi = v.y; }
+__device__ __forceinline__ void fma2(u64& d, u64 a, u64 b) { d = __ffma2_rn(a, b, d); }
+__device__ __forceinline__ void pack_tile(const float (&acc)[8][8], u64 (&p)[8][4]) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p[m][q] = pack2(acc[m][2 * q], acc[m][2 * q + 1]);
+}
+__device__ __forceinline__ void unpack_tile(const u64 (&p)[8][4], float (&acc)[8][8]) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) unpack2(p[m][q], acc[m][2 * q], acc[m][2 * q + 1]);
+}
+
 // acc[m][n] += sum_k A[k][s_m] * W[k][j_n]; s_m = ty*4 + (m&3) + 64*(m>>2), j_n = tx*4 + (n&3) + 32*(n>>2)
 __device__ __forceinline__ void tile_product(const float* __restrict__ A, const float* __restrict__ W, int wld, int K,
                                              int ty, int tx, float (&acc)[8][8]) {
     const float* a = A + ty * 4;
     const float* w = W + tx * 4;
+    u64 p[8][4];
+    pack_tile(acc, p);
+    // fragments of step k+1 are loaded before the FMAs of step k (software pipeline)
+    float4 a0 = ld4(a), a1 = ld4(a + 64), w0 = ld4(w), w1 = ld4(w + 32);
 #pragma unroll 2
     for (int k = 0; k < K; ++k) {
-        const float4 a0 = ld4(a + k * kLD), a1 = ld4(a + k * kLD + 64);
-        const float4 w0 = ld4(w + k * wld), w1 = ld4(w + k * wld + 32);
+        const int kn = (k + 1 < K) ? k + 1 : k;
+        const float4 na0 = ld4(a + kn * kLD), na1 = ld4(a + kn * kLD + 64);
+        const float4 nw0 = ld4(w + kn * wld), nw1 = ld4(w + kn * wld + 32);
         const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const u64 wp[4] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y), pack2(w1.z, w1.w)};
 #pragma unroll
-        for (int m = 0; m < 8; ++m)
+        for (int m = 0; m < 8; ++m) {
+            const u64 as = pack2(av[m], av[m]);
 #pragma unroll
-            for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(av[m], wv[n], acc[m][n]);
+            for (int q = 0; q < 4; ++q) fma2(p[m][q], as, wp[q]);
+        }
+        a0 = na0; a1 = na1; w0 = nw0; w1 = nw1;
     }
+    unpack_tile(p, acc);
 }
 
 template <int OUT>
@@ -244,19 +272,22 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
             const float* zb = H2 + tj * kLD + kg * 64;
 #pragma unroll 1
             for (int s = 0; s < 64; s += 4) {
-                float4 a[8], b[8];
+                float4 a[8];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) { a[m] = ld4(ha + 8 * m * kLD + s); b[m] = ld4(zb + 8 * m * kLD + s); }
+                for (int m = 0; m < 8; ++m) a[m] = ld4(ha + 8 * m * kLD + s);
+                float4 b = ld4(zb + s);
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    gb2[m] += (b[m].x + b[m].y) + (b[m].z + b[m].w);
+                for (int n = 0; n < 8; ++n) {
+                    const float4 nb = ld4(zb + 8 * ((n + 1) & 7) * kLD + s);  // next output row, one step ahead
+                    gb2[n] += (b.x + b.y) + (b.z + b.w);
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) {
+                    for (int m = 0; m < 8; ++m) {
                         float t = gW2[m][n];
-                        t = fmaf(a[m].x, b[n].x, t); t = fmaf(a[m].y, b[n].y, t);
-                        t = fmaf(a[m].z, b[n].z, t); t = fmaf(a[m].w, b[n].w, t);
+                        t = fmaf(a[m].x, b.x, t); t = fmaf(a[m].y, b.y, t);
+                        t = fmaf(a[m].z, b.z, t); t = fmaf(a[m].w, b.w, t);
                         gW2[m][n] = t;
                     }
+                    b = nb;
                 }
             }
         }
@@ -268,18 +299,32 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
         {
             const float* a = H2 + ty * 4;
             const float* w = W2t + tx * kWLD;
+            u64 p[8][4];
+            pack_tile(acc, p);
+            float4 a0 = ld4(a), a1 = ld4(a + 64);
+            float wv[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) wv[n] = w[8 * n * kWLD];
 #pragma unroll 2
             for (int k = 0; k < kH; ++k) {
-                const float4 a0 = ld4(a + k * kLD), a1 = ld4(a + k * kLD + 64);
+                const int kn = (k + 1 < kH) ? k + 1 : k;
+                const float4 na0 = ld4(a + kn * kLD), na1 = ld4(a + kn * kLD + 64);
+                float nw[8];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) nw[n] = w[8 * n * kWLD + kn];
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                float wv[8];
+                const u64 wp[4] = {pack2(wv[0], wv[1]), pack2(wv[2], wv[3]), pack2(wv[4], wv[5]), pack2(wv[6], wv[7])};
 #pragma unroll
-                for (int n = 0; n < 8; ++n) wv[n] = w[8 * n * kWLD + k];
+                for (int m = 0; m < 8; ++m) {
+                    const u64 as = pack2(av[m], av[m]);
 #pragma unroll
-                for (int m = 0; m < 8; ++m)
+                    for (int q = 0; q < 4; ++q) fma2(p[m][q], as, wp[q]);
+                }
+                a0 = na0; a1 = na1;
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(av[m], wv[n], acc[m][n]);
+                for (int n = 0; n < 8; ++n) wv[n] = nw[n];
             }
+            unpack_tile(p, acc);
         }
         __syncthreads();  // every thread has finished reading H1 (dW2) before it is overwritten
 #pragma unroll
