@@ -286,7 +286,7 @@ def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
         vclip = vl + torch.clamp(new_v - vl, -clip, clip)
         vloss = 0.5 * torch.max((new_v - rt) ** 2, (vclip - rt) ** 2).mean()
         (pg + vf * vloss).backward()
-        return torch.cat([p.grad.reshape(-1) for p in net.parameters()]), float((-logratio).sum())
+        return torch.cat([p.grad.reshape(-1) for p in net.parameters()]), float((-logratio).detach().sum())
 
     g32, kl32 = reference(agent, torch.float32)
     g64, kl64 = reference(copy.deepcopy(agent).double(), torch.float64)
