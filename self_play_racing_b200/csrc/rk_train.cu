@@ -65,7 +65,9 @@ __device__ __forceinline__ void unpack_tile(const u64 (&p)[8][4], float (&acc)[8
         for (int q = 0; q < 4; ++q) unpack2(p[m][q], acc[m][2 * q], acc[m][2 * q + 1]);
 }
 
-// acc[m][n] += sum_k A[k][s_m] * W[k][j_n]; s_m = ty*4 + (m&3) + 64*(m>>2), j_n = tx*4 + (n&3) + 32*(n>>2)
+// acc[m][n] += sum_k A[k][s_m] * W[k][j_n]; s_m = ty*4 + (m&3) + 64*(m>>2), j_n = tx + 8 n.  The weight
+// columns are stored permuted (column of output j = tx + 8n at (n>>2)*32 + tx*4 + (n&3): the 8 threads' 128-bit loads are contiguous) so that the thread's 8 outputs
+// are two 128-bit loads, while its activation rows tx + 8n land in distinct banks when stored.
 __device__ __forceinline__ void tile_product(const float* __restrict__ A, const float* __restrict__ W, int wld, int K,
                                              int ty, int tx, float (&acc)[8][8]) {
     const float* a = A + ty * 4;
@@ -109,8 +111,8 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
     float* DO = H2 + kH * kLD;           // [2][kLD]   d loss / d (pre-activation output)
     float* red = DO + 2 * kLD;           // [16]
 
-    for (int q = tid; q < kH * D; q += kNT) { const int j = q / D, i = q - j * D; W1t[i * kH + j] = P.W1[q]; }
-    for (int q = tid; q < kH * kH; q += kNT) { const int j = q >> 6, i = q & 63; W2t[i * kWLD + j] = P.W2[q]; }
+    for (int q = tid; q < kH * D; q += kNT) { const int j = q / D, i = q - j * D; W1t[i * kH + ((j >> 5) * 32 + (j & 7) * 4 + ((j >> 3) & 3))] = P.W1[q]; }
+    for (int q = tid; q < kH * kH; q += kNT) { const int j = q >> 6, i = q & 63; W2t[i * kWLD + ((j >> 5) * 32 + (j & 7) * 4 + ((j >> 3) & 3))] = P.W2[q]; }
     for (int q = tid; q < kH; q += kNT) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
     for (int q = tid; q < OUT * kH; q += kNT) sW3[q] = P.W3[q];
     float b3[OUT];
@@ -168,14 +170,14 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
         // ---- layer 1: H1 = tanh(X W1^T + b1) ----
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float b = sb1[tx * 4 + (n & 3) + 32 * (n >> 2)];
+            const float b = sb1[tx + 8 * n];
 #pragma unroll
             for (int m = 0; m < 8; ++m) acc[m][n] = b;
         }
         tile_product(X, W1t, kH, D, ty, tx, acc);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            float* h = H1 + (tx * 4 + (n & 3) + 32 * (n >> 2)) * kLD + ty * 4;
+            float* h = H1 + (tx + 8 * n) * kLD + ty * 4;
             st4(h, make_float4(tanh_fast(acc[0][n]), tanh_fast(acc[1][n]), tanh_fast(acc[2][n]), tanh_fast(acc[3][n])));
             st4(h + 64, make_float4(tanh_fast(acc[4][n]), tanh_fast(acc[5][n]), tanh_fast(acc[6][n]), tanh_fast(acc[7][n])));
         }
@@ -183,14 +185,14 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
         // ---- layer 2: H2 = tanh(H1 W2^T + b2) ----
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float b = sb2[tx * 4 + (n & 3) + 32 * (n >> 2)];
+            const float b = sb2[tx + 8 * n];
 #pragma unroll
             for (int m = 0; m < 8; ++m) acc[m][n] = b;
         }
         tile_product(H1, W2t, kWLD, kH, ty, tx, acc);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            float* h = H2 + (tx * 4 + (n & 3) + 32 * (n >> 2)) * kLD + ty * 4;
+            float* h = H2 + (tx + 8 * n) * kLD + ty * 4;
             st4(h, make_float4(tanh_fast(acc[0][n]), tanh_fast(acc[1][n]), tanh_fast(acc[2][n]), tanh_fast(acc[3][n])));
             st4(h + 64, make_float4(tanh_fast(acc[4][n]), tanh_fast(acc[5][n]), tanh_fast(acc[6][n]), tanh_fast(acc[7][n])));
         }
@@ -250,7 +252,7 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
             for (int o = 0; o < OUT; ++o) { d0[o] = ld4(DO + o * kLD + ty * 4); d1[o] = ld4(DO + o * kLD + 64 + ty * 4); }
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                const int j = tx * 4 + (n & 3) + 32 * (n >> 2);
+                const int j = tx + 8 * n;
                 float* h = H2 + j * kLD + ty * 4;
                 const float4 ha = ld4(h), hb = ld4(h + 64);
                 float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
@@ -311,7 +313,7 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
                 const float4 na0 = ld4(a + kn * kLD), na1 = ld4(a + kn * kLD + 64);
                 float nw[8];
 #pragma unroll
-                for (int n = 0; n < 8; ++n) nw[n] = w[8 * n * kWLD + kn];
+                for (int n = 0; n < 8; ++n) nw[n] = w[8 * n * kWLD + ((kn >> 5) * 32 + (kn & 7) * 4 + ((kn >> 3) & 3))];  // column of W2^T row k (permuted)
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const u64 wp[4] = {pack2(wv[0], wv[1]), pack2(wv[2], wv[3]), pack2(wv[4], wv[5]), pack2(wv[6], wv[7])};
 #pragma unroll
