@@ -233,7 +233,7 @@ RK_API int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, c
  * (agent/ppo.py:11-37) are evaluated, differentiated and their weight gradients
  * reduced over the minibatch by ONE kernel, fp32 throughout; nothing of size
  * [minibatch, 64] ever reaches HBM.  obs_dim <= RK_PPO_MAX_OBS_DIM. */
-#define RK_ADV_STAT_BLOCKS 64
+#define RK_ADV_STAT_BLOCKS 128
 #define RK_PPO_MAX_OBS_DIM 20
 /* partial (sum, sum of squares) in float64 of the minibatch's advantages adv[idx[k]],
  * k < n (idx NULL: adv[k]); part: double [RK_ADV_STAT_BLOCKS][2].  With several ranks
@@ -267,6 +267,37 @@ typedef struct rk_ppo_grad_io {
 } rk_ppo_grad_io;
 RK_API uint64_t rk_ppo_grad_workspace_bytes(void);
 RK_API int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream);
+
+/* Gradient clipping (nn.utils.clip_grad_norm_, agent/ppo.py:205), the Adam step (ppo.py:206;
+ * torch.optim.Adam without weight decay / amsgrad, learning rate read from a device scalar) and the
+ * KL early stop (ppo.py:178-182) of one minibatch as ONE kernel, in place on the caller's optimizer
+ * state.  If kl_sum / n_global > kl_target the step is not applied and state[0] latches to 1: every
+ * later call is a no-op until the caller clears it -- the host no longer has to synchronise once per
+ * minibatch to take the decision.  state[1] counts the steps applied.  flat_grad is divided by `world`
+ * first (the mean over ranks of an all-reduced sum). */
+typedef struct rk_adam_io {
+    int32_t struct_size;       /* sizeof(rk_adam_io) */
+    int32_t world;
+    float* params[12];         /* the tensors of rk_ppo_grad_io.params, updated in place */
+    float* exp_avg[12];        /* torch.optim.Adam state, updated in place */
+    float* exp_avg_sq[12];
+    float* step[12];           /* device float32 scalars (capturable Adam); each is advanced by 1 */
+    int32_t numel[12];
+    const float* flat_grad;    /* from rk_ppo_minibatch_grad (summed over ranks) */
+    const float* lr;           /* device scalar */
+    float beta1, beta2, eps, max_grad_norm, kl_target;
+    int32_t reserved0;
+    const double* kl_sum;      /* from rk_ppo_minibatch_grad (summed over ranks) */
+    double n_global;
+    int32_t* state;            /* device int32[4], zeroed by the caller: {stopped, steps applied, scratch, -} */
+    float* kl_at_stop;         /* device scalar: approx_kl that latched the stop */
+} rk_adam_io;
+RK_API int rk_ppo_adam_step(const rk_adam_io* io, void* stream);
+
+/* out[k], k < n: a seeded pseudo-random permutation of 0..n-1 (Feistel network + cycle walking, no
+ * sort) -- the minibatch shuffle of agent/ppo.py:168 (`np.random.shuffle(b_inds)`); a different
+ * (seed, counter) gives a different permutation, the same pair the same one on every rank. */
+RK_API int rk_random_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, void* stream);
 
 /* ---- measurement aid --------------------------------------------------------- */
 /* Sustained FMA throughput of the current device in TFLOP/s (fp32, or fp64 when

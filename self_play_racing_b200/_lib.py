@@ -49,6 +49,15 @@ class RkPpoGradIO(C.Structure):
                 ('workspace_bytes', C.c_uint64), ('flat_grad', C.c_void_p), ('kl_sum', C.c_void_p)]
 
 
+class RkAdamIO(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('world', C.c_int32), ('params', C.c_void_p * 12),
+                ('exp_avg', C.c_void_p * 12), ('exp_avg_sq', C.c_void_p * 12), ('step', C.c_void_p * 12),
+                ('numel', C.c_int32 * 12), ('flat_grad', C.c_void_p), ('lr', C.c_void_p),
+                ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float), ('max_grad_norm', C.c_float),
+                ('kl_target', C.c_float), ('reserved0', C.c_int32), ('kl_sum', C.c_void_p),
+                ('n_global', C.c_double), ('state', C.c_void_p), ('kl_at_stop', C.c_void_p)]
+
+
 class RkHostIO(C.Structure):
     _fields_ = [('struct_size', C.c_int32), ('n_chunks', C.c_int32), ('actions', C.c_void_p), ('obs', C.c_void_p),
                 ('arena_host', C.c_void_p), ('arena_dev', C.c_void_p), ('arena_bytes', C.c_int64),
@@ -88,6 +97,8 @@ SIGNATURES = {
     'rk_ppo_adv_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'rk_ppo_grad_workspace_bytes': (C.c_uint64, []),
     'rk_ppo_minibatch_grad': (C.c_int, [C.POINTER(RkPpoGradIO), C.c_void_p]),
+    'rk_random_permutation': (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
+    'rk_ppo_adam_step': (C.c_int, [C.POINTER(RkAdamIO), C.c_void_p]),
     'rk_ppo_loss_grad': (C.c_int, [C.c_void_p] * 10 + [C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

@@ -301,7 +301,7 @@ def ppo_loss_grad(mu, v, act, old_logp, adv, ret, v_old, log_std, adv_mean, adv_
                'rk_ppo_loss_grad')
 
 
-ADV_STAT_BLOCKS = 64     # RK_ADV_STAT_BLOCKS
+ADV_STAT_BLOCKS = 128    # RK_ADV_STAT_BLOCKS
 PPO_MAX_OBS_DIM = 20     # RK_PPO_MAX_OBS_DIM
 
 
@@ -372,3 +372,62 @@ class PpoMinibatchGrad:
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(lib.rk_ppo_minibatch_grad(C.byref(io), stream), None, 'rk_ppo_minibatch_grad')
         return self.flat_grad, self.kl_sum
+
+
+class PpoAdamStep:
+    """Gradient clipping + Adam + the KL early stop of one minibatch as one kernel
+    (rk_ppo_adam_step), in place on a torch.optim.Adam's own state tensors.
+    `state` is a device int32[2] = (stopped, steps applied); a latched stop turns
+    every later call into a no-op until `reset()`."""
+
+    def __init__(self, optimizer, params, flat_grad, kl_sum, max_grad_norm, kl_target, world=1):
+        _lib.load()
+        group = optimizer.param_groups[0]
+        if group.get('weight_decay', 0) or group.get('amsgrad', False) or group.get('maximize', False):
+            raise ValueError('PpoAdamStep: plain Adam only (no weight decay / amsgrad / maximize)')
+        if not isinstance(group['lr'], torch.Tensor) or not group['lr'].is_cuda:
+            raise ValueError('PpoAdamStep: needs a device-tensor learning rate (capturable Adam)')
+        params = list(params)
+        dev = params[0].device
+        self.device = dev
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.kl_at_stop = torch.zeros((), device=dev)
+        io = _lib.RkAdamIO()
+        io.struct_size = C.sizeof(_lib.RkAdamIO)
+        io.world = int(world)
+        keep = [flat_grad, kl_sum, group['lr']]
+        for k, p in enumerate(params):
+            st = optimizer.state[p]
+            if not all(key in st for key in ('exp_avg', 'exp_avg_sq', 'step')) or not st['step'].is_cuda:
+                raise ValueError('PpoAdamStep: optimizer state must exist on the device (run one step first)')
+            io.params[k], io.numel[k] = p.data_ptr(), p.numel()
+            io.exp_avg[k], io.exp_avg_sq[k], io.step[k] = (st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                                                         st['step'].data_ptr())
+            keep += [p, st['exp_avg'], st['exp_avg_sq'], st['step']]
+        io.flat_grad, io.lr, io.kl_sum = flat_grad.data_ptr(), group['lr'].data_ptr(), kl_sum.data_ptr()
+        io.beta1, io.beta2 = float(group['betas'][0]), float(group['betas'][1])
+        io.eps, io.max_grad_norm, io.kl_target = float(group['eps']), float(max_grad_norm), float(kl_target)
+        io.state, io.kl_at_stop = self.state.data_ptr(), self.kl_at_stop.data_ptr()
+        self.io, self._keep = io, keep
+
+    def reset(self):
+        self.state.zero_()
+
+    def __call__(self, n_global, kl_target=None):
+        if kl_target is not None:
+            self.io.kl_target = float(kl_target)
+        self.io.n_global = float(n_global)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.load().rk_ppo_adam_step(C.byref(self.io), stream), None, 'rk_ppo_adam_step')
+
+
+def random_permutation(n, seed, counter, out=None, device=None):
+    """int64 [n]: seeded pseudo-random permutation of 0..n-1 generated on the device
+    without sorting (rk_random_permutation)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=device)
+    stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+    _lib.check(lib.rk_random_permutation(int(seed) & (2 ** 64 - 1), int(counter), int(n), _ptr(out), stream), None,
+               'rk_random_permutation')
+    return out

@@ -677,6 +677,41 @@ int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
     return rc ? 1 : 0;
 }
 
+int rk_ppo_adam_step(const rk_adam_io* io, void* stream) {
+    if (!io || io->struct_size != (int32_t)sizeof(rk_adam_io)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adam_step: io->struct_size mismatch");
+        return 1;
+    }
+    bool ok = io->world >= 1 && io->flat_grad && io->lr && io->kl_sum && io->state && io->kl_at_stop && io->n_global >= 1.0;
+    for (int k = 0; k < 12; ++k)
+        ok = ok && io->params[k] && io->exp_avg[k] && io->exp_avg_sq[k] && io->step[k] && io->numel[k] > 0;
+    if (!ok) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adam_step: invalid arguments");
+        return 1;
+    }
+    PpoAdamIO a;
+    for (int k = 0; k < 12; ++k) {
+        a.params[k] = io->params[k]; a.exp_avg[k] = io->exp_avg[k]; a.exp_avg_sq[k] = io->exp_avg_sq[k];
+        a.step[k] = io->step[k]; a.numel[k] = io->numel[k];
+    }
+    a.flat_grad = io->flat_grad; a.lr = io->lr;
+    a.beta1 = io->beta1; a.beta2 = io->beta2; a.eps = io->eps; a.max_norm = io->max_grad_norm; a.kl_target = io->kl_target;
+    a.world = io->world; a.kl_sum = io->kl_sum; a.n_global = io->n_global; a.state = io->state; a.kl_at_stop = io->kl_at_stop;
+    if (launch_clip_adam(a, (cudaStream_t)stream)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adam_step: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
+int rk_random_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, void* stream) {
+    if (!out || n < 0 || n > ((int64_t)1 << 40)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_random_permutation: invalid arguments");
+        return 1;
+    }
+    return launch_permutation(seed, counter, n, out, (cudaStream_t)stream);
+}
+
 int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
                   uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
                   float* mean, void* stream) {

@@ -427,39 +427,57 @@ __global__ void __launch_bounds__(kNT, 2) ppo_mlp_grad_kernel(const GradArgs g) 
     else net_body<1>(g, g.net[1], train_smem);
 }
 
-// flat_grad[q] = sum over CTAs of partial[net][cta][q'] in a fixed order; *kl_sum = sum kl_partial
-__global__ void ppo_grad_reduce_kernel(const float* __restrict__ partial, const double* __restrict__ kl_partial,
-                                       int ncta, int n_actor, int n_total, float* __restrict__ flat_grad,
-                                       double* __restrict__ kl_sum) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// flat_grad[q] = sum over CTAs of partial[net][cta][q'] in a fixed order; *kl_sum = sum kl_partial.
+// Block = 64 gradient elements x 4 groups of CTAs (each thread sums its quarter with 4 independent
+// chains, the quarters are combined through shared memory in a fixed order).
+__global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const float* __restrict__ partial,
+                                                              const double* __restrict__ kl_partial, int ncta, int n_actor,
+                                                              int n_total, float* __restrict__ flat_grad,
+                                                              double* __restrict__ kl_sum) {
+    __shared__ float part[4][64];
+    const int lane64 = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int q = blockIdx.x * 64 + lane64;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (q < n_total) {
         const int net = q >= n_actor, local = net ? q - n_actor : q;
         const float* src = partial + (size_t)net * ncta * kNetStride + local;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int c = 0;
-        for (; c + 4 <= ncta; c += 4) {
+        const int per = (ncta + 3) >> 2, c0 = grp * per, c1 = min(ncta, c0 + per);
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
             s0 += src[(size_t)c * kNetStride]; s1 += src[(size_t)(c + 1) * kNetStride];
             s2 += src[(size_t)(c + 2) * kNetStride]; s3 += src[(size_t)(c + 3) * kNetStride];
         }
-        for (; c < ncta; ++c) s0 += src[(size_t)c * kNetStride];
-        flat_grad[q] = (s0 + s1) + (s2 + s3);
+        for (; c < c1; ++c) s0 += src[(size_t)c * kNetStride];
     }
-    if (q == 0) {
-        double s = 0.0;
-        for (int c = 0; c < ncta; ++c) s += kl_partial[c];
-        *kl_sum = s;
+    part[grp][lane64] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (grp == 0 && q < n_total) flat_grad[q] = (part[0][lane64] + part[1][lane64]) + (part[2][lane64] + part[3][lane64]);
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        double sk = 0.0;
+        for (int c = threadIdx.x; c < ncta; c += 32) sk += kl_partial[c];
+        for (int m = 16; m > 0; m >>= 1) sk += __shfl_xor_sync(0xffffffffu, sk, m);
+        if (threadIdx.x == 0) *kl_sum = sk;
     }
 }
 
 // partial (sum, sum of squares) of adv[idx[k]] in float64: kAdvBlocks blocks, fixed order inside each
-__global__ void adv_stats_kernel(const int64_t* __restrict__ idx, const float* __restrict__ adv, int n,
-                                 double* __restrict__ part) {
+__global__ void __launch_bounds__(512) adv_stats_kernel(const int64_t* __restrict__ idx, const float* __restrict__ adv,
+                                                        int n, double* __restrict__ part) {
     double s1 = 0.0, s2 = 0.0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int stride = gridDim.x * blockDim.x;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + 3 * stride < n; k += 4 * stride) {   // four independent gathers in flight
+        float a[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = adv[idx ? idx[k + r * stride] : (int64_t)(k + r * stride)];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { s1 += (double)a[r]; s2 += (double)a[r] * (double)a[r]; }
+    }
+    for (; k < n; k += stride) {
         const double a = (double)adv[idx ? idx[k] : (int64_t)k];
         s1 += a; s2 += a * a;
     }
-    __shared__ double r1[8], r2[8];
+    __shared__ double r1[16], r2[16];
     for (int m = 16; m > 0; m >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, m); s2 += __shfl_xor_sync(0xffffffffu, s2, m); }
     if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
     __syncthreads();
@@ -467,6 +485,121 @@ __global__ void adv_stats_kernel(const int64_t* __restrict__ idx, const float* _
         double a = 0.0, b = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r1[w]; b += r2[w]; }
         part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// A seeded pseudo-random permutation of 0..n-1 without sorting: a 6-round balanced Feistel network over
+// the next even power of two with cycle walking (out-of-range images are mapped again until they fall
+// below n).  Replaces np.random.shuffle(b_inds) (agent/ppo.py:168) / torch.randperm, which sorts.
+__device__ __forceinline__ uint32_t feistel_round(uint32_t x, uint32_t key) {
+    x = (x ^ key) * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+    return x;
+}
+__global__ void permutation_kernel(uint64_t seed, uint64_t counter, int64_t n, int half_bits, int64_t* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t keys[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), 0x7065726du, 0u};
+    philox4x32_10(keys, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint64_t x = (uint64_t)k;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 6; ++round) {
+            const uint32_t t = l ^ (feistel_round(r, keys[round & 3] + 0x9E3779B9u * (uint32_t)round) & mask);
+            l = r; r = t;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while ((int64_t)x >= n);
+    out[k] = (int64_t)x;
+}
+
+// Gradient clipping + Adam + the KL early stop of one minibatch step (agent/ppo.py:178-182,205-207) as one
+// single-CTA kernel over the ~11k parameters, operating in place on the torch optimizer's own state
+// tensors (exp_avg, exp_avg_sq, step), so that optimizer.state_dict() stays the reference's.
+//   approx_kl = kl_sum / n_global > kl_target  ->  the step is NOT applied and `state[0]` latches: every
+//   later call is a no-op until the host clears it (the reference breaks out of all epochs).
+// Otherwise: g /= world; g *= min(1, max_norm / (||g|| + 1e-6)) (nn.utils.clip_grad_norm_), then torch's
+// Adam update (no weight decay, no amsgrad) with the learning rate read from its device tensor.
+struct AdamArgs {
+    float* p[12];
+    float* m[12];
+    float* v[12];
+    float* step[12];
+    int off[13];
+    const float* grad;
+    const float* lr;
+    float beta1, beta2, eps, max_norm, kl_target;
+    int world;
+    const double* kl_sum;
+    double n_global;
+    int* state;        // [0] stopped, [1] optimizer steps applied since the host cleared it, [2] scratch counter
+    float* kl_at_stop;
+};
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a) {
+    __shared__ float red[8];
+    __shared__ float s_clip;
+    const int tid = threadIdx.x;
+    if (a.state[0]) return;
+    const double approx_kl = *a.kl_sum / a.n_global;
+    if (approx_kl > (double)a.kl_target) {
+        if (blockIdx.x == 0 && tid == 0) { *a.kl_at_stop = (float)approx_kl; }
+        // state[0] is latched by the LAST block to pass here, so that no block of this launch reads the flag set
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(&a.state[2], 1) == (int)gridDim.x - 1) { a.state[2] = 0; a.state[0] = 1; }
+        }
+        return;
+    }
+    // every block computes the global gradient norm itself, in the same fixed order (deterministic)
+    const float inv_world = 1.f / (float)a.world;
+    const int n = a.off[12];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int e = tid;
+    for (; e + 768 < n; e += 1024) {
+        const float g0 = a.grad[e] * inv_world, g1 = a.grad[e + 256] * inv_world, g2 = a.grad[e + 512] * inv_world,
+                    g3 = a.grad[e + 768] * inv_world;
+        s0 = fmaf(g0, g0, s0); s1 = fmaf(g1, g1, s1); s2 = fmaf(g2, g2, s2); s3 = fmaf(g3, g3, s3);
+    }
+    for (; e < n; e += 256) { const float gv = a.grad[e] * inv_world; s0 = fmaf(gv, gv, s0); }
+    float ss = (s0 + s1) + (s2 + s3);
+    for (int m = 16; m > 0; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_clip = fminf(a.max_norm / (sqrtf(t) + 1e-6f), 1.f);
+    }
+    __syncthreads();
+    const float scale = s_clip * inv_world;
+    const float t_new = a.step[0][0] + 1.f;   // advanced only by the last block to finish (below)
+    const float bc1 = (float)(1.0 - pow((double)a.beta1, (double)t_new));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, (double)t_new));
+    const float step_size = *a.lr / bc1;
+    const int q = blockIdx.x * 256 + tid;
+    if (q < n) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 12; ++j) k += (q >= a.off[j]);
+        const int el = q - a.off[k];
+        float *pp = a.p[k] + el, *pm = a.m[k] + el, *pv = a.v[k] + el;
+        const float gv = a.grad[q] * scale;
+        const float mm = *pm + (gv - *pm) * (1.f - a.beta1);           // torch: exp_avg.lerp_(grad, 1 - beta1)
+        const float vv = a.beta2 * *pv + (1.f - a.beta2) * gv * gv;
+        *pm = mm; *pv = vv;
+        *pp -= step_size * mm / (sqrtf(vv) / bc2_sqrt + a.eps);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&a.state[2], 1) == (int)gridDim.x - 1) {   // every other block has read step[] and finished
+            a.state[2] = 0;
+            for (int k = 0; k < 12; ++k) a.step[k][0] = t_new;
+            a.state[1] += 1;
+        }
     }
 }
 
@@ -493,7 +626,7 @@ size_t ppo_grad_workspace_bytes() {
 }
 
 int launch_adv_stats(const int64_t* idx, const float* adv, int n, double* part, cudaStream_t stream) {
-    adv_stats_kernel<<<kAdvBlocks, 256, 0, stream>>>(idx, adv, n, part);
+    adv_stats_kernel<<<kAdvBlocks, 512, 0, stream>>>(idx, adv, n, part);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -524,8 +657,34 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     count_launch();
     const int n_actor = kH * io.obs_dim + kH + kH * kH + kH + 2 * kH + 2;
     const int n_total = n_actor + kH * io.obs_dim + kH + kH * kH + kH + kH + 1;
-    ppo_grad_reduce_kernel<<<(n_total + 127) / 128, 128, 0, stream>>>(g.partial, g.kl_partial, ncta, n_actor, n_total,
+    ppo_grad_reduce_kernel<<<(n_total + 63) / 64, 256, 0, stream>>>(g.partial, g.kl_partial, ncta, n_actor, n_total,
                                                                        io.flat_grad, io.kl_sum);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_clip_adam(const PpoAdamIO& io, cudaStream_t stream) {
+    AdamArgs a;
+    int off = 0;
+    for (int k = 0; k < 12; ++k) {
+        a.p[k] = io.params[k]; a.m[k] = io.exp_avg[k]; a.v[k] = io.exp_avg_sq[k]; a.step[k] = io.step[k];
+        a.off[k] = off;
+        off += io.numel[k];
+    }
+    a.off[12] = off;
+    a.grad = io.flat_grad; a.lr = io.lr;
+    a.beta1 = io.beta1; a.beta2 = io.beta2; a.eps = io.eps; a.max_norm = io.max_norm; a.kl_target = io.kl_target;
+    a.world = io.world; a.kl_sum = io.kl_sum; a.n_global = io.n_global; a.state = io.state; a.kl_at_stop = io.kl_at_stop;
+    clip_adam_kernel<<<(off + 255) / 256, 256, 0, stream>>>(a);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    int bits = 2;
+    while (((int64_t)1 << bits) < n) bits += 2;   // even number of bits: two equal Feistel halves
+    permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, counter, n, bits / 2, out);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

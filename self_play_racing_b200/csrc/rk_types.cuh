@@ -131,7 +131,7 @@ int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, cons
                          double* kl_sum, cudaStream_t stream);
 
 // fused PPO minibatch gradient (rk_train.cu)
-constexpr int kAdvBlocks = 64;  // partial sums produced by launch_adv_stats ([kAdvBlocks][2] doubles)
+constexpr int kAdvBlocks = 128;  // partial sums produced by launch_adv_stats ([kAdvBlocks][2] doubles)
 struct PpoGradIO {
     int obs_dim, n;
     double n_global;
@@ -146,6 +146,23 @@ struct PpoGradIO {
     float* flat_grad;
     double* kl_sum;
 };
+struct PpoAdamIO {
+    float* params[12];
+    float* exp_avg[12];
+    float* exp_avg_sq[12];
+    float* step[12];
+    int numel[12];
+    const float* flat_grad;
+    const float* lr;
+    float beta1, beta2, eps, max_norm, kl_target;
+    int world;
+    const double* kl_sum;
+    double n_global;
+    int* state;
+    float* kl_at_stop;
+};
+int launch_clip_adam(const PpoAdamIO& io, cudaStream_t stream);
+int launch_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, cudaStream_t stream);
 size_t ppo_grad_workspace_bytes();
 int launch_adv_stats(const int64_t* idx, const float* adv, int n, double* part, cudaStream_t stream);
 int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream);

@@ -210,11 +210,12 @@ def test_graphed_update_equals_eager_update(pkg):
     same parameters as the eager step-by-step update, and honours the KL stop."""
     env_mod, agent_mod, configs = pkg
     results = []
-    for graphed, fused, fused_mlp in ((False, False, False), (True, False, False), (True, True, False),
-                                      (True, True, True)):
+    for graphed, fused, fused_mlp, fused_adam in ((False, False, False, False), (True, False, False, False),
+                                                  (True, True, False, False), (True, True, True, False),
+                                                  (True, True, True, True)):
         cfg = configs.base_config(num_envs=64, num_steps=64, update_epochs=2, num_minibatches=4, kl_target=1e9,
                                   cuda_graph_update=graphed, fused_update_kernels=fused,
-                                  fused_mlp_update=fused_mlp)
+                                  fused_mlp_update=fused_mlp, fused_adam_step=fused_adam)
         vec = env_mod.BatchedRacingVecEnv.synthetic('single', 64, n_tracks=4, seed=0)
         tr = agent_mod.PPO(vec, cfg, device='cuda')
         g = torch.Generator(device='cuda').manual_seed(0)
@@ -239,6 +240,7 @@ def test_graphed_update_equals_eager_update(pkg):
             assert torch.equal(a, b)
         vec.close()
     # eager autograd == graphed autograd == graphed + fused loss-gradient kernel == one-kernel forward/loss/backward
+    # == the same with clip + Adam + KL stop as one kernel (no per-minibatch host sync)
     for other in results[1:]:
         for a, b in zip(results[0], other):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
@@ -305,6 +307,26 @@ def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
     first = flat.clone()
     fused(idx, *src)
     assert torch.equal(first, fused.flat_grad)
+
+
+@pytest.mark.parametrize('n', [1, 2, 5, 64, 1000, 65536, 4194304, 3000001])
+def test_device_permutation_is_a_permutation(pkg, n):
+    """rk_random_permutation: every index exactly once, reproducible per (seed,
+    counter), different across counters, and not the identity / not sorted."""
+    from self_play_racing_b200.backend import random_permutation
+    a = random_permutation(n, 7, 1, device='cuda')
+    assert a.dtype == torch.int64 and a.shape == (n,)
+    assert torch.equal(torch.sort(a).values, torch.arange(n, device='cuda'))
+    assert torch.equal(a, random_permutation(n, 7, 1, device='cuda'))
+    if n >= 64:
+        b = random_permutation(n, 7, 2, device='cuda')
+        assert not torch.equal(a, b)
+        fixed = float((a == torch.arange(n, device='cuda')).float().mean())
+        assert fixed < 0.2
+        # no long-range order: neighbours are uncorrelated
+        x = a[:-1].double() / n - 0.5
+        y = a[1:].double() / n - 0.5
+        assert abs(float((x * y).mean()) * 12) < 0.2 if n < 1000 else abs(float((x * y).mean()) * 12) < 0.05
 
 
 def test_batched_evaluation_protocol(pkg):
