@@ -81,20 +81,28 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 // inputs stays rolled with static register indexing of the 2 x 64 accumulators.
 __device__ __forceinline__ void dense2(const float* __restrict__ wt, const float* __restrict__ b, int nin,
                                        const float* xs, float (&y0)[kHidden], float (&y1)[kHidden]) {
+    // packed fp32 FMA (SASS FFMA2, activation broadcast): 64 instead of 128 FMA instructions per input,
+    // bit-identical to scalar fmaf
+    float2 p0[kHidden / 2], p1[kHidden / 2];
 #pragma unroll
-    for (int j = 0; j < kHidden; ++j) { y0[j] = b[j]; y1[j] = b[j]; }
+    for (int j = 0; j < kHidden / 2; ++j) { p0[j] = make_float2(b[2 * j], b[2 * j + 1]); p1[j] = p0[j]; }
 #pragma unroll 2
     for (int i = 0; i < nin; ++i) {
         const float xa = xs[i * kPolicyCols], xb = xs[i * kPolicyCols + kPolicyThreads];
+        const float2 xa2 = make_float2(xa, xa), xb2 = make_float2(xb, xb);
         const float4* row = reinterpret_cast<const float4*>(wt + i * kHidden);
 #pragma unroll
         for (int j4 = 0; j4 < kHidden / 4; ++j4) {
             const float4 w = row[j4];
-            y0[4 * j4 + 0] = fmaf(w.x, xa, y0[4 * j4 + 0]); y1[4 * j4 + 0] = fmaf(w.x, xb, y1[4 * j4 + 0]);
-            y0[4 * j4 + 1] = fmaf(w.y, xa, y0[4 * j4 + 1]); y1[4 * j4 + 1] = fmaf(w.y, xb, y1[4 * j4 + 1]);
-            y0[4 * j4 + 2] = fmaf(w.z, xa, y0[4 * j4 + 2]); y1[4 * j4 + 2] = fmaf(w.z, xb, y1[4 * j4 + 2]);
-            y0[4 * j4 + 3] = fmaf(w.w, xa, y0[4 * j4 + 3]); y1[4 * j4 + 3] = fmaf(w.w, xb, y1[4 * j4 + 3]);
+            const float2 wl = make_float2(w.x, w.y), wh = make_float2(w.z, w.w);
+            p0[2 * j4] = __ffma2_rn(wl, xa2, p0[2 * j4]); p1[2 * j4] = __ffma2_rn(wl, xb2, p1[2 * j4]);
+            p0[2 * j4 + 1] = __ffma2_rn(wh, xa2, p0[2 * j4 + 1]); p1[2 * j4 + 1] = __ffma2_rn(wh, xb2, p1[2 * j4 + 1]);
         }
+    }
+#pragma unroll
+    for (int j = 0; j < kHidden / 2; ++j) {
+        y0[2 * j] = p0[j].x; y0[2 * j + 1] = p0[j].y;
+        y1[2 * j] = p1[j].x; y1[2 * j + 1] = p1[j].y;
     }
 }
 
