@@ -245,13 +245,14 @@ typedef struct rk_ppo_grad_io {
     int32_t struct_size;       /* sizeof(rk_ppo_grad_io) */
     int32_t obs_dim;
     int32_t n;                 /* rows of this rank's minibatch */
-    int32_t reserved0;
+    int32_t obs_stride;        /* floats between observation rows; 0 = obs_dim.  A stride that is a multiple
+                                * of 4 (rows padded to 16 bytes, padding readable) is gathered with 128-bit loads */
     double n_global;           /* rows of the global minibatch (n * world size) */
     /* parameters in torch layout [out][in]: actor_mu.{0,2,4}.{weight,bias} then critic.{0,2,4}.{weight,bias} */
     const float* params[12];
     const float* log_std;      /* [2] */
     /* the flat rollout buffers (agent/ppo.py:158-165) and the minibatch's row indices into them */
-    const float* obs;          /* [B, obs_dim] */
+    const float* obs;          /* [B, obs_stride] */
     const float* act;          /* [B, 2] */
     const float* old_logp;     /* [B] */
     const float* adv;          /* [B] raw advantages; normalised inside with `adv_part` */

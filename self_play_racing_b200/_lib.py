@@ -41,7 +41,7 @@ class RkStepIO(C.Structure):
 
 
 class RkPpoGradIO(C.Structure):
-    _fields_ = [('struct_size', C.c_int32), ('obs_dim', C.c_int32), ('n', C.c_int32), ('reserved0', C.c_int32),
+    _fields_ = [('struct_size', C.c_int32), ('obs_dim', C.c_int32), ('n', C.c_int32), ('obs_stride', C.c_int32),
                 ('n_global', C.c_double), ('params', C.c_void_p * 12), ('log_std', C.c_void_p),
                 ('obs', C.c_void_p), ('act', C.c_void_p), ('old_logp', C.c_void_p), ('adv', C.c_void_p),
                 ('ret', C.c_void_p), ('val', C.c_void_p), ('idx', C.c_void_p), ('adv_part', C.c_void_p),

@@ -394,16 +394,27 @@ class PPO:
         the reference), graph 2 = gradient clipping + Adam.  With world > 1 the flat
         gradient and the KL sum are all-reduced between the two graphs."""
         c = self.config
-        b_obs = obs.reshape(-1, obs.shape[-1]).contiguous()
+        g = self._graphed
+        d_obs = obs.shape[-1]
+        n_rows = obs.numel() // d_obs
+        mb_rows = max(n_rows // c['num_minibatches'], 1)
+        if g is None or g.mb != mb_rows or g.obs.shape[1] != d_obs:
+            g = self._graphed = _GraphedMinibatch(self, mb_rows, d_obs)
+        if g.fused_mlp:
+            # rows padded to a multiple of 4 floats (the kernel gathers them with 128-bit loads), filled
+            # straight from the rollout buffer's view
+            if getattr(g, 'obs_pad', None) is None or g.obs_pad.shape[0] != n_rows:
+                g.obs_pad = torch.zeros(n_rows, (d_obs + 3) & ~3, device=obs.device)
+            b_obs = g.obs_pad[:, :d_obs]
+            b_obs.unflatten(0, obs.shape[:-1]).copy_(obs)
+        else:
+            b_obs = obs.reshape(-1, d_obs).contiguous()
         b_actions = actions.reshape(-1, actions.shape[-1]).contiguous()
         b_logprobs, b_adv = logprobs.reshape(-1).contiguous(), advantages.reshape(-1).contiguous()
         b_returns, b_values = returns.reshape(-1).contiguous(), values.reshape(-1).contiguous()
         n_local = b_obs.shape[0]
         mb = max(n_local // c['num_minibatches'], 1)
         fused = c.get('fused_update_kernels', True)
-        g = self._graphed
-        if g is None or g.mb != mb or g.obs.shape[1] != b_obs.shape[1]:
-            g = self._graphed = _GraphedMinibatch(self, mb, b_obs.shape[1])
         n_steps = 0
         n_glob = float(mb * self.world)
         if g.fused_mlp and g.adam is not None:

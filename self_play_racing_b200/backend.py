@@ -365,6 +365,7 @@ class PpoMinibatchGrad:
         lib = _lib.load()
         io = self.io
         io.n = int(obs.shape[0] if idx is None else idx.numel())
+        io.obs_stride = int(obs.stride(0))    # rows may be padded (e.g. to 20 floats: 128-bit gathers)
         io.n_global = float(n_global if n_global is not None else io.n)
         io.obs, io.act, io.old_logp = obs.data_ptr(), act.data_ptr(), old_logp.data_ptr()
         io.adv, io.ret, io.val = adv.data_ptr(), ret.data_ptr(), val.data_ptr()

@@ -653,7 +653,8 @@ int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_minibatch_grad: io->struct_size mismatch");
         return 1;
     }
-    bool ok = io->n > 0 && io->obs_dim > 0 && io->obs_dim <= RK_PPO_MAX_OBS_DIM && io->n_global >= 2.0 && io->log_std &&
+    bool ok = io->n > 0 && io->obs_dim > 0 && io->obs_dim <= RK_PPO_MAX_OBS_DIM &&
+              (io->obs_stride == 0 || io->obs_stride >= io->obs_dim) && io->n_global >= 2.0 && io->log_std &&
               io->obs && io->act && io->old_logp && io->adv && io->ret && io->val && io->adv_part && io->workspace &&
               io->flat_grad && io->kl_sum;
     for (int k = 0; k < 12; ++k) ok = ok && io->params[k] != nullptr;
@@ -665,6 +666,7 @@ int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
     }
     PpoGradIO g;
     g.obs_dim = io->obs_dim; g.n = io->n; g.n_global = io->n_global;
+    g.obs_stride = io->obs_stride > 0 ? io->obs_stride : io->obs_dim;
     for (int k = 0; k < 12; ++k) g.params[k] = io->params[k];
     g.log_std = io->log_std;
     g.obs = io->obs; g.act = io->act; g.old_logp = io->old_logp; g.adv = io->adv; g.ret = io->ret; g.val = io->val;

@@ -36,7 +36,7 @@ struct GradArgs {
     const int64_t* idx;
     const double* adv_part;  // [kAdvBlocks][2] partial (sum, sum of squares) of the minibatch advantages
     double n_global;
-    int n, D;
+    int n, D, obs_stride;
     float clip, vf_coef;
     float* partial;       // [2][gridDim.x][kNetStride]
     double* kl_partial;   // [gridDim.x]
@@ -147,14 +147,23 @@ __device__ __forceinline__ void net_body(const GradArgs& g, const NetPtrs& P, fl
     __syncthreads();
 
     const int ntiles = (g.n + kTS - 1) / kTS;
+    const bool vec_rows = (g.obs_stride & 3) == 0 && g.obs_stride >= ((D + 3) & ~3) &&
+                          (reinterpret_cast<uintptr_t>(g.obs) & 15u) == 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- gather the tile: thread <-> sample ----
         const int gi = tile * kTS + tid;
         const bool valid = gi < g.n;
         const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
         {
-            const float* src = g.obs + row * D;
-            for (int i = 0; i < D; ++i) X[i * kLD + tid] = valid ? src[i] : 0.f;
+            const float* src = g.obs + row * g.obs_stride;
+            if (vec_rows) {   // rows padded to 16 bytes: ceil(D/4) 128-bit loads (the padding lands in unused X rows)
+                for (int i = 0; i < D; i += 4) {
+                    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    X[i * kLD + tid] = v.x; X[(i + 1) * kLD + tid] = v.y; X[(i + 2) * kLD + tid] = v.z; X[(i + 3) * kLD + tid] = v.w;
+                }
+            } else {
+                for (int i = 0; i < D; ++i) X[i * kLD + tid] = valid ? src[i] : 0.f;
+            }
         }
         float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
         if (valid) {
@@ -641,6 +650,7 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     g.log_std = io.log_std;
     g.obs = io.obs; g.act = io.act; g.old_logp = io.old_logp; g.adv = io.adv; g.ret = io.ret; g.val = io.val;
     g.idx = io.idx; g.adv_part = io.adv_part; g.n_global = io.n_global; g.n = io.n; g.D = io.obs_dim;
+    g.obs_stride = io.obs_stride;
     g.clip = io.clip; g.vf_coef = io.vf_coef;
     const int ncta = train_grid(io.n);
     if (io.workspace_bytes < 2 * (size_t)ncta * kNetStride * sizeof(float) + (size_t)ncta * sizeof(double)) return 3;

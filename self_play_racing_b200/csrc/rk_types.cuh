@@ -133,7 +133,7 @@ int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, cons
 // fused PPO minibatch gradient (rk_train.cu)
 constexpr int kAdvBlocks = 128;  // partial sums produced by launch_adv_stats ([kAdvBlocks][2] doubles)
 struct PpoGradIO {
-    int obs_dim, n;
+    int obs_dim, n, obs_stride;
     double n_global;
     const float* params[12];  // actor W1,b1,W2,b2,W3,b3 then critic, torch layouts [out][in]
     const float* log_std;

@@ -307,6 +307,12 @@ def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
     first = flat.clone()
     fused(idx, *src)
     assert torch.equal(first, fused.flat_grad)
+    # observation rows padded to 16 bytes (the 128-bit gather path): bit-identical gradient
+    dp = (obs_dim + 3) & ~3
+    padded = torch.full((src[0].shape[0], dp), 7.0, device='cuda')
+    padded[:, :obs_dim] = src[0]
+    fused(idx, padded[:, :obs_dim], *src[1:])
+    assert torch.equal(first, fused.flat_grad)
 
 
 @pytest.mark.parametrize('n', [1, 2, 5, 64, 1000, 65536, 4194304, 3000001])
