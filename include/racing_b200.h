@@ -265,6 +265,8 @@ typedef struct rk_ppo_grad_io {
     uint64_t workspace_bytes;
     float* flat_grad;          /* out: d loss / d params, concatenated in the order of `params` */
     double* kl_sum;            /* out: sum over the n rows of (logp_old - logp_new)  (ppo.py:178-182) */
+    float* kl_sum_f32;         /* optional out: the same as float32 -- e.g. the slot right after flat_grad, so
+                                * that ONE all-reduce carries the gradient and the KL sum across ranks */
 } rk_ppo_grad_io;
 RK_API uint64_t rk_ppo_grad_workspace_bytes(void);
 RK_API int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream);
@@ -289,6 +291,7 @@ typedef struct rk_adam_io {
     float beta1, beta2, eps, max_grad_norm, kl_target;
     int32_t reserved0;
     const double* kl_sum;      /* from rk_ppo_minibatch_grad (summed over ranks) */
+    const float* kl_sum_f32;   /* optional: if not NULL it is used instead of kl_sum */
     double n_global;
     int32_t* state;            /* device int32[4], zeroed by the caller: {stopped, steps applied, scratch, -} */
     float* kl_at_stop;         /* device scalar: approx_kl that latched the stop */

@@ -46,7 +46,8 @@ class RkPpoGradIO(C.Structure):
                 ('obs', C.c_void_p), ('act', C.c_void_p), ('old_logp', C.c_void_p), ('adv', C.c_void_p),
                 ('ret', C.c_void_p), ('val', C.c_void_p), ('idx', C.c_void_p), ('adv_part', C.c_void_p),
                 ('clip_coef', C.c_float), ('vf_coef', C.c_float), ('workspace', C.c_void_p),
-                ('workspace_bytes', C.c_uint64), ('flat_grad', C.c_void_p), ('kl_sum', C.c_void_p)]
+                ('workspace_bytes', C.c_uint64), ('flat_grad', C.c_void_p), ('kl_sum', C.c_void_p),
+                ('kl_sum_f32', C.c_void_p)]
 
 
 class RkAdamIO(C.Structure):
@@ -54,7 +55,7 @@ class RkAdamIO(C.Structure):
                 ('exp_avg', C.c_void_p * 12), ('exp_avg_sq', C.c_void_p * 12), ('step', C.c_void_p * 12),
                 ('numel', C.c_int32 * 12), ('flat_grad', C.c_void_p), ('lr', C.c_void_p),
                 ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float), ('max_grad_norm', C.c_float),
-                ('kl_target', C.c_float), ('reserved0', C.c_int32), ('kl_sum', C.c_void_p),
+                ('kl_target', C.c_float), ('reserved0', C.c_int32), ('kl_sum', C.c_void_p), ('kl_sum_f32', C.c_void_p),
                 ('n_global', C.c_double), ('state', C.c_void_p), ('kl_at_stop', C.c_void_p)]
 
 

@@ -190,7 +190,7 @@ class _GraphedMinibatch:
             if c.get('fused_adam_step', True):
                 # clip + Adam + KL stop as one kernel on the optimizer's own state: no per-minibatch host sync
                 self.adam = PpoAdamStep(opt, params, self.flat_grad, self.kl_sum, c['max_grad_norm'], c['kl_target'],
-                                        world=world)
+                                        world=world, kl_sum_f32=self.grad.kl_f32 if world > 1 else None)
             return
         with torch.cuda.graph(self.fwd_bwd):
             fwd_bwd()
@@ -422,14 +422,12 @@ class PPO:
             g.adam.reset()
             for epoch in range(c['update_epochs']):
                 perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
-                for start in range(0, n_local - mb + 1, mb):
-                    idx = perm[start:start + mb]
-                    part = g.grad.stats(idx, b_adv)
-                    self._all_reduce(part)
-                    g.grad(idx, b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values, n_global=n_glob)
-                    if self.world > 1:
-                        self._all_reduce(g.kl_sum)
-                        self._all_reduce(g.flat_grad)
+                # the epoch's advantage statistics need one all-reduce, every minibatch one more (gradient + KL)
+                self._all_reduce(g.grad.stats_epoch(perm, mb, b_adv))
+                for k, start in enumerate(range(0, n_local - mb + 1, mb)):
+                    g.grad.use_stats(k)
+                    g.grad(perm[start:start + mb], b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values, n_global=n_glob)
+                    self._all_reduce(g.grad.grad_and_kl)
                     g.adam(n_glob, kl_target=c['kl_target'])
                 stopped, n_steps = (int(v) for v in g.adam.state.tolist()[:2])   # one host sync per epoch
                 if stopped:

@@ -328,9 +328,13 @@ class PpoMinibatchGrad:
         dev = params[0].device
         self._keep = (params, log_std)
         self.device = dev
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+        n_total = sum(p.numel() for p in params)
+        # gradient and (float32) KL sum share one buffer: a single all-reduce carries both across ranks
+        self.grad_and_kl = torch.zeros(n_total + 1, device=dev)
+        self.flat_grad, self.kl_f32 = self.grad_and_kl[:n_total], self.grad_and_kl[n_total:]
         self.kl_sum = torch.zeros((), device=dev, dtype=torch.float64)
         self.adv_part = torch.zeros(ADV_STAT_BLOCKS, 2, device=dev, dtype=torch.float64)
+        self._adv_all = None
         nbytes = int(lib.rk_ppo_grad_workspace_bytes())
         self.workspace = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         io = _lib.RkPpoGradIO()
@@ -345,6 +349,7 @@ class PpoMinibatchGrad:
         io.clip_coef, io.vf_coef = float(clip_coef), float(vf_coef)
         io.workspace, io.workspace_bytes = self.workspace.data_ptr(), nbytes
         io.flat_grad, io.kl_sum = self.flat_grad.data_ptr(), self.kl_sum.data_ptr()
+        io.kl_sum_f32 = self.kl_f32.data_ptr()
         self.io = io
 
     def grad_views(self):
@@ -357,7 +362,21 @@ class PpoMinibatchGrad:
 
     def stats(self, idx, adv):
         ppo_adv_stats(idx, adv, self.adv_part)
+        self.io.adv_part = self.adv_part.data_ptr()
         return self.adv_part
+
+    def stats_epoch(self, perm, mb, adv):
+        """Advantage statistics of ALL minibatches perm[k*mb:(k+1)*mb] of an epoch: float64
+        [n_minibatches, ADV_STAT_BLOCKS, 2] (to be all-reduced once); select with use_stats(k)."""
+        nmb = perm.numel() // mb
+        if self._adv_all is None or self._adv_all.shape[0] != nmb:
+            self._adv_all = torch.zeros(nmb, ADV_STAT_BLOCKS, 2, device=self.device, dtype=torch.float64)
+        for k in range(nmb):
+            ppo_adv_stats(perm[k * mb:(k + 1) * mb], adv, self._adv_all[k])
+        return self._adv_all
+
+    def use_stats(self, k):
+        self.io.adv_part = self._adv_all[k].data_ptr()
 
     def __call__(self, idx, obs, act, old_logp, adv, ret, val, n_global=None):
         """flat_grad, kl_sum <- gradient of the minibatch rows idx (None: all rows);
@@ -381,7 +400,7 @@ class PpoAdamStep:
     `state` is a device int32[2] = (stopped, steps applied); a latched stop turns
     every later call into a no-op until `reset()`."""
 
-    def __init__(self, optimizer, params, flat_grad, kl_sum, max_grad_norm, kl_target, world=1):
+    def __init__(self, optimizer, params, flat_grad, kl_sum, max_grad_norm, kl_target, world=1, kl_sum_f32=None):
         _lib.load()
         group = optimizer.param_groups[0]
         if group.get('weight_decay', 0) or group.get('amsgrad', False) or group.get('maximize', False):
@@ -409,6 +428,8 @@ class PpoAdamStep:
         io.beta1, io.beta2 = float(group['betas'][0]), float(group['betas'][1])
         io.eps, io.max_grad_norm, io.kl_target = float(group['eps']), float(max_grad_norm), float(kl_target)
         io.state, io.kl_at_stop = self.state.data_ptr(), self.kl_at_stop.data_ptr()
+        io.kl_sum_f32 = None if kl_sum_f32 is None else kl_sum_f32.data_ptr()
+        keep.append(kl_sum_f32)
         self.io, self._keep = io, keep
 
     def reset(self):

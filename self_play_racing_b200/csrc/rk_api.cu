@@ -672,7 +672,7 @@ int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
     g.obs = io->obs; g.act = io->act; g.old_logp = io->old_logp; g.adv = io->adv; g.ret = io->ret; g.val = io->val;
     g.idx = io->idx; g.adv_part = io->adv_part; g.clip = io->clip_coef; g.vf_coef = io->vf_coef;
     g.workspace = io->workspace; g.workspace_bytes = (size_t)io->workspace_bytes;
-    g.flat_grad = io->flat_grad; g.kl_sum = io->kl_sum;
+    g.flat_grad = io->flat_grad; g.kl_sum = io->kl_sum; g.kl_sum_f32 = io->kl_sum_f32;
     const int rc = launch_ppo_minibatch_grad(g, (cudaStream_t)stream);
     if (rc) snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_minibatch_grad: %s",
                      rc == 3 ? "workspace too small" : rc == 2 ? "unsupported shape" : cudaGetErrorString(cudaGetLastError()));
@@ -698,7 +698,7 @@ int rk_ppo_adam_step(const rk_adam_io* io, void* stream) {
     }
     a.flat_grad = io->flat_grad; a.lr = io->lr;
     a.beta1 = io->beta1; a.beta2 = io->beta2; a.eps = io->eps; a.max_norm = io->max_grad_norm; a.kl_target = io->kl_target;
-    a.world = io->world; a.kl_sum = io->kl_sum; a.n_global = io->n_global; a.state = io->state; a.kl_at_stop = io->kl_at_stop;
+    a.world = io->world; a.kl_sum = io->kl_sum; a.kl_sum_f32 = io->kl_sum_f32; a.n_global = io->n_global; a.state = io->state; a.kl_at_stop = io->kl_at_stop;
     if (launch_clip_adam(a, (cudaStream_t)stream)) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adam_step: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kNT, 2) ppo_mlp_grad_kernel(const GradArgs g) 
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const float* __restrict__ partial,
                                                               const double* __restrict__ kl_partial, int ncta, int n_actor,
                                                               int n_total, float* __restrict__ flat_grad,
-                                                              double* __restrict__ kl_sum) {
+                                                              double* __restrict__ kl_sum, float* __restrict__ kl_sum_f32) {
     __shared__ float part[4][64];
     const int lane64 = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int q = blockIdx.x * 64 + lane64;
@@ -465,7 +465,10 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const float* __res
         double sk = 0.0;
         for (int c = threadIdx.x; c < ncta; c += 32) sk += kl_partial[c];
         for (int m = 16; m > 0; m >>= 1) sk += __shfl_xor_sync(0xffffffffu, sk, m);
-        if (threadIdx.x == 0) *kl_sum = sk;
+        if (threadIdx.x == 0) {
+            *kl_sum = sk;
+            if (kl_sum_f32) *kl_sum_f32 = (float)sk;
+        }
     }
 }
 
@@ -542,6 +545,7 @@ struct AdamArgs {
     float beta1, beta2, eps, max_norm, kl_target;
     int world;
     const double* kl_sum;
+    const float* kl_sum_f32;  // if set, used instead (it travelled through the gradient's all-reduce)
     double n_global;
     int* state;        // [0] stopped, [1] optimizer steps applied since the host cleared it, [2] scratch counter
     float* kl_at_stop;
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(const AdamArgs a) {
     __shared__ float s_clip;
     const int tid = threadIdx.x;
     if (a.state[0]) return;
-    const double approx_kl = *a.kl_sum / a.n_global;
+    const double approx_kl = (a.kl_sum_f32 ? (double)*a.kl_sum_f32 : *a.kl_sum) / a.n_global;
     if (approx_kl > (double)a.kl_target) {
         if (blockIdx.x == 0 && tid == 0) { *a.kl_at_stop = (float)approx_kl; }
         // state[0] is latched by the LAST block to pass here, so that no block of this launch reads the flag set
@@ -668,7 +672,7 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     const int n_actor = kH * io.obs_dim + kH + kH * kH + kH + 2 * kH + 2;
     const int n_total = n_actor + kH * io.obs_dim + kH + kH * kH + kH + kH + 1;
     ppo_grad_reduce_kernel<<<(n_total + 63) / 64, 256, 0, stream>>>(g.partial, g.kl_partial, ncta, n_actor, n_total,
-                                                                       io.flat_grad, io.kl_sum);
+                                                                       io.flat_grad, io.kl_sum, io.kl_sum_f32);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
@@ -684,7 +688,7 @@ int launch_clip_adam(const PpoAdamIO& io, cudaStream_t stream) {
     a.off[12] = off;
     a.grad = io.flat_grad; a.lr = io.lr;
     a.beta1 = io.beta1; a.beta2 = io.beta2; a.eps = io.eps; a.max_norm = io.max_norm; a.kl_target = io.kl_target;
-    a.world = io.world; a.kl_sum = io.kl_sum; a.n_global = io.n_global; a.state = io.state; a.kl_at_stop = io.kl_at_stop;
+    a.world = io.world; a.kl_sum = io.kl_sum; a.kl_sum_f32 = io.kl_sum_f32; a.n_global = io.n_global; a.state = io.state; a.kl_at_stop = io.kl_at_stop;
     clip_adam_kernel<<<(off + 255) / 256, 256, 0, stream>>>(a);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;

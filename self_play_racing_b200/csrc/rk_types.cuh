@@ -145,6 +145,7 @@ struct PpoGradIO {
     size_t workspace_bytes;
     float* flat_grad;
     double* kl_sum;
+    float* kl_sum_f32;
 };
 struct PpoAdamIO {
     float* params[12];
@@ -157,6 +158,7 @@ struct PpoAdamIO {
     float beta1, beta2, eps, max_norm, kl_target;
     int world;
     const double* kl_sum;
+    const float* kl_sum_f32;
     double n_global;
     int* state;
     float* kl_at_stop;
