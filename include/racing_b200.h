@@ -208,6 +208,16 @@ RK_API int rk_gae(const float* rewards, const float* values, const float* dones,
 RK_API int rk_policy_act(const float* params, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
                   uint64_t seed, uint64_t counter, float* action, int64_t act_stride,
                   float* logprob, float* value, float* mean, void* stream);
+/* The same against a POOL of stacked packed blocks (`pool_stride` floats apart, a multiple of 4):
+ * samples are split into consecutive blocks of `block_len` (a multiple of RK_POLICY_BLOCK) and block k
+ * is driven by policy block_policy[k] (device int32 [ceil(B / block_len)]).  One launch plays every
+ * environment against its own snapshot of SelfPlayPPO's opponent pool (self_play_ppo.py:12,40-44) --
+ * a superset of the reference's one-opponent-per-update rule. */
+#define RK_POLICY_BLOCK 256
+RK_API int rk_policy_act_pool(const float* params_pool, int64_t pool_stride, const int32_t* block_policy,
+                              int32_t block_len, int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B,
+                              uint64_t seed, uint64_t counter, float* action, int64_t act_stride,
+                              float* logprob, float* value, float* mean, void* stream);
 /* number of float32 values in the packed Agent block for a given obs_dim (action_dim = 2) */
 RK_API int rk_policy_param_count(int32_t obs_dim);
 

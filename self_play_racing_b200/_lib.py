@@ -98,6 +98,9 @@ SIGNATURES = {
     'rk_ppo_adv_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'rk_ppo_grad_workspace_bytes': (C.c_uint64, []),
     'rk_ppo_minibatch_grad': (C.c_int, [C.POINTER(RkPpoGradIO), C.c_void_p]),
+    'rk_policy_act_pool': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                     C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     'rk_random_permutation': (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p]),
     'rk_ppo_adam_step': (C.c_int, [C.POINTER(RkAdamIO), C.c_void_p]),
     'rk_ppo_loss_grad': (C.c_int, [C.c_void_p] * 10 + [C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,

@@ -53,8 +53,14 @@ class SelfPlayPPO(PPO):
         starts from fresh start-line states while the learner's carried
         next_obs stays stale for step 0 -- reproduced by
         resetting the batch without touching the rollout buffer's slot 0."""
-        self.curr_opponent = self.select_opponent()
-        self.envs.set_opponent(self.curr_opponent)
+        if self.config.get('opponents_per_update', 'one') == 'pool' and len(self.opponent_pool) > 1:
+            # superset of the reference (SURVEY 8f.2): every block of 256 envs draws its own pool member,
+            # all of them served by one inference launch
+            self.curr_opponent = self.opponent_pool[-1]
+            self.envs.set_opponents(self.opponent_pool, seed=int(np.random.randint(0, 2 ** 31 - 1)))
+        else:
+            self.curr_opponent = self.select_opponent()
+            self.envs.set_opponent(self.curr_opponent)
         self.envs.reset_device()
 
     def load_checkpoint(self, checkpoint_path):

@@ -279,6 +279,26 @@ def policy_act(params, obs, action_out, seed, counter, logprob=None, value=None,
                                  stream), None, 'rk_policy_act')
 
 
+POLICY_BLOCK = 256   # RK_POLICY_BLOCK
+
+
+def policy_act_pool(params_pool, block_policy, block_len, obs, action_out, seed, counter, logprob=None, value=None,
+                    mean=None):
+    """policy_act against a pool: params_pool [P, n_packed] (rows = flatten_agent blocks, row stride
+    a multiple of 4 floats), block_policy int32 [ceil(B / block_len)] = pool row driving each block of
+    `block_len` consecutive samples (a multiple of POLICY_BLOCK)."""
+    lib = _lib.load()
+    B = action_out.shape[0]
+    assert action_out.stride(-1) == 1 and obs.stride(-1) == 1 and obs.dtype == torch.float32
+    assert params_pool.dim() == 2 and params_pool.stride(1) == 1 and block_policy.dtype == torch.int32
+    assert block_policy.numel() * block_len >= B
+    stream = C.c_void_p(torch.cuda.current_stream(action_out.device).cuda_stream)
+    _lib.check(lib.rk_policy_act_pool(_ptr(params_pool), params_pool.stride(0), _ptr(block_policy), int(block_len),
+                                      obs.shape[-1], _ptr(obs), obs.stride(0), B, int(seed), int(counter),
+                                      _ptr(action_out), action_out.stride(0), _ptr(logprob), _ptr(value), _ptr(mean),
+                                      stream), None, 'rk_policy_act_pool')
+
+
 def gather_minibatch(idx, src, dst):
     """dst[k] = src[idx[k]] for the six per-sample arrays of a PPO minibatch, one
     launch.  src/dst: (obs [.,D], actions [.,2], logprobs, advantages, returns,

@@ -638,6 +638,26 @@ int rk_ppo_loss_grad(const float* mu, const float* v, const float* act, const fl
                                 vf_coef, dmu, dv, kl_sum, (cudaStream_t)stream);
 }
 
+int rk_policy_act_pool(const float* params_pool, int64_t pool_stride, const int32_t* block_policy, int32_t block_len,
+                       int32_t obs_dim, const float* obs, int64_t obs_stride, int32_t B, uint64_t seed,
+                       uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value, float* mean,
+                       void* stream) {
+    if (!params_pool || !block_policy || !action || !obs || B < 0 || obs_dim <= 0 || obs_dim > 256 || block_len <= 0 ||
+        block_len % RK_POLICY_BLOCK != 0 || pool_stride < rk_policy_param_count(obs_dim) || (pool_stride & 3) != 0) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "rk_policy_act_pool: invalid arguments (block_len must be a multiple of %d, pool_stride a multiple "
+                 "of 4 and >= rk_policy_param_count)", RK_POLICY_BLOCK);
+        return 1;
+    }
+    if (launch_policy_act(params_pool, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value,
+                          mean, (cudaStream_t)stream, block_policy, block_len, pool_stride)) {
+        snprintf(g_create_err, sizeof(g_create_err), "rk_policy_act_pool: launch failed: %s",
+                 cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
 int rk_ppo_adv_stats(const int64_t* idx, const float* adv, int32_t n, double* part, void* stream) {
     if (!adv || !part || n <= 0) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_adv_stats: invalid arguments");

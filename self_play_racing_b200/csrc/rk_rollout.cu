@@ -120,8 +120,12 @@ __device__ __forceinline__ void stage_obs(float* xs, const float* __restrict__ o
 __global__ void __launch_bounds__(kPolicyThreads, 2)
 policy_act_kernel(const float* __restrict__ params, int obs_dim, const float* __restrict__ obs, int64_t obs_stride,
                   int B, uint64_t seed, uint64_t counter, float* __restrict__ action, int64_t act_stride,
-                  float* __restrict__ logprob, float* __restrict__ value, float* __restrict__ mean) {
+                  float* __restrict__ logprob, float* __restrict__ value, float* __restrict__ mean,
+                  const int32_t* __restrict__ block_policy, int block_len, int64_t pool_stride) {
     extern __shared__ __align__(128) float sm[];
+    // a pool of stacked parameter blocks: this CTA's samples all belong to one block of `block_len` samples,
+    // whose policy id selects the block it stages (self-play against several snapshots in one launch)
+    if (block_policy != nullptr) params += (int64_t)block_policy[(blockIdx.x * kPolicyCols) / block_len] * pool_stride;
     __shared__ __align__(8) unsigned long long bar;
     const int n_packed = policy_packed_floats(obs_dim);
     const int n0 = obs_dim * kHidden;
@@ -341,7 +345,8 @@ int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, cons
 
 int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B, uint64_t seed,
                       uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
-                      float* mean, cudaStream_t stream) {
+                      float* mean, cudaStream_t stream, const int32_t* block_policy, int block_len,
+                      int64_t pool_stride) {
     if (B <= 0) return 0;
     if (params == nullptr) {
         random_act_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, seed, counter, action, act_stride);
@@ -349,6 +354,7 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
     if ((reinterpret_cast<uintptr_t>(params) & 15u) != 0) return 2;  // the bulk copy needs a 16-byte aligned source
+    if (block_policy != nullptr && (block_len <= 0 || block_len % kPolicyCols != 0 || (pool_stride & 3) != 0)) return 2;
     const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -356,7 +362,8 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
         attr_set = true;
     }
     policy_act_kernel<<<(B + kPolicyCols - 1) / kPolicyCols, kPolicyThreads, smem, stream>>>(
-        params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean);
+        params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean, block_policy,
+        block_len, pool_stride);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -120,7 +120,8 @@ int launch_gae(const float* rewards, const float* values, const float* dones, co
                cudaStream_t stream);
 int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B,
                       uint64_t seed, uint64_t counter, float* action, int64_t act_stride, float* logprob,
-                      float* value, float* mean, cudaStream_t stream);
+                      float* value, float* mean, cudaStream_t stream, const int32_t* block_policy = nullptr,
+                      int block_len = 0, int64_t pool_stride = 0);
 int policy_param_count(int obs_dim);
 int launch_gather_minibatch(const int64_t* idx, int n, int obs_dim, const float* obs, const float* act,
                             const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from .. import spaces
-from ..backend import RacingBackend, flatten_agent, policy_act
+from ..backend import RacingBackend, flatten_agent, policy_act, policy_act_pool
 from .multi_racing_env import MultiRacingEnv
 from .racing_env import RacingEnv
 from .track import Track
@@ -136,6 +136,7 @@ class BatchedRacingVecEnv:
         E, D = self.num_envs, be.D
         self.seed = int(seed)
         self._opp_params = None     # flattened frozen opponent (device float32) or None -> random
+        self._opp_pool = None       # (stacked params [P, n], block -> pool row, block length) after set_opponents
         self._opp_counter = 0
         self._obs_cur = be.obs
         self._tracks = {}
@@ -197,6 +198,7 @@ class BatchedRacingVecEnv:
         """SelfPlayWrapper.set_opponent for every environment at once.  Accepts
         an Agent module, a state_dict, an already flattened parameter vector, or
         None (uniform random opponent, wrappers.py:30-32)."""
+        self._opp_pool = None
         if opponent_policy is None:
             self._opp_params = None
             return
@@ -206,6 +208,30 @@ class BatchedRacingVecEnv:
             sd = opponent_policy.state_dict() if hasattr(opponent_policy, 'state_dict') else opponent_policy
             flat = flatten_agent(sd)
         self._opp_params = flat.to(self.be.device, torch.float32).contiguous()
+
+    def set_opponents(self, policies, block_policy=None, block_len=256, seed=None):
+        """Several frozen opponents at once (a superset of the reference's one
+        opponent per update): the environments are split into blocks
+        of `block_len` consecutive envs and block k plays against
+        policies[block_policy[k]] (default: drawn uniformly, as select_opponent
+        does per update, self_play_ppo.py:40-44).  One inference launch serves
+        all of them (rk_policy_act_pool)."""
+        flats = []
+        for pol in policies:
+            if isinstance(pol, torch.Tensor):
+                flats.append(pol)
+            else:
+                flats.append(flatten_agent(pol.state_dict() if hasattr(pol, 'state_dict') else pol))
+        pool = torch.stack([f.to(self.be.device, torch.float32) for f in flats]).contiguous()
+        n_blocks = (self.num_envs + block_len - 1) // block_len
+        if block_policy is None:
+            rs = np.random.RandomState(self.seed if seed is None else seed)
+            block_policy = rs.randint(0, len(flats), size=n_blocks)
+        block_policy = torch.as_tensor(np.asarray(block_policy, dtype=np.int32)).to(self.be.device)
+        if block_policy.numel() != n_blocks or int(block_policy.max()) >= len(flats) or int(block_policy.min()) < 0:
+            raise ValueError('set_opponents: block_policy needs one valid pool index per block of envs')
+        self._opp_params = pool[0]
+        self._opp_pool = (pool, block_policy, int(block_len))
 
     # ---- device face -------------------------------------------------------------
     @property
@@ -225,6 +251,11 @@ class BatchedRacingVecEnv:
         obs = be.obs if obs is None else obs
         actions = be.actions if actions is None else actions
         self._opp_counter += 1
+        if getattr(self, '_opp_pool', None) is not None:
+            pool, block_policy, block_len = self._opp_pool
+            policy_act_pool(pool, block_policy, block_len, obs[1], actions[1], seed=self.seed ^ 0x5eed0bb,
+                            counter=self._opp_counter)
+            return
         policy_act(self._opp_params, obs[1] if self._opp_params is not None else None, actions[1],
                    seed=self.seed ^ 0x5eed0bb, counter=self._opp_counter)
 
@@ -272,9 +303,9 @@ class BatchedRacingVecEnv:
         step; by default they come from the backend's Philox stream."""
         be = self.be
         self._h_actions.numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
-        if self.host_chunks > 0:
+        if self.host_chunks > 0 and getattr(self, '_opp_pool', None) is None:
             self._step_host(start_slot)
-        elif self.pipeline_chunks > 1 and start_slot is None:
+        elif self.pipeline_chunks > 1 and start_slot is None and getattr(self, '_opp_pool', None) is None:
             self._step_pipelined()
         else:
             be.actions[0].copy_(self._h_actions, non_blocking=True)

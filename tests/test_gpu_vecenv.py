@@ -335,6 +335,54 @@ def test_device_permutation_is_a_permutation(pkg, n):
         assert abs(float((x * y).mean()) * 12) < 0.2 if n < 1000 else abs(float((x * y).mean()) * 12) < 0.05
 
 
+def test_opponent_pool_one_launch_equals_per_opponent_launches(pkg):
+    """rk_policy_act_pool: blocks of 256 envs driven by different pool members in ONE
+    launch give exactly the actions of one rk_policy_act launch per member on its blocks;
+    BatchedRacingVecEnv.set_opponents routes the self-play step through it."""
+    env_mod, agent_mod, _ = pkg
+    from self_play_racing_b200 import spaces
+    from self_play_racing_b200.backend import flatten_agent, policy_act, policy_act_pool
+    torch.manual_seed(5)
+    agents = [agent_mod.Agent(spaces.Box(-1, 1, (19,)), spaces.Box(-1, 1, (2,))).cuda() for _ in range(3)]
+    for a in agents:
+        with torch.no_grad():
+            for p in a.parameters():
+                p.add_(0.3 * torch.randn_like(p))
+    flats = [flatten_agent(a.state_dict()).cuda() for a in agents]
+    pool = torch.stack(flats).contiguous()
+    B, block = 2000, 512            # 4 blocks, the last one ragged
+    ids = torch.tensor([2, 0, 1, 2], dtype=torch.int32, device='cuda')
+    obs = torch.rand(B, 19, device='cuda') * 2 - 1
+    out = torch.zeros(B, 2, device='cuda')
+    mean = torch.zeros(B, 2, device='cuda')
+    policy_act_pool(pool, ids, block, obs, out, seed=11, counter=3, mean=mean)
+    ref, ref_mean = torch.zeros_like(out), torch.zeros_like(mean)
+    for k in range(3):
+        full, fmean = torch.zeros_like(out), torch.zeros_like(mean)
+        policy_act(flats[k], obs, full, seed=11, counter=3, mean=fmean)
+        for b in range(4):
+            if int(ids[b]) == k:
+                ref[b * block:(b + 1) * block] = full[b * block:(b + 1) * block]
+                ref_mean[b * block:(b + 1) * block] = fmean[b * block:(b + 1) * block]
+    assert torch.equal(out, ref) and torch.equal(mean, ref_mean)
+    for k in range(3):   # and the means are the torch Agents' means
+        sel = torch.cat([torch.arange(b * block, min((b + 1) * block, B)) for b in range(4) if int(ids[b]) == k]).cuda()
+        with torch.no_grad():
+            mu = agents[k].actor_mu(obs[sel])
+        torch.testing.assert_close(mean[sel], mu, rtol=0, atol=2e-6)
+    # through the vector env: the opponent's actions differ between blocks with different members
+    vec = env_mod.BatchedRacingVecEnv.synthetic('multi', 1024, n_tracks=4, num_agents=2, selfplay=True, seed=0)
+    vec.set_opponents(agents, block_policy=[0, 1, 2, 0], block_len=256)
+    vec.reset()
+    o, r, te, tr, _ = vec.step(np.zeros((1024, 2), dtype=np.float32))
+    assert o.shape == (1024, 19) and np.isfinite(o).all()
+    act1 = vec.be.actions[1].cpu().numpy()
+    assert not np.allclose(act1[:256], act1[256:512])
+    with pytest.raises(ValueError):
+        vec.set_opponents(agents, block_policy=[0, 1, 5, 0], block_len=256)
+    vec.close()
+
+
 def test_batched_evaluation_protocol(pkg):
     """evaluate.py's tracks x runs protocol as one batch: result keys of
     evaluate.py:51-64 / utils/metrics.py, reproducible, and -- with a (nearly)
