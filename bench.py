@@ -217,6 +217,34 @@ def time_ppo(args, wl, vec, dev, rank, world):
         torch.cuda.synchronize(dev)
         if it > 0:
             times.append((e0.elapsed_time(e1), e1.elapsed_time(e2), steps))
+    # the update's dominant kernel on its own: rk_ppo_minibatch_grad over the trainer's padded observation
+    # buffer, CUDA events on the launching stream, L2 flushed between calls
+    grad_kernel = None
+    g = getattr(trainer, '_graphed', None)
+    if g is not None and getattr(g, 'fused_mlp', False) and getattr(g, 'obs_pad', None) is not None:
+        n_rows, mb = g.obs_pad.shape[0], g.mb
+        D = buf['obs'].shape[-1]
+        gen = torch.Generator(device=dev).manual_seed(0)
+        act = torch.rand(n_rows, 2, device=dev, generator=gen) * 2 - 1
+        lp, adv, ret, val = (torch.randn(n_rows, device=dev, generator=gen) for _ in range(4))
+        perm = torch.randperm(n_rows, device=dev, generator=gen)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = [(ev(), ev()) for _ in range(min(16, n_rows // mb))]
+        for rep in range(2):
+            for k, (a, b) in enumerate(evs):
+                idx = perm[k * mb:(k + 1) * mb]
+                flush.zero_()
+                g.grad.stats(idx, adv)
+                a.record()
+                g.grad(idx, g.obs_pad[:, :D], act, lp, adv, ret, val)
+                b.record()
+            torch.cuda.synchronize(dev)
+        us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2]
+        fma_per_row = 2 * (2 * D * 64 + 3 * 64 * 64)   # both networks: forward 2 products, backward dH1 + dW2 + dW1
+        grad_kernel = {'kernel': 'rk::ppo_mlp_grad_kernel + rk::ppo_grad_reduce_kernel', 'rows_per_minibatch': mb,
+                       'us_per_minibatch': us, 'fma_per_row': fma_per_row,
+                       'tflops': 2.0 * fma_per_row * mb / (us * 1e-6) / 1e12}
+        del flush
     roll = float(np.mean([t[0] for t in times]))
     upd = float(np.mean([t[1] for t in times]))
     tot = torch.tensor([roll + upd], dtype=torch.float64, device=dev)
@@ -228,7 +256,7 @@ def time_ppo(args, wl, vec, dev, rank, world):
             'update_epochs': cfg['update_epochs'], 'num_minibatches': cfg['num_minibatches'],
             'kl_early_stop': 'disabled for timing', 'opponent_pool': cfg['pool_size'],
             'update_matmul_precision': args.ppo_precision,
-            'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3)}
+            'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3), 'grad_kernel': grad_kernel}
 
 
 def fp_peaks(torch, dev):
@@ -421,6 +449,8 @@ def main():
                            'effective_tflops': flops_step / (kms * 1e-3) / 1e12, 'measured_peaks': fp}
         if fp and fp.get('fp32_tflops'):
             roof['fp_pipe']['frac_of_fp32_peak'] = roof['fp_pipe']['effective_tflops'] / fp['fp32_tflops']
+        if ppo and ppo.get('grad_kernel') and fp and fp.get('fp32_tflops'):
+            ppo['grad_kernel']['frac_of_fp32_peak'] = ppo['grad_kernel']['tflops'] / fp['fp32_tflops']
         line = {'metric': 'agent_env_steps_per_sec', 'value': agent_steps * args.steps * world / (total_ms_max * 1e-3),
                 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': total_ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
