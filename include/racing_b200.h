@@ -314,8 +314,8 @@ RK_API int rk_ppo_adam_step(const rk_adam_io* io, void* stream);
 RK_API int rk_random_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, void* stream);
 
 /* ---- measurement aid --------------------------------------------------------- */
-/* Sustained FMA throughput of the current device in TFLOP/s (fp32, or fp64 when
- * use_fp64 != 0): the non-tensor roofline denominator bench.py reports the step
+/* Sustained FMA throughput of the current device in TFLOP/s (use_fp64 = 0: fp32 FFMA, 1: fp64 DFMA,
+ * 2: packed fp32 FFMA2, 3: legacy tensor path mma.sync m16n8k8 TF32): the non-tensor roofline denominator bench.py reports the step
  * kernel against (SURVEY.md 8d asks the builder to measure it). */
 RK_API double rk_fma_peak(int32_t use_fp64, int32_t iters);
 

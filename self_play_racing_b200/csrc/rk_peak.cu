@@ -46,8 +46,30 @@ __global__ void __launch_bounds__(256) fma2_chain_kernel(float* out, int iters, 
     if (s == 123456789.f) out[0] = s;
 }
 
+// legacy tensor-core path: mma.sync m16n8k8 TF32 -> FP32, 8 independent accumulator fragments per warp
+// (what a 3xTF32 version of the update's 64-wide products could draw on; measured, not assumed)
+__global__ void __launch_bounds__(256) mma_tf32_chain_kernel(float* out, int iters) {
+    float c[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) c[u][r] = (float)(threadIdx.x + u + r);
+    const unsigned a0 = 0x3f800000u, a1 = 0x3f000000u, a2 = 0x3e800000u, a3 = 0x3f400000u, b0 = 0x3f800000u, b1 = 0x3f000000u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[u][0]), "+f"(c[u][1]), "+f"(c[u][2]), "+f"(c[u][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += c[u][0] + c[u][1] + c[u][2] + c[u][3];
+    if (s == 123456789.f) out[0] = s;
+}
+
 template <typename T>
-double measure(int iters, bool packed = false) {
+double measure(int iters, bool packed = false, bool tensor = false) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -60,14 +82,16 @@ double measure(int iters, bool packed = false) {
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
-        if (packed) fma2_chain_kernel<<<grid, block>>>((float*)out, iters, 1.0000001f, 1e-7f);
+        if (tensor) mma_tf32_chain_kernel<<<grid, block>>>((float*)out, iters);
+        else if (packed) fma2_chain_kernel<<<grid, block>>>((float*)out, iters, 1.0000001f, 1e-7f);
         else fma_chain_kernel<T><<<grid, block>>>(out, iters, (T)1.0000001, (T)1e-7);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         count_launch();
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * block;
+        // per thread-iteration: 64 FMAs (scalar / packed chains) or 8 warp-wide m16n8k8 MMAs = 8 * 1024 / 32 FMAs
+        const double flops = 2.0 * (tensor ? 256.0 : 64.0) * (double)iters * (double)grid * block;
         if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0);
@@ -81,6 +105,7 @@ double measure(int iters, bool packed = false) {
 
 extern "C" RK_API double rk_fma_peak(int32_t use_fp64, int32_t iters) {
     if (iters <= 0) iters = 1024;
+    if (use_fp64 == 3) return rk::measure<float>(iters, false, true);  // mma.sync m16n8k8 TF32 (legacy tensor path)
     if (use_fp64 == 2) return rk::measure<float>(iters, true);  // packed fp32 (FFMA2), same 64 FMAs per thread-iteration
     return use_fp64 ? rk::measure<double>(iters) : rk::measure<float>(iters);
 }
