@@ -231,6 +231,29 @@ class PPO:
             return optim.Adam(self.agent.parameters(), lr=lr, eps=1e-5, capturable=True, fused=True)
         return optim.Adam(self.agent.parameters(), lr=c['learning_rate'], eps=1e-5)
 
+    def load_optimizer_state(self, state_dict):
+        """optimizer.load_state_dict that keeps the device-resident update valid: the loaded
+        state replaces the optimizer's tensors, so the cached graphs / kernel argument blocks
+        are dropped, and a checkpoint written by the reference (plain Adam: python-float lr,
+        non-capturable, `step` on the host) is converted to the capturable form used here."""
+        self.optimizer.load_state_dict(state_dict)
+        self._graphed = None
+        if self.device.type != 'cuda':
+            return
+        for group in self.optimizer.param_groups:
+            lr = group['lr']
+            group['lr'] = torch.tensor(float(lr), device=self.device) if not isinstance(lr, torch.Tensor) \
+                else lr.to(self.device, torch.float32).reshape(())
+            group['capturable'], group['fused'], group['foreach'] = True, True, False
+            for p in group['params']:
+                st = self.optimizer.state.get(p)
+                if st and 'step' in st:
+                    step = st['step']
+                    st['step'] = (step if isinstance(step, torch.Tensor) else torch.tensor(float(step))).to(
+                        self.device, torch.float32).reshape(())
+                    st['exp_avg'] = st['exp_avg'].to(self.device, torch.float32).contiguous()
+                    st['exp_avg_sq'] = st['exp_avg_sq'].to(self.device, torch.float32).contiguous()
+
     def _set_lr(self, value):
         g = self.optimizer.param_groups[0]
         if isinstance(g['lr'], torch.Tensor):

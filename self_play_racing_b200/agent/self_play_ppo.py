@@ -66,7 +66,7 @@ class SelfPlayPPO(PPO):
     def load_checkpoint(self, checkpoint_path):
         ck = torch.load(checkpoint_path, map_location=self.device, weights_only=False)
         self.agent.load_state_dict(ck['agent_state_dict'])
-        self.optimizer.load_state_dict(ck['optimizer_state_dict'])
+        self.load_optimizer_state(ck['optimizer_state_dict'])
         self.opponent_pool = []
         for sd in ck['opponent_pool']:
             opp = Agent(self.envs.single_observation_space, self.envs.single_action_space).to(self.device)

@@ -727,6 +727,7 @@ int rk_ppo_adam_step(const rk_adam_io* io, void* stream) {
 }
 
 int rk_random_permutation(uint64_t seed, uint64_t counter, int64_t n, int64_t* out, void* stream) {
+    if (n == 0) return 0;
     if (!out || n < 0 || n > ((int64_t)1 << 40)) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_random_permutation: invalid arguments");
         return 1;

@@ -453,6 +453,27 @@ def test_error_behaviour_through_the_abi(B):
         B.RacingBackend(8, kind='single', num_sensors=65)                     # RK_MAX_SENSORS = 64
     with pytest.raises(RuntimeError, match='invalid config'):
         B.RacingBackend(8, kind='multi', num_agents=9)                        # RK_MAX_AGENTS = 8
+    # update-path entry points
+    import ctypes as C
+    from self_play_racing_b200 import _lib
+    lib = _lib.load()
+    io = _lib.RkPpoGradIO()
+    io.struct_size = 8
+    assert lib.rk_ppo_minibatch_grad(C.byref(io), None) != 0 and b'struct_size' in lib.rk_last_error(None)
+    io.struct_size = C.sizeof(_lib.RkPpoGradIO)
+    io.obs_dim, io.n = 21, 128                                                # RK_PPO_MAX_OBS_DIM = 20
+    assert lib.rk_ppo_minibatch_grad(C.byref(io), None) != 0 and b'obs_dim' in lib.rk_last_error(None)
+    ad = _lib.RkAdamIO()
+    ad.struct_size = C.sizeof(_lib.RkAdamIO)
+    assert lib.rk_ppo_adam_step(C.byref(ad), None) != 0 and b'invalid arguments' in lib.rk_last_error(None)
+    out = torch.zeros(300, 2, device='cuda')
+    with pytest.raises(RuntimeError, match='multiple of 256'):
+        B.policy_act_pool(torch.zeros(2, 11080, device='cuda'), torch.zeros(3, dtype=torch.int32, device='cuda'), 100,
+                          torch.zeros(300, 19, device='cuda'), out, seed=1, counter=1)
+    assert B.random_permutation(0, 1, 1, device='cuda').numel() == 0          # empty input is not an error
+    with pytest.raises(RuntimeError, match='invalid arguments'):
+        lib_rc = lib.rk_random_permutation(1, 1, 5, None, None)
+        _lib.check(lib_rc, None, 'rk_random_permutation')
 
 
 def test_extreme_track_shapes(B):

@@ -192,6 +192,49 @@ def test_selfplay_ppo_runs_on_device(pkg, tmp_path):
     t2.envs.close()
 
 
+def test_reference_style_checkpoint_resumes_on_device(pkg, tmp_path):
+    """A checkpoint as the reference writes it (self_play_ppo.py:155-166: plain torch Adam --
+    python-float lr, non-capturable, host `step`) loads into the CUDA trainer, the
+    device-resident update keeps working on the loaded optimizer state, and the state
+    written back has the reference's layout."""
+    env_mod, agent_mod, configs = pkg
+    cfg = configs.self_play_config(num_envs=256, num_steps=16, total_timesteps=256 * 16 * 2, update_epochs=2,
+                                   num_minibatches=2, snapshot_freq=1, pool_size=2)
+    vec = env_mod.BatchedRacingVecEnv.synthetic('multi', 256, n_tracks=4, num_agents=2, selfplay=True, seed=0)
+    tr = agent_mod.SelfPlayPPO(vec, cfg, device='cuda')
+    # reference-style optimizer state: CPU agent, plain Adam, three steps
+    ref_agent = agent_mod.Agent(vec.single_observation_space, vec.single_action_space)
+    ref_opt = torch.optim.Adam(ref_agent.parameters(), lr=2.5e-4, eps=1e-5)
+    for _ in range(3):
+        ref_opt.zero_grad()
+        _, lp, _, v = ref_agent.get_action_and_value(torch.rand(32, 19) * 2 - 1)
+        (lp.mean() + v.mean()).backward()
+        ref_opt.step()
+    path = tmp_path / 'ref_style.pth'
+    torch.save({'update': 7, 'global_step': 7 * 256 * 16, 'agent_state_dict': ref_agent.state_dict(),
+                'optimizer_state_dict': ref_opt.state_dict(), 'opponent_pool': [ref_agent.state_dict()],
+                'config': cfg, 'training_info': {'steps': [], 'rewards': [], 'opponent_pool_size': []}}, path)
+    upd, gstep, _ = tr.load_checkpoint(str(path))
+    assert (upd, gstep) == (7, 7 * 256 * 16) and len(tr.opponent_pool) == 1
+    p0 = next(tr.agent.parameters())
+    st = tr.optimizer.state[p0]
+    assert st['step'].is_cuda and float(st['step']) == 3.0 and st['exp_avg'].is_cuda
+    assert isinstance(tr.optimizer.param_groups[0]['lr'], torch.Tensor) and tr.optimizer.param_groups[0]['lr'].is_cuda
+    buf = tr.alloc_buffers()
+    buf['obs'][0].copy_(tr._reset_all())
+    tr.update_opponent()
+    tr._anneal(7, 100)
+    tr.collect_rollout(buf)
+    before = p0.detach().clone()
+    steps = tr._learn_from(buf)
+    assert steps == 4 and tr._graphed.fused_mlp and tr._graphed.adam is not None
+    assert float(tr.optimizer.state[p0]['step']) == 7.0            # the kernel advanced torch's own step tensors
+    assert not torch.equal(before, p0)
+    sd = tr.optimizer.state_dict()
+    assert set(sd['state'][0]) >= {'step', 'exp_avg', 'exp_avg_sq'} and len(sd['state']) == 12
+    vec.close()
+
+
 def test_single_ppo_learns_something(pkg):
     """A short single-agent PPO run: mean episode return improves over the
     first updates (a sanity check of rollout/GAE/update wiring, not a claim)."""
