@@ -277,6 +277,9 @@ typedef struct rk_ppo_grad_io {
     double* kl_sum;            /* out: sum over the n rows of (logp_old - logp_new)  (ppo.py:178-182) */
     float* kl_sum_f32;         /* optional out: the same as float32 -- e.g. the slot right after flat_grad, so
                                 * that ONE all-reduce carries the gradient and the KL sum across ranks */
+    int32_t tensor_cores;      /* 0: fp32 FMA kernel; 1: the per-sample products on tcgen05 tensor cores (TF32 x 3
+                                * split, fp32-grade accuracy, accumulators and chained operands in TMEM) */
+    int32_t reserved1;
 } rk_ppo_grad_io;
 RK_API uint64_t rk_ppo_grad_workspace_bytes(void);
 RK_API int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream);

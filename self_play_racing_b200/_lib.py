@@ -47,7 +47,7 @@ class RkPpoGradIO(C.Structure):
                 ('ret', C.c_void_p), ('val', C.c_void_p), ('idx', C.c_void_p), ('adv_part', C.c_void_p),
                 ('clip_coef', C.c_float), ('vf_coef', C.c_float), ('workspace', C.c_void_p),
                 ('workspace_bytes', C.c_uint64), ('flat_grad', C.c_void_p), ('kl_sum', C.c_void_p),
-                ('kl_sum_f32', C.c_void_p)]
+                ('kl_sum_f32', C.c_void_p), ('tensor_cores', C.c_int32), ('reserved1', C.c_int32)]
 
 
 class RkAdamIO(C.Structure):

@@ -340,7 +340,7 @@ class PpoMinibatchGrad:
     flat gradient; `params` are the twelve weight/bias tensors in
     `Agent.parameters()` order (actor_mu.{0,2,4}, critic.{0,2,4}), read in place."""
 
-    def __init__(self, params, log_std, obs_dim, clip_coef, vf_coef):
+    def __init__(self, params, log_std, obs_dim, clip_coef, vf_coef, tensor_cores=False):
         lib = _lib.load()
         params = list(params)
         if len(params) != 12 or obs_dim > PPO_MAX_OBS_DIM:
@@ -370,6 +370,7 @@ class PpoMinibatchGrad:
         io.workspace, io.workspace_bytes = self.workspace.data_ptr(), nbytes
         io.flat_grad, io.kl_sum = self.flat_grad.data_ptr(), self.kl_sum.data_ptr()
         io.kl_sum_f32 = self.kl_f32.data_ptr()
+        io.tensor_cores = 1 if tensor_cores else 0
         self.io = io
 
     def grad_views(self):

@@ -692,7 +692,7 @@ int rk_ppo_minibatch_grad(const rk_ppo_grad_io* io, void* stream) {
     g.obs = io->obs; g.act = io->act; g.old_logp = io->old_logp; g.adv = io->adv; g.ret = io->ret; g.val = io->val;
     g.idx = io->idx; g.adv_part = io->adv_part; g.clip = io->clip_coef; g.vf_coef = io->vf_coef;
     g.workspace = io->workspace; g.workspace_bytes = (size_t)io->workspace_bytes;
-    g.flat_grad = io->flat_grad; g.kl_sum = io->kl_sum; g.kl_sum_f32 = io->kl_sum_f32;
+    g.flat_grad = io->flat_grad; g.kl_sum = io->kl_sum; g.kl_sum_f32 = io->kl_sum_f32; g.tensor_cores = io->tensor_cores;
     const int rc = launch_ppo_minibatch_grad(g, (cudaStream_t)stream);
     if (rc) snprintf(g_create_err, sizeof(g_create_err), "rk_ppo_minibatch_grad: %s",
                      rc == 3 ? "workspace too small" : rc == 2 ? "unsupported shape" : cudaGetErrorString(cudaGetLastError()));

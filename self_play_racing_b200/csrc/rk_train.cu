@@ -436,6 +436,437 @@ __global__ void __launch_bounds__(kNT, 2) ppo_mlp_grad_kernel(const GradArgs g) 
     else net_body<1>(g, g.net[1], train_smem);
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant (opt-in): the three per-sample products of a tile -- layer 1, layer 2 and
+// dH1 = dZ2 . W2 -- run on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM)
+// as a chain THROUGH tensor memory: thread t owns sample t = TMEM lane t; it reads its accumulator row
+// with tcgen05.ld, applies bias / tanh / the loss gradient, and writes the row back with tcgen05.st as
+// the A operand of the next product (A comes from TMEM, B = the weights in shared memory in the K-major
+// core-matrix layout).  fp32 accuracy is kept with the 3-pass split x = hi + lo (both exactly
+// representable in TF32): A.B ~ Ah.Bh + Ah.Bl + Al.Bh, accumulated in fp32.  The weight-gradient
+// accumulations stay on the CUDA cores (their operands are needed feature-major) and read
+// the same plain [feature][sample] tiles as the FFMA kernel, now written by the thread-per-sample epilogues.
+// Building blocks verified stand-alone in tools/umma_selftest.cu.
+// ---------------------------------------------------------------------------
+constexpr int kTmemCols = 512;
+constexpr int kColAcc0 = 0, kColAcc1 = 64, kColXh = 128, kColXl = 160, kColHh = 192, kColHl = 256, kColZh = 320, kColZl = 384;
+constexpr int kXK = 24;  // layer-1 reduction length padded to a multiple of the MMA K (8)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major no-swizzle operand tile [rows][F features]: 8-row x 16-byte core matrices, feature cores contiguous
+__device__ __forceinline__ int umma_off(int r, int f, int F) { return ((r >> 3) * (F >> 2) + (f >> 2)) * 32 + (r & 7) * 4 + (f & 3); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    const float h = tf32_rn(x);
+    hi = __float_as_uint(h);
+    lo = __float_as_uint(tf32_rn(x - h));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// D[128 x 64] (+)= A[128 x K] . B[64 x K]^T, 3-pass split; A hi/lo in TMEM columns, B hi/lo K-major tiles in smem
+__device__ __forceinline__ void issue_product(uint32_t tmem, int colD, int colAh, int colAl, const float* Bh, const float* Bl,
+                                              int K, unsigned long long* bar) {
+    // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kH >> 3) << 17) | ((uint32_t)(kTS >> 4) << 24);
+    const uint32_t sbo = (uint32_t)(K >> 2) * 128u;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int colA = (pass == 2) ? colAl : colAh;
+        const uint32_t b = smem_u32((pass == 1) ? Bl : Bh);
+        for (int kb = 0; kb < (K >> 3); ++kb) {
+            const uint64_t db = umma_desc(b + kb * 256, 128, sbo);
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                         ::"r"(tmem + colD), "r"(tmem + colA + kb * 8), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            acc = 1;
+        }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait_product(unsigned long long* bar, unsigned& phase) {
+    unsigned done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(phase) : "memory");
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// publish this thread's tcgen05.st writes to the thread that issues the next MMA
+__device__ __forceinline__ void tmem_publish_and_sync() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+template <int OUT>
+__device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P, float* smem) {
+    constexpr bool kActor = OUT == 2;
+    const int tid = threadIdx.x, warp = tid >> 5, D = g.D;
+    // shared-memory carve-up: operand tiles of the tensor-core products first (16-byte aligned core matrices)
+    float* W1h = smem;                      // [64][kXK]  B of layer 1 (K-major, rows = output j)
+    float* W1l = W1h + kH * kXK;
+    float* W2h = W1l + kH * kXK;            // [64][64]   B of layer 2: rows = output j, k = input i
+    float* W2l = W2h + kH * kH;
+    float* W2th = W2l + kH * kH;            // [64][64]   B of dH1: rows = input i, k = output j
+    float* W2tl = W2th + kH * kH;
+    float* sb1 = W2tl + kH * kH;            // [64]
+    float* sb2 = sb1 + kH;                  // [64]
+    float* sW3 = sb2 + kH;                  // [OUT][64]
+    float* X = sW3 + 2 * kH;                // [kMaxD][kLD]  plain feature-major tiles of the CUDA-core phases
+    float* H1 = X + kMaxD * kLD;            // [64][kLD]  h1, then dz1
+    float* H2 = H1 + kH * kLD;              // [64][kLD]  h2, then dz2
+    float* DO = H2 + kH * kLD;              // [2][kLD]
+    float* red = DO + 2 * kLD;              // [16]
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+
+    for (int q = tid; q < kH * kXK; q += kNT) {
+        const int j = q / kXK, i = q - j * kXK;
+        uint32_t hi = 0, lo = 0;
+        if (i < D) split_tf32(P.W1[j * D + i], hi, lo);
+        W1h[umma_off(j, i, kXK)] = __uint_as_float(hi);
+        W1l[umma_off(j, i, kXK)] = __uint_as_float(lo);
+    }
+    for (int q = tid; q < kH * kH; q += kNT) {
+        const int j = q >> 6, i = q & 63;
+        uint32_t hi, lo;
+        split_tf32(P.W2[q], hi, lo);
+        W2h[umma_off(j, i, kH)] = __uint_as_float(hi); W2l[umma_off(j, i, kH)] = __uint_as_float(lo);
+        W2th[umma_off(i, j, kH)] = __uint_as_float(hi); W2tl[umma_off(i, j, kH)] = __uint_as_float(lo);
+    }
+    for (int q = tid; q < kH; q += kNT) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
+    for (int q = tid; q < OUT * kH; q += kNT) sW3[q] = P.W3[q];
+    for (int q = tid; q < kMaxD * kLD; q += kNT) X[q] = 0.f;
+    float b3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) b3[o] = P.b3[o];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the weight tiles are read by the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's quarter of the TMEM lanes
+    unsigned phase = 0;
+
+    float adv_mean = 0.f, adv_std = 1.f;
+    if (kActor) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int b = 0; b < kAdvBlocks; ++b) { s1 += g.adv_part[2 * b]; s2 += g.adv_part[2 * b + 1]; }
+        const double mean = s1 / g.n_global;
+        const double var = (s2 - g.n_global * mean * mean) / (g.n_global - 1.0);
+        adv_mean = (float)mean;
+        adv_std = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    const float ls0 = kActor ? g.log_std[0] : 0.f, ls1 = kActor ? g.log_std[1] : 0.f;
+
+    // accumulators of the CUDA-core weight-gradient phases (same roles as in net_body)
+    const int kg = tid >> 6, u = tid & 63, ti = u >> 3, tj = u & 7;
+    float gW2[8][8], gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        gb2[m] = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) gW2[m][n] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxD; ++i) gW1[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
+
+    const int ntiles = (g.n + kTS - 1) / kTS;
+    const bool vec_rows = (g.obs_stride & 3) == 0 && g.obs_stride >= ((D + 3) & ~3) &&
+                          (reinterpret_cast<uintptr_t>(g.obs) & 15u) == 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- gather: thread <-> sample; the row goes to the plain X tile (dW1) and, split, to TMEM (A of layer 1) ----
+        const int gi = tile * kTS + tid;
+        const bool valid = gi < g.n;
+        const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
+        {
+            const float* src = g.obs + row * g.obs_stride;
+#pragma unroll
+            for (int c0 = 0; c0 < kXK; c0 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int i = c0 + c;
+                    float v = 0.f;
+                    if (valid && i < D) v = (vec_rows || true) ? src[i] : 0.f;
+                    if (i < D) X[i * kLD + tid] = v;
+                    split_tf32(v, hi[c], lo[c]);
+                }
+                tmem_st8(lane_base + kColXh + c0, hi);
+                tmem_st8(lane_base + kColXl + c0, lo);
+            }
+        }
+        float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
+        if (valid) {
+            if (kActor) {
+                const float2 a = *reinterpret_cast<const float2*>(g.act + 2 * row);
+                d_a0 = a.x; d_a1 = a.y; d_lp = g.old_logp[row]; d_adv = g.adv[row];
+            } else {
+                d_ret = g.ret[row]; d_val = g.val[row];
+            }
+        }
+        tmem_publish_and_sync();
+        // ---- layer 1 on the tensor core: ACC0 = X W1^T ----
+        if (tid == 0) issue_product(tmem, kColAcc0, kColXh, kColXl, W1h, W1l, kXK, &bar);
+        wait_product(&bar, phase);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + kColAcc0 + c0, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 32; c8 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = c0 + c8 + c;
+                    const float h = tanh_fast(__uint_as_float(v[c8 + c]) + sb1[j]);
+                    H1[j * kLD + tid] = h;
+                    split_tf32(h, hi[c], lo[c]);
+                }
+                tmem_st8(lane_base + kColHh + c0 + c8, hi);
+                tmem_st8(lane_base + kColHl + c0 + c8, lo);
+            }
+        }
+        tmem_publish_and_sync();
+        // ---- layer 2: ACC1 = H1 W2^T ----
+        if (tid == 0) issue_product(tmem, kColAcc1, kColHh, kColHl, W2h, W2l, kH, &bar);
+        wait_product(&bar, phase);
+        float dpre[OUT];
+        {
+            float out[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) out[o] = b3[o];
+#pragma unroll 1
+            for (int c0 = 0; c0 < kH; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + kColAcc1 + c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int j = c0 + c;
+                    const float h = tanh_fast(__uint_as_float(v[c]) + sb2[j]);
+                    H2[j * kLD + tid] = h;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) out[o] = fmaf(h, sW3[o * kH + j], out[o]);
+                }
+            }
+            if (kActor) {
+                const float mu0 = tanh_fast(out[0]), mu1 = tanh_fast(out[OUT - 1]);  // actor_mu ends in nn.Tanh (ppo.py:19)
+                float dmu0 = 0.f, dmu1 = 0.f, klv = 0.f;
+                if (valid)
+                    ppo_policy_grad(mu0, mu1, d_a0, d_a1, d_lp, d_adv, adv_mean, adv_std, ls0, ls1, g.clip, g.n, dmu0,
+                                    dmu1, klv);
+                kl += klv;
+                dpre[0] = dmu0 * (1.f - mu0 * mu0);
+                dpre[OUT - 1] = dmu1 * (1.f - mu1 * mu1);
+            } else {
+                dpre[0] = valid ? ppo_value_grad(out[0], d_ret, d_val, g.clip, g.vf_coef, g.n) : 0.f;
+            }
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { DO[o * kLD + tid] = dpre[o]; gb3[o] += dpre[o]; }
+        }
+        __syncthreads();
+        // ---- dW3 += H2^T dOut (thread <-> (o, j) or (sample half, j)) ----
+        {
+            const int o = kActor ? kg : 0;
+            const int s0 = kActor ? 0 : kg * 64, s1 = kActor ? kTS : s0 + 64;
+            const float* h = H2 + u * kLD;
+            const float* d = DO + o * kLD;
+            float a = 0.f;
+#pragma unroll 4
+            for (int s = s0; s < s1; s += 4) {
+                const float4 hv = ld4(h + s), dv = ld4(d + s);
+                a = fmaf(hv.x, dv.x, a); a = fmaf(hv.y, dv.y, a); a = fmaf(hv.z, dv.z, a); a = fmaf(hv.w, dv.w, a);
+            }
+            gW3 += a;
+        }
+        __syncthreads();
+        // ---- dZ2 = (dOut W3) * (1 - H2^2): plain tile in place + A operand of the dH1 product ----
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = c0 + c;
+                const float h = H2[j * kLD + tid];
+                float z = 0.f;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) z = fmaf(dpre[o], sW3[o * kH + j], z);
+                z *= 1.f - h * h;
+                H2[j * kLD + tid] = z;
+                split_tf32(z, hi[c], lo[c]);
+            }
+            tmem_st8(lane_base + kColZh + c0, hi);
+            tmem_st8(lane_base + kColZl + c0, lo);
+        }
+        tmem_publish_and_sync();
+        // ---- dH1 = dZ2 W2 on the tensor core (ACC0) while the CUDA cores accumulate dW2 += H1^T dZ2 ----
+        if (tid == 0) issue_product(tmem, kColAcc0, kColZh, kColZl, W2th, W2tl, kH, &bar);
+        {
+            const float* ha = H1 + ti * kLD + kg * 64;
+            const float* zb = H2 + tj * kLD + kg * 64;
+#pragma unroll 1
+            for (int s = 0; s < 64; s += 4) {
+                float4 a[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) a[m] = ld4(ha + 8 * m * kLD + s);
+                float4 b = ld4(zb + s);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float4 nb = ld4(zb + 8 * ((n + 1) & 7) * kLD + s);
+                    gb2[n] += (b.x + b.y) + (b.z + b.w);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        float t = gW2[m][n];
+                        t = fmaf(a[m].x, b.x, t); t = fmaf(a[m].y, b.y, t);
+                        t = fmaf(a[m].z, b.z, t); t = fmaf(a[m].w, b.w, t);
+                        gW2[m][n] = t;
+                    }
+                    b = nb;
+                }
+            }
+        }
+        wait_product(&bar, phase);
+        __syncthreads();  // every thread has finished reading H1 (dW2) before it is overwritten
+        // ---- dZ1 = dH1 * (1 - H1^2), in place ----
+#pragma unroll 1
+        for (int c0 = 0; c0 < kH; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + kColAcc0 + c0, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                float* h = H1 + (c0 + c) * kLD + tid;
+                const float hv = *h;
+                *h = __uint_as_float(v[c]) * (1.f - hv * hv);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- dW1 += X^T dZ1, db1 += sum dZ1 ----
+        {
+            const float* z = H1 + u * kLD + kg * 64;
+            const float* x = X + kg * 64;
+#pragma unroll 2
+            for (int s = 0; s < 64; s += 4) {
+                const float4 zv = ld4(z + s);
+                gb1 += (zv.x + zv.y) + (zv.z + zv.w);
+#pragma unroll
+                for (int i = 0; i < kMaxD; ++i) {
+                    if (i < D) {
+                        const float4 xv = ld4(x + i * kLD + s);
+                        float t = gW1[i];
+                        t = fmaf(xv.x, zv.x, t); t = fmaf(xv.y, zv.y, t); t = fmaf(xv.z, zv.z, t); t = fmaf(xv.w, zv.w, t);
+                        gW1[i] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // X, H1, H2 are rewritten by the next tile
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+
+    // ---- combine the two sample halves and write this CTA's partial gradient (as in net_body) ----
+    float* stage = H1;
+    const int oW1 = 0, ob1 = kH * D, oW2 = ob1 + kH, ob2 = oW2 + kH * kH, oW3 = ob2 + kH, ob3 = oW3 + OUT * kH;
+    for (int pass = 1; pass >= 0; --pass) {
+        if (kg == pass) {
+            const bool add = pass == 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    float* d = stage + oW2 + (tj + 8 * n) * kH + (ti + 8 * m);
+                    *d = add ? *d + gW2[m][n] : gW2[m][n];
+                }
+            if (ti == 0) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    float* d = stage + ob2 + tj + 8 * n;
+                    *d = add ? *d + gb2[n] : gb2[n];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i)
+                if (i < D) {
+                    float* d = stage + oW1 + u * D + i;
+                    *d = add ? *d + gW1[i] : gW1[i];
+                }
+            {
+                float* d = stage + ob1 + u;
+                *d = add ? *d + gb1 : gb1;
+            }
+            if (kActor) {
+                stage[oW3 + kg * kH + u] = gW3;
+            } else {
+                float* d = stage + oW3 + u;
+                *d = add ? *d + gW3 : gW3;
+            }
+        }
+        __syncthreads();
+    }
+    float r[OUT + 1];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) r[o] = gb3[o];
+    r[OUT] = kl;
+#pragma unroll
+    for (int o = 0; o <= OUT; ++o) {
+        for (int m = 16; m > 0; m >>= 1) r[o] += __shfl_xor_sync(0xffffffffu, r[o], m);
+        if ((tid & 31) == 0) red[o * 4 + (tid >> 5)] = r[o];
+    }
+    __syncthreads();
+    if (tid < OUT) stage[ob3 + tid] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+    if (kActor && tid == 0)
+        g.kl_partial[blockIdx.x] = (double)((red[OUT * 4] + red[OUT * 4 + 1]) + (red[OUT * 4 + 2] + red[OUT * 4 + 3]));
+    __syncthreads();
+    float* dst = g.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kNetStride;
+    const int np = ob3 + OUT;
+    for (int q = tid; q < np; q += kNT) dst[q] = stage[q];
+}
+
+__global__ void __launch_bounds__(kNT, 1) ppo_mlp_grad_tc_kernel(const GradArgs g) {
+    extern __shared__ __align__(1024) float train_smem[];
+    if (blockIdx.y == 0) net_body_tc<2>(g, g.net[0], train_smem);
+    else net_body_tc<1>(g, g.net[1], train_smem);
+}
+
+constexpr size_t kTrainTcSmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH + 2 * kH + 2 * kH + (size_t)kMaxD * kLD +
+                                      2 * (size_t)kH * kLD + 2 * kLD + 16;
+static_assert(kTrainTcSmemFloats * sizeof(float) <= 226 * 1024, "one CTA per SM");
+static_assert((kH * kXK) % 4 == 0, "16-byte aligned carve-up");
+
 // flat_grad[q] = sum over CTAs of partial[net][cta][q'] in a fixed order; *kl_sum = sum kl_partial.
 // Block = 64 gradient elements x 4 groups of CTAs (each thread sums its quarter with 4 independent
 // chains, the quarters are combined through shared memory in a fixed order).
@@ -656,7 +1087,8 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     g.idx = io.idx; g.adv_part = io.adv_part; g.n_global = io.n_global; g.n = io.n; g.D = io.obs_dim;
     g.obs_stride = io.obs_stride;
     g.clip = io.clip; g.vf_coef = io.vf_coef;
-    const int ncta = train_grid(io.n);
+    int ncta = train_grid(io.n);
+    if (io.tensor_cores) ncta = (ncta + 1) / 2;   // one CTA per SM: half of the SMs per network
     if (io.workspace_bytes < 2 * (size_t)ncta * kNetStride * sizeof(float) + (size_t)ncta * sizeof(double)) return 3;
     g.kl_partial = reinterpret_cast<double*>(io.workspace);
     g.partial = reinterpret_cast<float*>(g.kl_partial + ((ncta + 1) & ~1));
@@ -667,7 +1099,17 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
         cudaFuncSetAttribute(ppo_mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    ppo_mlp_grad_kernel<<<dim3(ncta, 2), kNT, smem, stream>>>(g);
+    if (io.tensor_cores) {
+        const size_t smem_tc = kTrainTcSmemFloats * sizeof(float);
+        static bool tc_attr_set = false;
+        if (!tc_attr_set) {
+            cudaFuncSetAttribute(ppo_mlp_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+            tc_attr_set = true;
+        }
+        ppo_mlp_grad_tc_kernel<<<dim3(ncta, 2), kNT, smem_tc, stream>>>(g);
+    } else {
+        ppo_mlp_grad_kernel<<<dim3(ncta, 2), kNT, smem, stream>>>(g);
+    }
     count_launch();
     const int n_actor = kH * io.obs_dim + kH + kH * kH + kH + 2 * kH + 2;
     const int n_total = n_actor + kH * io.obs_dim + kH + kH * kH + kH + kH + 1;

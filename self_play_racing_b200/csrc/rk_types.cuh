@@ -147,6 +147,7 @@ struct PpoGradIO {
     float* flat_grad;
     double* kl_sum;
     float* kl_sum_f32;
+    int tensor_cores;
 };
 struct PpoAdamIO {
     float* params[12];
