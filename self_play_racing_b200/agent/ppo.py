@@ -127,7 +127,10 @@ class _GraphedMinibatch:
         self.dmu, self.dv = z(mb, 2), z(mb)
         agent = ppo.agent
         if self.fused_mlp:
-            self.grad = PpoMinibatchGrad(params, agent.log_std, obs_dim, c['clip_coef'], c['vf_coef'])
+            # 'tensor_core_update': the per-sample products on tcgen05 (TF32 x 3 split, fp32-grade); opt-in --
+            # verified against the FMA kernel to 1e-6, but not yet faster
+            self.grad = PpoMinibatchGrad(params, agent.log_std, obs_dim, c['clip_coef'], c['vf_coef'],
+                                         tensor_cores=bool(c.get('tensor_core_update', False)))
             self.flat_grad, self.kl_sum = self.grad.flat_grad, self.grad.kl_sum
             for p, gview in zip(params, self.grad.grad_views()):
                 p.grad = gview                      # the kernel writes the gradients where Adam reads them

@@ -43,6 +43,7 @@ struct GradArgs {
 };
 
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -522,10 +523,15 @@ __device__ __forceinline__ void tmem_publish_and_sync() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+constexpr int kNT2 = 256;   // threads of the tensor-core variant: 8 warps; warps w and w + 4 share TMEM lane quarter w & 3
+
 template <int OUT>
 __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P, float* smem) {
     constexpr bool kActor = OUT == 2;
-    const int tid = threadIdx.x, warp = tid >> 5, D = g.D;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = g.D;
+    const int half = warp >> 2;                    // which 32 of the 64 accumulator columns this thread handles
+    const int srow = (warp & 3) * 32 + lane;       // sample of the tile = TMEM lane
+    const int cbase = half * 32;
     // shared-memory carve-up: operand tiles of the tensor-core products first (16-byte aligned core matrices)
     float* W1h = smem;                      // [64][kXK]  B of layer 1 (K-major, rows = output j)
     float* W1l = W1h + kH * kXK;
@@ -539,28 +545,29 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     float* X = sW3 + 2 * kH;                // [kMaxD][kLD]  plain feature-major tiles of the CUDA-core phases
     float* H1 = X + kMaxD * kLD;            // [64][kLD]  h1, then dz1
     float* H2 = H1 + kH * kLD;              // [64][kLD]  h2, then dz2
-    float* DO = H2 + kH * kLD;              // [2][kLD]
-    float* red = DO + 2 * kLD;              // [16]
+    float* DO = H2 + kH * kLD;              // [2][kLD]   d loss / d (pre-activation output)
+    float* OP = DO + 2 * kLD;               // [2 halves][2][kLD]  partial output-layer sums of the two column halves
+    float* red = OP + 4 * kLD;              // [32]
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_slot;
 
-    for (int q = tid; q < kH * kXK; q += kNT) {
+    for (int q = tid; q < kH * kXK; q += kNT2) {
         const int j = q / kXK, i = q - j * kXK;
         uint32_t hi = 0, lo = 0;
         if (i < D) split_tf32(P.W1[j * D + i], hi, lo);
         W1h[umma_off(j, i, kXK)] = __uint_as_float(hi);
         W1l[umma_off(j, i, kXK)] = __uint_as_float(lo);
     }
-    for (int q = tid; q < kH * kH; q += kNT) {
+    for (int q = tid; q < kH * kH; q += kNT2) {
         const int j = q >> 6, i = q & 63;
         uint32_t hi, lo;
         split_tf32(P.W2[q], hi, lo);
         W2h[umma_off(j, i, kH)] = __uint_as_float(hi); W2l[umma_off(j, i, kH)] = __uint_as_float(lo);
         W2th[umma_off(i, j, kH)] = __uint_as_float(hi); W2tl[umma_off(i, j, kH)] = __uint_as_float(lo);
     }
-    for (int q = tid; q < kH; q += kNT) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
-    for (int q = tid; q < OUT * kH; q += kNT) sW3[q] = P.W3[q];
-    for (int q = tid; q < kMaxD * kLD; q += kNT) X[q] = 0.f;
+    for (int q = tid; q < kH; q += kNT2) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
+    for (int q = tid; q < OUT * kH; q += kNT2) sW3[q] = P.W3[q];
+    for (int q = tid; q < kMaxD * kLD; q += kNT2) X[q] = 0.f;
     float b3[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) b3[o] = P.b3[o];
@@ -577,7 +584,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's quarter of the TMEM lanes
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's quarter of the TMEM lanes
     unsigned phase = 0;
 
     float adv_mean = 0.f, adv_std = 1.f;
@@ -591,14 +598,16 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     }
     const float ls0 = kActor ? g.log_std[0] : 0.f, ls1 = kActor ? g.log_std[1] : 0.f;
 
-    // accumulators of the CUDA-core weight-gradient phases (same roles as in net_body)
-    const int kg = tid >> 6, u = tid & 63, ti = u >> 3, tj = u & 7;
-    float gW2[8][8], gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
+    // roles in the CUDA-core weight-gradient phases
+    const int kg = tid >> 7;                              // dW2: half of the tile's samples
+    const int ti = (tid & 127) >> 3, tj = tid & 7;        // dW2: inputs i = ti + 16 m (m < 4), outputs j = tj + 8 n (n < 8)
+    const int u = tid & 63, grp = tid >> 6;               // dW1 / dW3: output j = u, sample quarter (or output x sample half)
+    float gW2[4][8], gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        gb2[m] = 0.f;
+    for (int n = 0; n < 8; ++n) {
+        gb2[n] = 0.f;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) gW2[m][n] = 0.f;
+        for (int m = 0; m < 4; ++m) gW2[m][n] = 0.f;
     }
 #pragma unroll
     for (int i = 0; i < kMaxD; ++i) gW1[i] = 0.f;
@@ -606,24 +615,22 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
 
     const int ntiles = (g.n + kTS - 1) / kTS;
-    const bool vec_rows = (g.obs_stride & 3) == 0 && g.obs_stride >= ((D + 3) & ~3) &&
-                          (reinterpret_cast<uintptr_t>(g.obs) & 15u) == 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- gather: thread <-> sample; the row goes to the plain X tile (dW1) and, split, to TMEM (A of layer 1) ----
-        const int gi = tile * kTS + tid;
+        // ---- gather: two threads per sample (columns 0-15 / 16-23 of the padded row); the row goes to the plain X
+        //      tile (dW1) and, split into hi + lo, to TMEM (A operand of layer 1) ----
+        const int gi = tile * kTS + srow;
         const bool valid = gi < g.n;
         const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
         {
             const float* src = g.obs + row * g.obs_stride;
-#pragma unroll
-            for (int c0 = 0; c0 < kXK; c0 += 8) {
+            const int c_lo = half ? 16 : 0, c_hi = half ? kXK : 16;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int i = c0 + c;
-                    float v = 0.f;
-                    if (valid && i < D) v = (vec_rows || true) ? src[i] : 0.f;
-                    if (i < D) X[i * kLD + tid] = v;
+                    const float v = (valid && i < D) ? src[i] : 0.f;
+                    if (i < D) X[i * kLD + srow] = v;
                     split_tf32(v, hi[c], lo[c]);
                 }
                 tmem_st8(lane_base + kColXh + c0, hi);
@@ -631,7 +638,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
             }
         }
         float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
-        if (valid) {
+        if (valid && half == 0) {
             if (kActor) {
                 const float2 a = *reinterpret_cast<const float2*>(g.act + 2 * row);
                 d_a0 = a.x; d_a1 = a.y; d_lp = g.old_logp[row]; d_adv = g.adv[row];
@@ -639,50 +646,64 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
                 d_ret = g.ret[row]; d_val = g.val[row];
             }
         }
+        if (half == 1) {   // the next tile's random rows start their way from DRAM to L2 now
+            const int gn = (tile + (int)gridDim.x) * kTS + srow;
+            if (gn < g.n) {
+                const int64_t rn = g.idx ? g.idx[gn] : (int64_t)gn;
+                const float* pn = g.obs + rn * g.obs_stride;
+                prefetch_l2(pn); prefetch_l2(pn + D - 1);
+                if (kActor) { prefetch_l2(g.act + 2 * rn); prefetch_l2(g.old_logp + rn); prefetch_l2(g.adv + rn); }
+                else { prefetch_l2(g.ret + rn); prefetch_l2(g.val + rn); }
+            }
+        }
         tmem_publish_and_sync();
         // ---- layer 1 on the tensor core: ACC0 = X W1^T ----
         if (tid == 0) issue_product(tmem, kColAcc0, kColXh, kColXl, W1h, W1l, kXK, &bar);
         wait_product(&bar, phase);
-#pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
+        {
             uint32_t v[32];
-            tmem_ld32(lane_base + kColAcc0 + c0, v);
+            tmem_ld32(lane_base + kColAcc0 + cbase, v);
 #pragma unroll
             for (int c8 = 0; c8 < 32; c8 += 8) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int j = c0 + c8 + c;
+                    const int j = cbase + c8 + c;
                     const float h = tanh_fast(__uint_as_float(v[c8 + c]) + sb1[j]);
-                    H1[j * kLD + tid] = h;
+                    H1[j * kLD + srow] = h;
                     split_tf32(h, hi[c], lo[c]);
                 }
-                tmem_st8(lane_base + kColHh + c0 + c8, hi);
-                tmem_st8(lane_base + kColHl + c0 + c8, lo);
+                tmem_st8(lane_base + kColHh + cbase + c8, hi);
+                tmem_st8(lane_base + kColHl + cbase + c8, lo);
             }
         }
         tmem_publish_and_sync();
         // ---- layer 2: ACC1 = H1 W2^T ----
         if (tid == 0) issue_product(tmem, kColAcc1, kColHh, kColHl, W2h, W2l, kH, &bar);
         wait_product(&bar, phase);
-        float dpre[OUT];
         {
             float out[OUT];
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) out[o] = b3[o];
-#pragma unroll 1
-            for (int c0 = 0; c0 < kH; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + kColAcc1 + c0, v);
+            for (int o = 0; o < OUT; ++o) out[o] = 0.f;
+            uint32_t v[32];
+            tmem_ld32(lane_base + kColAcc1 + cbase, v);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int j = c0 + c;
-                    const float h = tanh_fast(__uint_as_float(v[c]) + sb2[j]);
-                    H2[j * kLD + tid] = h;
+            for (int c = 0; c < 32; ++c) {
+                const int j = cbase + c;
+                const float h = tanh_fast(__uint_as_float(v[c]) + sb2[j]);
+                H2[j * kLD + srow] = h;
 #pragma unroll
-                    for (int o = 0; o < OUT; ++o) out[o] = fmaf(h, sW3[o * kH + j], out[o]);
-                }
+                for (int o = 0; o < OUT; ++o) out[o] = fmaf(h, sW3[o * kH + j], out[o]);
             }
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) OP[(half * 2 + o) * kLD + srow] = out[o];
+        }
+        __syncthreads();
+        // ---- output layer + loss gradient: one thread per sample (column half 0) ----
+        if (half == 0) {
+            float out[OUT], dpre[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) out[o] = b3[o] + (OP[o * kLD + srow] + OP[(2 + o) * kLD + srow]);
             if (kActor) {
                 const float mu0 = tanh_fast(out[0]), mu1 = tanh_fast(out[OUT - 1]);  // actor_mu ends in nn.Tanh (ppo.py:19)
                 float dmu0 = 0.f, dmu1 = 0.f, klv = 0.f;
@@ -696,13 +717,13 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
                 dpre[0] = valid ? ppo_value_grad(out[0], d_ret, d_val, g.clip, g.vf_coef, g.n) : 0.f;
             }
 #pragma unroll
-            for (int o = 0; o < OUT; ++o) { DO[o * kLD + tid] = dpre[o]; gb3[o] += dpre[o]; }
+            for (int o = 0; o < OUT; ++o) { DO[o * kLD + srow] = dpre[o]; gb3[o] += dpre[o]; }
         }
         __syncthreads();
-        // ---- dW3 += H2^T dOut (thread <-> (o, j) or (sample half, j)) ----
+        // ---- dW3 += H2^T dOut: thread <-> (output o, sample half, j) [actor] or (sample quarter, j) [critic] ----
         {
-            const int o = kActor ? kg : 0;
-            const int s0 = kActor ? 0 : kg * 64, s1 = kActor ? kTS : s0 + 64;
+            const int o = kActor ? (grp & 1) : 0;
+            const int s0 = kActor ? (grp >> 1) * 64 : grp * 32, s1 = s0 + (kActor ? 64 : 32);
             const float* h = H2 + u * kLD;
             const float* d = DO + o * kLD;
             float a = 0.f;
@@ -715,22 +736,27 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         }
         __syncthreads();
         // ---- dZ2 = (dOut W3) * (1 - H2^2): plain tile in place + A operand of the dH1 product ----
-#pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 8) {
-            uint32_t hi[8], lo[8];
+        {
+            float dpre[OUT];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int j = c0 + c;
-                const float h = H2[j * kLD + tid];
-                float z = 0.f;
+            for (int o = 0; o < OUT; ++o) dpre[o] = DO[o * kLD + srow];
 #pragma unroll
-                for (int o = 0; o < OUT; ++o) z = fmaf(dpre[o], sW3[o * kH + j], z);
-                z *= 1.f - h * h;
-                H2[j * kLD + tid] = z;
-                split_tf32(z, hi[c], lo[c]);
+            for (int c8 = 0; c8 < 32; c8 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = cbase + c8 + c;
+                    const float h = H2[j * kLD + srow];
+                    float z = 0.f;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) z = fmaf(dpre[o], sW3[o * kH + j], z);
+                    z *= 1.f - h * h;
+                    H2[j * kLD + srow] = z;
+                    split_tf32(z, hi[c], lo[c]);
+                }
+                tmem_st8(lane_base + kColZh + cbase + c8, hi);
+                tmem_st8(lane_base + kColZl + cbase + c8, lo);
             }
-            tmem_st8(lane_base + kColZh + c0, hi);
-            tmem_st8(lane_base + kColZl + c0, lo);
         }
         tmem_publish_and_sync();
         // ---- dH1 = dZ2 W2 on the tensor core (ACC0) while the CUDA cores accumulate dW2 += H1^T dZ2 ----
@@ -740,16 +766,16 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
             const float* zb = H2 + tj * kLD + kg * 64;
 #pragma unroll 1
             for (int s = 0; s < 64; s += 4) {
-                float4 a[8];
+                float4 a[4];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) a[m] = ld4(ha + 8 * m * kLD + s);
+                for (int m = 0; m < 4; ++m) a[m] = ld4(ha + 16 * m * kLD + s);
                 float4 b = ld4(zb + s);
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                     const float4 nb = ld4(zb + 8 * ((n + 1) & 7) * kLD + s);
                     gb2[n] += (b.x + b.y) + (b.z + b.w);
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
+                    for (int m = 0; m < 4; ++m) {
                         float t = gW2[m][n];
                         t = fmaf(a[m].x, b.x, t); t = fmaf(a[m].y, b.y, t);
                         t = fmaf(a[m].z, b.z, t); t = fmaf(a[m].w, b.w, t);
@@ -762,25 +788,24 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         wait_product(&bar, phase);
         __syncthreads();  // every thread has finished reading H1 (dW2) before it is overwritten
         // ---- dZ1 = dH1 * (1 - H1^2), in place ----
-#pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
+        {
             uint32_t v[32];
-            tmem_ld32(lane_base + kColAcc0 + c0, v);
+            tmem_ld32(lane_base + kColAcc0 + cbase, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float* h = H1 + (c0 + c) * kLD + tid;
+                float* h = H1 + (cbase + c) * kLD + srow;
                 const float hv = *h;
                 *h = __uint_as_float(v[c]) * (1.f - hv * hv);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- dW1 += X^T dZ1, db1 += sum dZ1 ----
+        // ---- dW1 += X^T dZ1, db1 += sum dZ1: thread <-> (sample quarter, output j) ----
         {
-            const float* z = H1 + u * kLD + kg * 64;
-            const float* x = X + kg * 64;
+            const float* z = H1 + u * kLD + grp * 32;
+            const float* x = X + grp * 32;
 #pragma unroll 2
-            for (int s = 0; s < 64; s += 4) {
+            for (int s = 0; s < 32; s += 4) {
                 const float4 zv = ld4(z + s);
                 gb1 += (zv.x + zv.y) + (zv.z + zv.w);
 #pragma unroll
@@ -798,45 +823,33 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 
-    // ---- combine the two sample halves and write this CTA's partial gradient (as in net_body) ----
+    // ---- combine the thread groups in a fixed order and write this CTA's partial gradient ----
+    // layout = torch's parameter order of one Sequential: W1 [64][D], b1, W2 [64][64], b2, W3 [OUT][64], b3
     float* stage = H1;
     const int oW1 = 0, ob1 = kH * D, oW2 = ob1 + kH, ob2 = oW2 + kH * kH, oW3 = ob2 + kH, ob3 = oW3 + OUT * kH;
-    for (int pass = 1; pass >= 0; --pass) {
-        if (kg == pass) {
-            const bool add = pass == 0;
+    for (int q = tid; q < kNetStride; q += kNT2) stage[q] = 0.f;
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        if (kg == pass) {   // dW2, db2: two sample halves
 #pragma unroll
-            for (int m = 0; m < 8; ++m)
+            for (int m = 0; m < 4; ++m)
 #pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    float* d = stage + oW2 + (tj + 8 * n) * kH + (ti + 8 * m);
-                    *d = add ? *d + gW2[m][n] : gW2[m][n];
-                }
+                for (int n = 0; n < 8; ++n) stage[oW2 + (tj + 8 * n) * kH + (ti + 16 * m)] += gW2[m][n];
             if (ti == 0) {
 #pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    float* d = stage + ob2 + tj + 8 * n;
-                    *d = add ? *d + gb2[n] : gb2[n];
-                }
+                for (int n = 0; n < 8; ++n) stage[ob2 + tj + 8 * n] += gb2[n];
             }
+        }
+        if (grp == pass) {  // dW1, db1, dW3: four groups
 #pragma unroll
             for (int i = 0; i < kMaxD; ++i)
-                if (i < D) {
-                    float* d = stage + oW1 + u * D + i;
-                    *d = add ? *d + gW1[i] : gW1[i];
-                }
-            {
-                float* d = stage + ob1 + u;
-                *d = add ? *d + gb1 : gb1;
-            }
-            if (kActor) {
-                stage[oW3 + kg * kH + u] = gW3;
-            } else {
-                float* d = stage + oW3 + u;
-                *d = add ? *d + gW3 : gW3;
-            }
+                if (i < D) stage[oW1 + u * D + i] += gW1[i];
+            stage[ob1 + u] += gb1;
+            stage[oW3 + (kActor ? (grp & 1) : 0) * kH + u] += gW3;
         }
         __syncthreads();
     }
+    // db3 and the KL sum: fixed-order block reduction (only column-half-0 threads hold contributions)
     float r[OUT + 1];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) r[o] = gb3[o];
@@ -844,26 +857,26 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
 #pragma unroll
     for (int o = 0; o <= OUT; ++o) {
         for (int m = 16; m > 0; m >>= 1) r[o] += __shfl_xor_sync(0xffffffffu, r[o], m);
-        if ((tid & 31) == 0) red[o * 4 + (tid >> 5)] = r[o];
+        if (lane == 0) red[o * 8 + warp] = r[o];
     }
     __syncthreads();
-    if (tid < OUT) stage[ob3 + tid] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+    if (tid < OUT) stage[ob3 + tid] = (red[tid * 8] + red[tid * 8 + 1]) + (red[tid * 8 + 2] + red[tid * 8 + 3]);
     if (kActor && tid == 0)
-        g.kl_partial[blockIdx.x] = (double)((red[OUT * 4] + red[OUT * 4 + 1]) + (red[OUT * 4 + 2] + red[OUT * 4 + 3]));
+        g.kl_partial[blockIdx.x] = (double)((red[OUT * 8] + red[OUT * 8 + 1]) + (red[OUT * 8 + 2] + red[OUT * 8 + 3]));
     __syncthreads();
     float* dst = g.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kNetStride;
     const int np = ob3 + OUT;
-    for (int q = tid; q < np; q += kNT) dst[q] = stage[q];
+    for (int q = tid; q < np; q += kNT2) dst[q] = stage[q];
 }
 
-__global__ void __launch_bounds__(kNT, 1) ppo_mlp_grad_tc_kernel(const GradArgs g) {
+__global__ void __launch_bounds__(kNT2, 1) ppo_mlp_grad_tc_kernel(const GradArgs g) {
     extern __shared__ __align__(1024) float train_smem[];
     if (blockIdx.y == 0) net_body_tc<2>(g, g.net[0], train_smem);
     else net_body_tc<1>(g, g.net[1], train_smem);
 }
 
 constexpr size_t kTrainTcSmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH + 2 * kH + 2 * kH + (size_t)kMaxD * kLD +
-                                      2 * (size_t)kH * kLD + 2 * kLD + 16;
+                                      2 * (size_t)kH * kLD + 2 * kLD + 4 * kLD + 32;
 static_assert(kTrainTcSmemFloats * sizeof(float) <= 226 * 1024, "one CTA per SM");
 static_assert((kH * kXK) % 4 == 0, "16-byte aligned carve-up");
 
@@ -1106,7 +1119,7 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
             cudaFuncSetAttribute(ppo_mlp_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
             tc_attr_set = true;
         }
-        ppo_mlp_grad_tc_kernel<<<dim3(ncta, 2), kNT, smem_tc, stream>>>(g);
+        ppo_mlp_grad_tc_kernel<<<dim3(ncta, 2), kNT2, smem_tc, stream>>>(g);
     } else {
         ppo_mlp_grad_kernel<<<dim3(ncta, 2), kNT, smem, stream>>>(g);
     }

@@ -358,6 +358,48 @@ def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
     assert torch.equal(first, fused.flat_grad)
 
 
+@pytest.mark.parametrize('n,obs_dim', [(128, 19), (1000, 19), (4133, 15), (77, 7)])
+def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim):
+    """The tcgen05 variant of rk_ppo_minibatch_grad (layer 1, layer 2 and dH1 as TF32 x 3-pass
+    tensor-core products chained through TMEM) against the fp32 FMA kernel on the same inputs:
+    relative difference of the whole gradient <= 2e-5 of its largest element, same KL sum,
+    deterministic on replay."""
+    _, agent_mod, _ = pkg
+    from self_play_racing_b200 import spaces
+    from self_play_racing_b200.backend import PpoMinibatchGrad
+    torch.manual_seed(n)
+    agent = agent_mod.Agent(spaces.Box(-1, 1, (obs_dim,)), spaces.Box(-1, 1, (2,))).cuda()
+    with torch.no_grad():
+        for p in agent.parameters():
+            p.add_(0.2 * torch.randn_like(p))
+        agent.log_std.fill_(-0.7)
+    g = torch.Generator(device='cuda').manual_seed(2)
+    B = 2 * n
+    obs = torch.rand(B, obs_dim, device='cuda', generator=g) * 2 - 1
+    act = torch.rand(B, 2, device='cuda', generator=g) * 2 - 1
+    adv = torch.randn(B, device='cuda', generator=g)
+    val = torch.randn(B, device='cuda', generator=g)
+    ret = val + 0.3 * torch.randn(B, device='cuda', generator=g)
+    with torch.no_grad():
+        _, logp, _, _ = agent.get_action_and_value(obs, act)
+    logp = logp + 0.15 * torch.randn(B, device='cuda', generator=g)
+    idx = torch.randperm(B, device='cuda', generator=g)[:n]
+    params = list(agent.parameters())
+    fma = PpoMinibatchGrad(params, agent.log_std, obs_dim, 0.2, 0.5)
+    fma.stats(idx, adv)
+    g0, k0 = fma(idx, obs, act, logp, adv, ret, val)
+    g0, k0 = g0.clone(), float(k0)
+    tc = PpoMinibatchGrad(params, agent.log_std, obs_dim, 0.2, 0.5, tensor_cores=True)
+    tc.stats(idx, adv)
+    g1, k1 = tc(idx, obs, act, logp, adv, ret, val)
+    g1, k1 = g1.clone(), float(k1)
+    assert torch.isfinite(g1).all()
+    assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+    assert abs(k1 - k0) <= 1e-3 * max(1.0, abs(k0))
+    tc(idx, obs, act, logp, adv, ret, val)
+    assert torch.equal(g1, tc.flat_grad)
+
+
 @pytest.mark.parametrize('n', [1, 2, 5, 64, 1000, 65536, 4194304, 3000001])
 def test_device_permutation_is_a_permutation(pkg, n):
     """rk_random_permutation: every index exactly once, reproducible per (seed,
