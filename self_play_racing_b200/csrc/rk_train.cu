@@ -491,6 +491,7 @@ __device__ __forceinline__ void issue_product(uint32_t tmem, int colD, int colAh
     // instruction descriptor: D fp32, A/B tf32, both K-major, N = 64, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kH >> 3) << 17) | ((uint32_t)(kTS >> 4) << 24);
     const uint32_t sbo = (uint32_t)(K >> 2) * 128u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t acc = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 3; ++pass) {
@@ -542,8 +543,8 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     float* sb1 = W2tl + kH * kH;            // [64]
     float* sb2 = sb1 + kH;                  // [64]
     float* sW3 = sb2 + kH;                  // [OUT][64]
-    float* X = sW3 + 2 * kH;                // [kMaxD][kLD]  plain feature-major tiles of the CUDA-core phases
-    float* H1 = X + kMaxD * kLD;            // [64][kLD]  h1, then dz1
+    float* X = sW3 + 2 * kH;                // 2 x [kMaxD][kLD]  plain feature-major tiles of the CUDA-core phases (X double-buffered)
+    float* H1 = X + 2 * kMaxD * kLD;        // [64][kLD]  h1, then dz1
     float* H2 = H1 + kH * kLD;              // [64][kLD]  h2, then dz2
     float* DO = H2 + kH * kLD;              // [2][kLD]   d loss / d (pre-activation output)
     float* OP = DO + 2 * kLD;               // [2 halves][2][kLD]  partial output-layer sums of the two column halves
@@ -567,7 +568,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     }
     for (int q = tid; q < kH; q += kNT2) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
     for (int q = tid; q < OUT * kH; q += kNT2) sW3[q] = P.W3[q];
-    for (int q = tid; q < kMaxD * kLD; q += kNT2) X[q] = 0.f;
+    for (int q = tid; q < 2 * kMaxD * kLD; q += kNT2) X[q] = 0.f;
     float b3[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) b3[o] = P.b3[o];
@@ -615,50 +616,73 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
 
     const int ntiles = (g.n + kTS - 1) / kTS;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- gather: two threads per sample (columns 0-15 / 16-23 of the padded row); the row goes to the plain X
-        //      tile (dW1) and, split into hi + lo, to TMEM (A operand of layer 1) ----
+    // One tile's observation rows: two threads per sample (columns 0-15 / 16-23 of the padded row); the row goes
+    // to a plain X tile (dW1) and, split into hi + lo, to the TMEM columns that are the A operand of layer 1.
+    auto gather = [&](int tile, float* Xbuf, bool& valid, float& a0, float& a1, float& lp, float& adv, float& ret,
+                      float& val) {
         const int gi = tile * kTS + srow;
-        const bool valid = gi < g.n;
+        valid = gi < g.n;
         const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
-        {
-            const float* src = g.obs + row * g.obs_stride;
-            const int c_lo = half ? 16 : 0, c_hi = half ? kXK : 16;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
-                uint32_t hi[8], lo[8];
+        const float* src = g.obs + row * g.obs_stride;
+        const int c_lo = half ? 16 : 0, c_hi = half ? kXK : 16;
+        for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+            uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int i = c0 + c;
-                    const float v = (valid && i < D) ? src[i] : 0.f;
-                    if (i < D) X[i * kLD + srow] = v;
-                    split_tf32(v, hi[c], lo[c]);
-                }
-                tmem_st8(lane_base + kColXh + c0, hi);
-                tmem_st8(lane_base + kColXl + c0, lo);
+            for (int c = 0; c < 8; ++c) {
+                const int i = c0 + c;
+                const float v = (valid && i < D) ? src[i] : 0.f;
+                if (i < D) Xbuf[i * kLD + srow] = v;
+                split_tf32(v, hi[c], lo[c]);
             }
+            tmem_st8(lane_base + kColXh + c0, hi);
+            tmem_st8(lane_base + kColXl + c0, lo);
         }
-        float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
+        a0 = a1 = lp = adv = ret = val = 0.f;
         if (valid && half == 0) {
             if (kActor) {
                 const float2 a = *reinterpret_cast<const float2*>(g.act + 2 * row);
-                d_a0 = a.x; d_a1 = a.y; d_lp = g.old_logp[row]; d_adv = g.adv[row];
+                a0 = a.x; a1 = a.y; lp = g.old_logp[row]; adv = g.adv[row];
             } else {
-                d_ret = g.ret[row]; d_val = g.val[row];
+                ret = g.ret[row]; val = g.val[row];
             }
         }
-        if (half == 1) {   // the next tile's random rows start their way from DRAM to L2 now
-            const int gn = (tile + (int)gridDim.x) * kTS + srow;
-            if (gn < g.n) {
-                const int64_t rn = g.idx ? g.idx[gn] : (int64_t)gn;
-                const float* pn = g.obs + rn * g.obs_stride;
-                prefetch_l2(pn); prefetch_l2(pn + D - 1);
-                if (kActor) { prefetch_l2(g.act + 2 * rn); prefetch_l2(g.old_logp + rn); prefetch_l2(g.adv + rn); }
-                else { prefetch_l2(g.ret + rn); prefetch_l2(g.val + rn); }
+    };
+    // dW1 += X^T dZ1, db1 += sum dZ1 of one tile: thread <-> (sample quarter, output j)
+    auto dw1 = [&](const float* Xbuf) {
+        const float* z = H1 + u * kLD + grp * 32;
+        const float* x = Xbuf + grp * 32;
+#pragma unroll 2
+        for (int s = 0; s < 32; s += 4) {
+            const float4 zv = ld4(z + s);
+            gb1 += (zv.x + zv.y) + (zv.z + zv.w);
+#pragma unroll
+            for (int i = 0; i < kMaxD; ++i) {
+                if (i < D) {
+                    const float4 xv = ld4(x + i * kLD + s);
+                    float t = gW1[i];
+                    t = fmaf(xv.x, zv.x, t); t = fmaf(xv.y, zv.y, t); t = fmaf(xv.z, zv.z, t); t = fmaf(xv.w, zv.w, t);
+                    gW1[i] = t;
+                }
             }
         }
-        tmem_publish_and_sync();
-        // ---- layer 1 on the tensor core: ACC0 = X W1^T ----
+    };
+    // Software pipeline across tiles: the tensor core never waits for the CUDA cores to have nothing to do --
+    // dW1 of tile t-1 runs while layer 1 of tile t is in flight, the gather of tile t+1 while layer 2 is,
+    // dW2 while dH1 is.
+    bool valid = false, n_valid = false;
+    float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
+    float n_a0 = 0.f, n_a1 = 0.f, n_lp = 0.f, n_adv = 0.f, n_ret = 0.f, n_val = 0.f;
+    int buf = 0;
+    bool have_prev = false;
+    if ((int)blockIdx.x < ntiles) gather(blockIdx.x, X, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
+    tmem_publish_and_sync();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        float* Xcur = X + buf * kMaxD * kLD;
+        float* Xoth = X + (buf ^ 1) * kMaxD * kLD;
+        // ---- layer 1 on the tensor core: ACC0 = X W1^T; meanwhile dW1 of the previous tile ----
         if (tid == 0) issue_product(tmem, kColAcc0, kColXh, kColXl, W1h, W1l, kXK, &bar);
+        if (have_prev) dw1(Xoth);
+        __syncthreads();   // dW1 has finished reading H1 (dZ1 of the previous tile) before the epilogue overwrites it
         wait_product(&bar, phase);
         {
             uint32_t v[32];
@@ -678,8 +702,9 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
             }
         }
         tmem_publish_and_sync();
-        // ---- layer 2: ACC1 = H1 W2^T ----
+        // ---- layer 2: ACC1 = H1 W2^T; meanwhile the next tile's rows are gathered (layer 1 has released the X columns) ----
         if (tid == 0) issue_product(tmem, kColAcc1, kColHh, kColHl, W2h, W2l, kH, &bar);
+        if (tile + (int)gridDim.x < ntiles) gather(tile + gridDim.x, Xoth, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
         wait_product(&bar, phase);
         {
             float out[OUT];
@@ -800,27 +825,13 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- dW1 += X^T dZ1, db1 += sum dZ1: thread <-> (sample quarter, output j) ----
-        {
-            const float* z = H1 + u * kLD + grp * 32;
-            const float* x = X + grp * 32;
-#pragma unroll 2
-            for (int s = 0; s < 32; s += 4) {
-                const float4 zv = ld4(z + s);
-                gb1 += (zv.x + zv.y) + (zv.z + zv.w);
-#pragma unroll
-                for (int i = 0; i < kMaxD; ++i) {
-                    if (i < D) {
-                        const float4 xv = ld4(x + i * kLD + s);
-                        float t = gW1[i];
-                        t = fmaf(xv.x, zv.x, t); t = fmaf(xv.y, zv.y, t); t = fmaf(xv.z, zv.z, t); t = fmaf(xv.w, zv.w, t);
-                        gW1[i] = t;
-                    }
-                }
-            }
-        }
-        __syncthreads();  // X, H1, H2 are rewritten by the next tile
+        // dW1 of this tile is deferred to the next iteration (or to the epilogue below)
+        have_prev = true;
+        buf ^= 1;
+        valid = n_valid; d_a0 = n_a0; d_a1 = n_a1; d_lp = n_lp; d_adv = n_adv; d_ret = n_ret; d_val = n_val;
     }
+    if (have_prev) dw1(X + (buf ^ 1) * kMaxD * kLD);
+    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 
     // ---- combine the thread groups in a fixed order and write this CTA's partial gradient ----
@@ -875,7 +886,7 @@ __global__ void __launch_bounds__(kNT2, 1) ppo_mlp_grad_tc_kernel(const GradArgs
     else net_body_tc<1>(g, g.net[1], train_smem);
 }
 
-constexpr size_t kTrainTcSmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH + 2 * kH + 2 * kH + (size_t)kMaxD * kLD +
+constexpr size_t kTrainTcSmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH + 2 * kH + 2 * kH + 2 * (size_t)kMaxD * kLD +
                                       2 * (size_t)kH * kLD + 2 * kLD + 4 * kLD + 32;
 static_assert(kTrainTcSmemFloats * sizeof(float) <= 226 * 1024, "one CTA per SM");
 static_assert((kH * kXK) % 4 == 0, "16-byte aligned carve-up");
