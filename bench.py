@@ -244,6 +244,26 @@ def time_ppo(args, wl, vec, dev, rank, world):
         grad_kernel = {'kernel': 'rk::ppo_mlp_grad_kernel + rk::ppo_grad_reduce_kernel', 'rows_per_minibatch': mb,
                        'us_per_minibatch': us, 'fma_per_row': fma_per_row,
                        'tflops': 2.0 * fma_per_row * mb / (us * 1e-6) / 1e12}
+        # the opt-in tcgen05 variant of the same entry point (TF32 x 3-pass products chained through TMEM), same inputs
+        try:
+            from self_play_racing_b200.backend import PpoMinibatchGrad
+            tc = PpoMinibatchGrad(list(trainer.agent.parameters()), trainer.agent.log_std, D, cfg['clip_coef'],
+                                  cfg['vf_coef'], tensor_cores=True)
+            for rep in range(2):
+                for k, (a, b) in enumerate(evs):
+                    idx = perm[k * mb:(k + 1) * mb]
+                    flush.zero_()
+                    tc.stats(idx, adv)
+                    a.record()
+                    tc(idx, g.obs_pad[:, :D], act, lp, adv, ret, val)
+                    b.record()
+                torch.cuda.synchronize(dev)
+            grad_kernel['tensor_core_variant_us'] = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2]
+            rel = float((tc.flat_grad - g.grad.flat_grad).abs().max() / g.grad.flat_grad.abs().max().clamp_min(1e-30))
+            grad_kernel['tensor_core_variant_max_rel_diff'] = rel
+        except Exception as exc:  # the default path does not depend on it
+            grad_kernel['tensor_core_variant_us'] = None
+            grad_kernel['tensor_core_variant_error'] = str(exc)[:200]
         del flush
     roll = float(np.mean([t[0] for t in times]))
     upd = float(np.mean([t[1] for t in times]))
