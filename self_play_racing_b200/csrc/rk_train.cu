@@ -607,12 +607,13 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     const int kg = tid >> 7;                              // dW2: half of the tile's samples
     const int ti = (tid & 127) >> 3, tj = tid & 7;        // dW2: inputs i = ti + 16 m (m < 4), outputs j = tj + 8 n (n < 8)
     const int u = tid & 63, grp = tid >> 6;               // dW1 / dW3: output j = u, sample quarter (or output x sample half)
-    float gW2[4][8], gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
+    float2 gW2[4][8];   // FFMA2 lanes = partial sums over even / odd samples (added at the end)
+    float gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
         gb2[n] = 0.f;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) gW2[m][n] = 0.f;
+        for (int m = 0; m < 4; ++m) gW2[m][n] = make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < kMaxD; ++i) gW1[i] = 0.f;
@@ -805,9 +806,9 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
                     gb2[n] += (b.x + b.y) + (b.z + b.w);
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
-                        float t = gW2[m][n];
-                        t = fmaf(a[m].x, b.x, t); t = fmaf(a[m].y, b.y, t);
-                        t = fmaf(a[m].z, b.z, t); t = fmaf(a[m].w, b.w, t);
+                        float2 t = gW2[m][n];
+                        t = __ffma2_rn(make_float2(a[m].x, a[m].y), make_float2(b.x, b.y), t);
+                        t = __ffma2_rn(make_float2(a[m].z, a[m].w), make_float2(b.z, b.w), t);
                         gW2[m][n] = t;
                     }
                     b = nb;
@@ -849,7 +850,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
 #pragma unroll
             for (int m = 0; m < 4; ++m)
 #pragma unroll
-                for (int n = 0; n < 8; ++n) stage[oW2 + (tj + 8 * n) * kH + (ti + 16 * m)] += gW2[m][n];
+                for (int n = 0; n < 8; ++n) stage[oW2 + (tj + 8 * n) * kH + (ti + 16 * m)] += gW2[m][n].x + gW2[m][n].y;
             if (ti == 0) {
 #pragma unroll
                 for (int n = 0; n < 8; ++n) stage[ob2 + tj + 8 * n] += gb2[n];
