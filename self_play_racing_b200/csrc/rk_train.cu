@@ -608,7 +608,8 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
     const int ti = (tid & 127) >> 3, tj = tid & 7;        // dW2: inputs i = ti + 16 m (m < 4), outputs j = tj + 8 n (n < 8)
     const int u = tid & 63, grp = tid >> 6;               // dW1 / dW3: output j = u, sample quarter (or output x sample half)
     float2 gW2[4][8];   // FFMA2 lanes = partial sums over even / odd samples (added at the end)
-    float gW1[kMaxD], gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
+    float2 gW1[kMaxD];
+    float gb2[8], gb1 = 0.f, gW3 = 0.f, gb3[OUT], kl = 0.f;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
         gb2[n] = 0.f;
@@ -616,7 +617,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         for (int m = 0; m < 4; ++m) gW2[m][n] = make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i) gW1[i] = 0.f;
+    for (int i = 0; i < kMaxD; ++i) gW1[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
 
@@ -664,8 +665,9 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
             for (int i = 0; i < kMaxD; ++i) {
                 if (i < D) {
                     const float4 xv = ld4(x + i * kLD + s);
-                    float t = gW1[i];
-                    t = fmaf(xv.x, zv.x, t); t = fmaf(xv.y, zv.y, t); t = fmaf(xv.z, zv.z, t); t = fmaf(xv.w, zv.w, t);
+                    float2 t = gW1[i];
+                    t = __ffma2_rn(make_float2(xv.x, xv.y), make_float2(zv.x, zv.y), t);
+                    t = __ffma2_rn(make_float2(xv.z, xv.w), make_float2(zv.z, zv.w), t);
                     gW1[i] = t;
                 }
             }
@@ -859,7 +861,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         if (grp == pass) {  // dW1, db1, dW3: four groups
 #pragma unroll
             for (int i = 0; i < kMaxD; ++i)
-                if (i < D) stage[oW1 + u * D + i] += gW1[i];
+                if (i < D) stage[oW1 + u * D + i] += gW1[i].x + gW1[i].y;
             stage[ob1 + u] += gb1;
             stage[oW3 + (kActor ? (grp & 1) : 0) * kH + u] += gW3;
         }
