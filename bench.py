@@ -218,10 +218,12 @@ def time_ppo(args, wl, vec, dev, rank, world):
         if it > 0:
             times.append((e0.elapsed_time(e1), e1.elapsed_time(e2), steps))
     # the update's dominant kernel on its own: rk_ppo_minibatch_grad over the trainer's padded observation
-    # buffer, CUDA events on the launching stream, L2 flushed between calls
+    # buffer, CUDA events on the launching stream, L2 flushed between calls; both implementations of the entry
+    # point (fp32 FMA kernel / tcgen05 TF32 x 3-pass kernel) on the same inputs
     grad_kernel = None
     g = getattr(trainer, '_graphed', None)
     if g is not None and getattr(g, 'fused_mlp', False) and getattr(g, 'obs_pad', None) is not None:
+        from self_play_racing_b200.backend import PpoMinibatchGrad
         n_rows, mb = g.obs_pad.shape[0], g.mb
         D = buf['obs'].shape[-1]
         gen = torch.Generator(device=dev).manual_seed(0)
@@ -230,40 +232,32 @@ def time_ppo(args, wl, vec, dev, rank, world):
         perm = torch.randperm(n_rows, device=dev, generator=gen)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         evs = [(ev(), ev()) for _ in range(min(16, n_rows // mb))]
-        for rep in range(2):
-            for k, (a, b) in enumerate(evs):
-                idx = perm[k * mb:(k + 1) * mb]
-                flush.zero_()
-                g.grad.stats(idx, adv)
-                a.record()
-                g.grad(idx, g.obs_pad[:, :D], act, lp, adv, ret, val)
-                b.record()
-            torch.cuda.synchronize(dev)
-        us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2]
-        fma_per_row = 2 * (2 * D * 64 + 3 * 64 * 64)   # both networks: forward 2 products, backward dH1 + dW2 + dW1
-        grad_kernel = {'kernel': 'rk::ppo_mlp_grad_kernel + rk::ppo_grad_reduce_kernel', 'rows_per_minibatch': mb,
-                       'us_per_minibatch': us, 'fma_per_row': fma_per_row,
-                       'tflops': 2.0 * fma_per_row * mb / (us * 1e-6) / 1e12}
-        # the opt-in tcgen05 variant of the same entry point (TF32 x 3-pass products chained through TMEM), same inputs
-        try:
-            from self_play_racing_b200.backend import PpoMinibatchGrad
-            tc = PpoMinibatchGrad(list(trainer.agent.parameters()), trainer.agent.log_std, D, cfg['clip_coef'],
-                                  cfg['vf_coef'], tensor_cores=True)
+        params = list(trainer.agent.parameters())
+
+        def time_impl(tensor_cores):
+            k = PpoMinibatchGrad(params, trainer.agent.log_std, D, cfg['clip_coef'], cfg['vf_coef'], tensor_cores=tensor_cores)
             for rep in range(2):
-                for k, (a, b) in enumerate(evs):
-                    idx = perm[k * mb:(k + 1) * mb]
+                for i, (a, b) in enumerate(evs):
+                    idx = perm[i * mb:(i + 1) * mb]
                     flush.zero_()
-                    tc.stats(idx, adv)
+                    k.stats(idx, adv)
                     a.record()
-                    tc(idx, g.obs_pad[:, :D], act, lp, adv, ret, val)
+                    k(idx, g.obs_pad[:, :D], act, lp, adv, ret, val)
                     b.record()
                 torch.cuda.synchronize(dev)
-            grad_kernel['tensor_core_variant_us'] = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2]
-            rel = float((tc.flat_grad - g.grad.flat_grad).abs().max() / g.grad.flat_grad.abs().max().clamp_min(1e-30))
-            grad_kernel['tensor_core_variant_max_rel_diff'] = rel
-        except Exception as exc:  # the default path does not depend on it
-            grad_kernel['tensor_core_variant_us'] = None
-            grad_kernel['tensor_core_variant_error'] = str(exc)[:200]
+            return sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2], k.flat_grad.clone()
+        us_fma, grad_fma = time_impl(False)
+        us_tc, grad_tc = time_impl(True)
+        used_tc = bool(getattr(g, 'tensor_cores', False))
+        us = us_tc if used_tc else us_fma
+        fma_per_row = 2 * (2 * D * 64 + 3 * 64 * 64)   # both networks: forward 2 products, backward dH1 + dW2 + dW1
+        grad_kernel = {'kernel': ('rk::ppo_mlp_grad_tc_kernel' if used_tc else 'rk::ppo_mlp_grad_kernel') +
+                                 ' + rk::ppo_grad_reduce_kernel',
+                       'rows_per_minibatch': mb, 'us_per_minibatch': us, 'fma_per_row': fma_per_row,
+                       'tflops': 2.0 * fma_per_row * mb / (us * 1e-6) / 1e12,
+                       'fp32_fma_kernel_us': us_fma, 'tcgen05_kernel_us': us_tc,
+                       'max_rel_diff_between_them': float((grad_tc - grad_fma).abs().max() /
+                                                          grad_fma.abs().max().clamp_min(1e-30))}
         del flush
     roll = float(np.mean([t[0] for t in times]))
     upd = float(np.mean([t[1] for t in times]))
@@ -276,6 +270,8 @@ def time_ppo(args, wl, vec, dev, rank, world):
             'update_epochs': cfg['update_epochs'], 'num_minibatches': cfg['num_minibatches'],
             'kl_early_stop': 'disabled for timing', 'opponent_pool': cfg['pool_size'],
             'update_matmul_precision': args.ppo_precision,
+            'update_products': ('tcgen05 tf32 x 3 passes (fp32 emulation, fp32 accumulate)'
+                                if getattr(getattr(trainer, '_graphed', None), 'tensor_cores', False) else 'fp32 FMA'),
             'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3), 'grad_kernel': grad_kernel}
 
 
