@@ -446,17 +446,62 @@ class PPO:
         n_steps = 0
         n_glob = float(mb * self.world)
         if g.fused_mlp and g.adam is not None:
-            # the whole minibatch step stays on the device; the KL stop latches there and is read once per epoch
+            # The whole minibatch step stays on the device; the KL stop latches there and is read once per epoch.
+            # One epoch (statistics, 16 x [gradient, all-reduce, clip + Adam]) is captured ONCE as a CUDA graph
+            # over static buffers and replayed with a fresh permutation per epoch, so the update's speed does not
+            # depend on how fast the host can issue ~50 launches per epoch ('graph_update_epoch': False disables).
             g.adam.reset()
-            for epoch in range(c['update_epochs']):
-                perm = permutation(epoch) if permutation is not None else self._permutation(n_local, b_obs.device)
-                # the epoch's advantage statistics need one all-reduce, every minibatch one more (gradient + KL)
-                self._all_reduce(g.grad.stats_epoch(perm, mb, b_adv))
+            dev = b_obs.device
+            st = getattr(g, 'epoch_static', None)
+            if st is None or st['perm'].numel() != n_local:
+                st = g.epoch_static = {'perm': torch.empty(n_local, dtype=torch.int64, device=dev),
+                                       'act': torch.empty_like(b_actions), 'logp': torch.empty_like(b_logprobs),
+                                       'adv': torch.empty_like(b_adv), 'ret': torch.empty_like(b_returns),
+                                       'val': torch.empty_like(b_values)}
+                g.epoch_graph, g.epoch_key = None, None
+            for key, src in (('act', b_actions), ('logp', b_logprobs), ('adv', b_adv), ('ret', b_returns), ('val', b_values)):
+                st[key].copy_(src)
+
+            def run_epoch():
+                self._all_reduce(g.grad.stats_epoch(st['perm'], mb, st['adv']))
                 for k, start in enumerate(range(0, n_local - mb + 1, mb)):
                     g.grad.use_stats(k)
-                    g.grad(perm[start:start + mb], b_obs, b_actions, b_logprobs, b_adv, b_returns, b_values, n_global=n_glob)
+                    g.grad(st['perm'][start:start + mb], b_obs, st['act'], st['logp'], st['adv'], st['ret'], st['val'],
+                           n_global=n_glob)
                     self._all_reduce(g.grad.grad_and_kl)
                     g.adam(n_glob, kl_target=c['kl_target'])
+            use_graph = bool(c.get('graph_update_epoch', True))
+            key = (n_local, mb, float(c['kl_target']), b_obs.data_ptr(), self.world)
+            for epoch in range(c['update_epochs']):
+                if permutation is not None:
+                    st['perm'].copy_(permutation(epoch))
+                else:
+                    self._perm_count = getattr(self, '_perm_count', 0) + 1
+                    random_permutation(n_local, c['seed'] + 12345, self._perm_count, out=st['perm'])
+                if not use_graph:
+                    run_epoch()
+                elif g.epoch_graph is None or g.epoch_key != key:
+                    run_epoch()                                   # this epoch runs eagerly (and warms everything up) ...
+                    torch.cuda.synchronize(dev)
+                    stopped = int(g.adam.state[0])
+                    if not stopped:                               # ... then the same sequence is captured for the next ones
+                        saved_state = g.adam.state.clone()
+                        graph = torch.cuda.CUDAGraph()
+                        snap = [p.detach().clone() for p in self.agent.parameters()]
+                        osnap = [{k2: v.clone() for k2, v in self.optimizer.state[p].items() if torch.is_tensor(v)}
+                                 for p in self.agent.parameters()]
+                        with torch.cuda.graph(graph):
+                            run_epoch()
+                        # capture does not execute, but be explicit: parameters, optimizer state and flags are as before
+                        with torch.no_grad():
+                            for p, q, o in zip(self.agent.parameters(), snap, osnap):
+                                p.copy_(q)
+                                for k2, v in o.items():
+                                    self.optimizer.state[p][k2].copy_(v)
+                        g.adam.state.copy_(saved_state)
+                        g.epoch_graph, g.epoch_key = graph, key
+                else:
+                    g.epoch_graph.replay()
                 stopped, n_steps = (int(v) for v in g.adam.state.tolist()[:2])   # one host sync per epoch
                 if stopped:
                     if self.rank == 0:
