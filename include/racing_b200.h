@@ -162,7 +162,10 @@ typedef struct rk_host_io {
     const void* arena_dev;        /* device: contiguous block holding the small per-env results  */
     int64_t arena_bytes;
     int32_t selfplay;             /* != 0: car 1 is driven here (SelfPlayWrapper, wrappers.py:29-45) */
-    int32_t reserved0;
+    int32_t reserved0;            /* bit 0: zero-copy observations -- if `obs` is pinned (mapped) host memory the step
+                                   * kernel writes car 0's complete rows straight into it (one coalesced store per
+                                   * environment) and no device->host copy of the observations follows; culled
+                                   * queries, num_agents <= 2, num_agents * num_sensors <= 32; ignored otherwise */
     const float* opponent_params; /* device, packed Agent (see rk_policy_act) or NULL = uniform Box samples */
     uint64_t seed, counter;       /* Philox stream of the opponent's sampling                    */
 } rk_host_io;

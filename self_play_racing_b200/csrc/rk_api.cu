@@ -456,6 +456,19 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
     p.mode = 0;
     p.io = *io;
     p.group_env = nullptr;  // range launches are plain launches
+    // zero-copy observations (host->reserved0 bit 0): if the caller's host buffer is pinned (mapped into the device's
+    // address space) the step kernel also writes car 0's complete rows straight into it, one coalesced store per
+    // environment, so that they cross PCIe while the kernel is still running and no device->host copy follows
+    bool zero_copy = false;
+    if ((host->reserved0 & 1) && h->cfg.query_mode == RK_QUERY_CULLED && A <= 2 && A * h->cfg.num_sensors <= 32 && D <= 32) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host->obs) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            p.obs_host0 = static_cast<float*>(attr.devicePointer);
+            zero_copy = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     const int n = host->n_chunks < 1 ? 1 : (host->n_chunks > 8 ? 8 : host->n_chunks);
     cudaSetDevice(h->cfg.device);
     for (int c = 0; c < n; ++c)
@@ -487,8 +500,9 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
             snprintf(h->err, sizeof(h->err), "rk_step_host: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return 1;
         }
-        H_CUDA(h, cudaMemcpyAsync(host->obs + (size_t)lo * D, io->obs + (size_t)lo * D, (size_t)m * D * sizeof(float),
-                                  cudaMemcpyDeviceToHost, st));
+        if (!zero_copy)
+            H_CUDA(h, cudaMemcpyAsync(host->obs + (size_t)lo * D, io->obs + (size_t)lo * D, (size_t)m * D * sizeof(float),
+                                      cudaMemcpyDeviceToHost, st));
         H_CUDA(h, cudaEventRecord(h->hevent[c], st));
     }
     cudaStream_t last = h->hstream[n - 1];

@@ -847,6 +847,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     }
     __syncwarp();
     // non-ray slots, every car in parallel
+    float nrv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // car 0's non-ray values, for the zero-copy host row
     if (want_obs) {
         float* orow = obs + ci * D + R;
         const double vf = clipd(ddiv(dadd(dmul(vx, cs), dmul(vy, sn)), kMaxSpeed), -1.0, 1.0);
@@ -855,6 +856,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         orow[1] = (float)vl;
         orow[2] = 0.f;  // Car.angular_velocity is never updated
         orow[3] = last_steer;
+        nrv[0] = (float)vf; nrv[1] = (float)vl; nrv[2] = 0.f; nrv[3] = last_steer;
         if (KIND == RK_ENV_MULTI) {
             const double mtd = tmp->max_track_distance;
             int w = 4;
@@ -863,12 +865,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const int l = base + o;
                 const double rx = dsub(S.x[l], x), ry = dsub(S.y[l], y);
                 const double rvx = dsub(S.vx[l], vx), rvy = dsub(S.vy[l], vy);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(rx, cs), dmul(ry, sn)), mtd), -1.0, 1.0);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rx, sn), dmul(ry, cs)), mtd), -1.0, 1.0);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(rvx, cs), dmul(rvy, sn)), kMaxSpeed), -1.0, 1.0);
-                orow[w++] = (float)clipd(ddiv(dadd(dmul(-rvx, sn), dmul(rvy, cs)), kMaxSpeed), -1.0, 1.0);
+                const float o0 = (float)clipd(ddiv(dadd(dmul(rx, cs), dmul(ry, sn)), mtd), -1.0, 1.0);
+                const float o1 = (float)clipd(ddiv(dadd(dmul(-rx, sn), dmul(ry, cs)), mtd), -1.0, 1.0);
+                const float o2 = (float)clipd(ddiv(dadd(dmul(rvx, cs), dmul(rvy, sn)), kMaxSpeed), -1.0, 1.0);
+                const float o3 = (float)clipd(ddiv(dadd(dmul(-rvx, sn), dmul(rvy, cs)), kMaxSpeed), -1.0, 1.0);
+                if (w == 4) { nrv[4] = o0; nrv[5] = o1; nrv[6] = o2; nrv[7] = o3; }
+                orow[w++] = o0; orow[w++] = o1; orow[w++] = o2; orow[w++] = o3;
             }
         }
+    }
+
+    // zero-copy rows: S.vx / S.vy are dead from here on; they become the per-environment store of car 0's non-ray
+    // values ([8][16] floats), picked up by the lanes that write the complete host row after the raycast
+    float* nr_sh = reinterpret_cast<float*>(S.vx);
+    if (p.obs_host0 != nullptr) {
+        __syncwarp();   // every lane has finished reading S.vx / S.vy
+        if (want_obs && a == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nr_sh[k * 16 + g] = nrv[k];
+        }
+        __syncwarp();
     }
 
     if (STAGED && p.mode != 0) {  // reset / observe launches did not pass the wait above
@@ -916,6 +932,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const double ox = S.x[gbase + ca], oy = S.y[gbase + ca];
                 double v3x = 0.0, v3y = 1.0, wall = INFINITY;
                 bool redo = false;
+                float hval = 0.f;
                 if (live) {
                     const double2 d = cv.dir64[slot];
                     v3x = -d.y; v3y = d.x;  // track.py:178
@@ -944,7 +961,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     else if (t == INFINITY)
                         t = kMaxRange;  // track.py:196-197
                     const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
-                    obs[oi * D + r] = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+                    hval = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+                    obs[oi * D + r] = hval;
+                }
+                if (p.obs_host0 != nullptr) {
+                    // the complete row of car 0 (rays from lanes 0..R-1, the rest from shared memory) in ONE coalesced store
+                    bool st = live && ca == 0;
+                    if (lane >= R && lane < D) { hval = nr_sh[(lane - R) * 16 + gg]; st = true; }
+                    if (st) p.obs_host0[(size_t)ee * D + lane] = hval;
                 }
             }
             __syncwarp();

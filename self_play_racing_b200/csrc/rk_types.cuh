@@ -88,6 +88,9 @@ struct StepParams {
     uint64_t seed;
     // reset-only
     const uint8_t* reset_mask;
+    float* obs_host0;  // optional: car 0's observation block [E, D] in mapped pinned HOST memory; each warp then also
+                       // writes the complete row there with one coalesced store, so that the rows cross PCIe
+                       // while the kernel is still running (culled queries, A <= 2, A*R <= 32 only)
     int32_t mode;  // 0 = step, 1 = reset(mask), 2 = observe only
 };
 

@@ -18,6 +18,8 @@ whose inference is one fused kernel over all environments.
 """
 from __future__ import annotations
 
+import os as _os
+
 import numpy as np
 import torch
 
@@ -170,7 +172,7 @@ class BatchedRacingVecEnv:
                                       actions=self._h_actions.data_ptr(), obs=self._h_obs.data_ptr(),
                                       arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
                                       arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
-                                      reserved0=0, opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
+                                      reserved0=int(_os.environ.get('RK_B200_ZEROCOPY_OBS', '1')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
