@@ -18,7 +18,7 @@ whose inference is one fused kernel over all environments.
 """
 from __future__ import annotations
 
-import os as _os
+import os
 
 import numpy as np
 import torch
@@ -110,7 +110,6 @@ class BatchedRacingVecEnv:
         self._specs = None
         # env e runs on track e % n_tracks; RK_B200_BLOCKED=1 assigns contiguous
         # blocks of environments to each track instead (what the opt-in staged launch prefers)
-        import os
         if os.environ.get('RK_B200_BLOCKED') == '1':
             self.env_to_track = (np.arange(self.num_envs, dtype=np.int64) * n_tracks // self.num_envs).astype(np.int32)
         else:
@@ -158,21 +157,19 @@ class BatchedRacingVecEnv:
         # B200 (profiles/r01_e2e_pipeline.log) the extra launches cost more than the overlap wins at
         # 65,536 envs, so the default is a single chunk.
         if self.pipeline_chunks is None:
-            import os
             self.pipeline_chunks = int(os.environ.get('RK_B200_PIPELINE_CHUNKS', 1))
         self._streams = [torch.cuda.Stream(device=be.device) for _ in range(self.pipeline_chunks)] \
             if self.pipeline_chunks > 1 else []
         # default Gymnasium-face path: one C call per step with host buffers (rk_step_host), the batch cut
         # into `host_chunks` ranges so that copies overlap kernels; 0 falls back to the torch-level path
         import ctypes as C
-        import os as _os
         from .. import _lib
-        self.host_chunks = int(_os.environ.get('RK_B200_HOST_CHUNKS', 4 if E >= 16384 else 1))
+        self.host_chunks = int(os.environ.get('RK_B200_HOST_CHUNKS', 4 if E >= 16384 else 1))
         self._host_io = _lib.RkHostIO(struct_size=C.sizeof(_lib.RkHostIO), n_chunks=max(self.host_chunks, 1),
                                       actions=self._h_actions.data_ptr(), obs=self._h_obs.data_ptr(),
                                       arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
                                       arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
-                                      reserved0=int(_os.environ.get('RK_B200_ZEROCOPY_OBS', '1')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
+                                      reserved0=int(os.environ.get('RK_B200_ZEROCOPY_OBS', '1')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
