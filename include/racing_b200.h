@@ -165,7 +165,9 @@ typedef struct rk_host_io {
     int32_t reserved0;            /* bit 0: zero-copy observations -- if `obs` is pinned (mapped) host memory the step
                                    * kernel writes car 0's complete rows straight into it (one coalesced store per
                                    * environment) and no device->host copy of the observations follows; culled
-                                   * queries, num_agents <= 2, num_agents * num_sensors <= 32; ignored otherwise */
+                                   * queries, num_agents <= 2, num_agents * num_sensors <= 32; ignored otherwise.
+                                   * bit 1 (with bit 0): the same for the small per-environment results -- stores
+                                   * that fall into arena_dev are mirrored into a pinned arena_host, no copy follows */
     const float* opponent_params; /* device, packed Agent (see rk_policy_act) or NULL = uniform Box samples */
     uint64_t seed, counter;       /* Philox stream of the opponent's sampling                    */
 } rk_host_io;

@@ -469,6 +469,21 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
             cudaGetLastError();
         }
     }
+    // the small per-environment results (rewards, flags, episode statistics) take the same route when the host
+    // arena is pinned: the kernel mirrors every store that falls into the device arena at the same offset there
+    bool zero_copy_arena = false;
+    if (zero_copy && (host->reserved0 & 2) && host->arena_host && host->arena_dev && host->arena_bytes > 0) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host->arena_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer) {
+            p.arena_lo = static_cast<const char*>(host->arena_dev);
+            p.arena_hi = p.arena_lo + host->arena_bytes;
+            p.arena_delta = (long long)(static_cast<const char*>(attr.devicePointer) - p.arena_lo);
+            zero_copy_arena = p.arena_delta != 0;
+        } else {
+            cudaGetLastError();
+        }
+    }
     const int n = host->n_chunks < 1 ? 1 : (host->n_chunks > 8 ? 8 : host->n_chunks);
     cudaSetDevice(h->cfg.device);
     for (int c = 0; c < n; ++c)
@@ -507,7 +522,7 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
     }
     cudaStream_t last = h->hstream[n - 1];
     for (int c = 0; c < n - 1; ++c) H_CUDA(h, cudaStreamWaitEvent(last, h->hevent[c], 0));
-    if (host->arena_host && host->arena_dev && host->arena_bytes > 0)
+    if (!zero_copy_arena && host->arena_host && host->arena_dev && host->arena_bytes > 0)
         H_CUDA(h, cudaMemcpyAsync(host->arena_host, host->arena_dev, (size_t)host->arena_bytes, cudaMemcpyDeviceToHost, last));
     H_CUDA(h, cudaStreamSynchronize(last));
     return 0;

@@ -103,6 +103,16 @@ struct CullView {
     float2* dir32;                // [A*R]
     unsigned short* list;         // [kListCap]
 };
+// store of a per-environment result; mirrored into the caller's pinned host arena when zero-copy is on (consecutive
+// environments are consecutive lanes, so a warp's stores form one PCIe-friendly run)
+template <typename T>
+__device__ __forceinline__ void out_store(const StepParams& p, T* ptr, size_t i, T v) {
+    ptr[i] = v;
+    if (p.arena_delta != 0) {
+        char* q = reinterpret_cast<char*>(ptr + i);
+        if (q >= p.arena_lo && q < p.arena_hi) *reinterpret_cast<T*>(q + p.arena_delta) = v;
+    }
+}
 __host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
     return (sizeof(CarS) + (size_t)A * R * (16 + 8 + 8) + kListCap * 2 + 15) / 16 * 16;
 }
@@ -753,18 +763,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
             const int el = p.st.ep_length[e] + 1;
             p.st.ep_return[e] = er;
             p.st.ep_length[e] = el;
-            if (p.io.ep_mask) p.io.ep_mask[e] = ended;
-            if (p.io.ep_return) p.io.ep_return[e] = ended ? er : 0.0;
-            if (p.io.ep_length) p.io.ep_length[e] = ended ? el : 0;
+            if (p.io.ep_mask) out_store(p, p.io.ep_mask, (size_t)e, (uint8_t)ended);
+            if (p.io.ep_return) out_store(p, p.io.ep_return, (size_t)e, ended ? er : 0.0);
+            if (p.io.ep_length) out_store(p, p.io.ep_length, (size_t)e, (int32_t)(ended ? el : 0));
             if (p.io.ep_stats && ended) {
                 atomicAdd(p.io.ep_stats + 0, er);
                 atomicAdd(p.io.ep_stats + 1, (double)el);
                 atomicAdd(p.io.ep_stats + 2, 1.0);
             }
         } else {
-            if (p.io.ep_mask) p.io.ep_mask[e] = 0;
-            if (p.io.ep_return) p.io.ep_return[e] = 0.0;
-            if (p.io.ep_length) p.io.ep_length[e] = 0;
+            if (p.io.ep_mask) out_store(p, p.io.ep_mask, (size_t)e, (uint8_t)0);
+            if (p.io.ep_return) out_store(p, p.io.ep_return, (size_t)e, 0.0);
+            if (p.io.ep_length) out_store(p, p.io.ep_length, (size_t)e, (int32_t)0);
         }
     }
     // per-car info of the step itself (before any same-step reset)
@@ -821,10 +831,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     if (p.mode == 0 && is_car) {
         const double r = stepping ? reward : 0.0;
         if (p.io.reward_f32) p.io.reward_f32[ci] = (float)r;
-        if (p.io.reward_f64) p.io.reward_f64[ci] = r;
+        if (p.io.reward_f64) out_store(p, p.io.reward_f64, (size_t)ci, r);
         if (a == 0) {
-            p.io.terminated[e] = terminated;
-            p.io.truncated[e] = truncated;
+            out_store(p, p.io.terminated, (size_t)e, (uint8_t)terminated);
+            out_store(p, p.io.truncated, (size_t)e, (uint8_t)truncated);
             if (p.io.done) p.io.done[e] = ended;
             if (p.io.done_f32) p.io.done_f32[e] = ended ? 1.f : 0.f;
         }

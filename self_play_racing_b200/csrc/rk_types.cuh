@@ -88,6 +88,10 @@ struct StepParams {
     uint64_t seed;
     // reset-only
     const uint8_t* reset_mask;
+    // optional zero-copy of the small per-environment results: stores that land in [arena_lo, arena_hi) are mirrored
+    // at +arena_delta bytes (the caller's pinned host arena, same layout)
+    const char *arena_lo, *arena_hi;
+    long long arena_delta;
     float* obs_host0;  // optional: car 0's observation block [E, D] in mapped pinned HOST memory; each warp then also
                        // writes the complete row there with one coalesced store, so that the rows cross PCIe
                        // while the kernel is still running (culled queries, A <= 2, A*R <= 32 only)
