@@ -433,7 +433,10 @@ def main():
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         e2e = {'value': E * A * args.steps * world / float(tw.item()), 'unit': 'agent-steps/s',
                'h2d_bytes_per_step': int(vec.h2d_bytes_per_step), 'd2h_bytes_per_step': int(vec.d2h_bytes_per_step),
-               'ms_per_step': 1e3 * float(tw.item()) / args.steps}
+               'ms_per_step': 1e3 * float(tw.item()) / args.steps,
+               'transfer': ('the step kernel reads the actions from and writes the results into the pinned host buffers '
+                            '(zero-copy over PCIe, same bytes)' if getattr(vec, 'host_chunks', 0) > 0 and
+                            int(os.environ.get('RK_B200_ZEROCOPY_OBS', '7')) & 1 else 'cudaMemcpyAsync from/to pinned host buffers')}
 
     ppo = None
     if args.ppo_updates > 0 and wl['selfplay']:

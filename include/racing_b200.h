@@ -167,7 +167,9 @@ typedef struct rk_host_io {
                                    * environment) and no device->host copy of the observations follows; culled
                                    * queries, num_agents <= 2, num_agents * num_sensors <= 32; ignored otherwise.
                                    * bit 1 (with bit 0): the same for the small per-environment results -- stores
-                                   * that fall into arena_dev are mirrored into a pinned arena_host, no copy follows */
+                                   * that fall into arena_dev are mirrored into a pinned arena_host, no copy follows;
+                                   * bit 2 (with bit 0): car 0's actions are read by the kernel from a pinned
+                                   * `actions` buffer (and written through to the device array), no copy precedes */
     const float* opponent_params; /* device, packed Agent (see rk_policy_act) or NULL = uniform Box samples */
     uint64_t seed, counter;       /* Philox stream of the opponent's sampling                    */
 } rk_host_io;

@@ -471,6 +471,18 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
     }
     // the small per-environment results (rewards, flags, episode statistics) take the same route when the host
     // arena is pinned: the kernel mirrors every store that falls into the device arena at the same offset there
+    // ... and car 0's actions are read by the kernel straight from the caller's pinned buffer (bit 2)
+    bool zero_copy_act = false;
+    if (zero_copy && (host->reserved0 & 4)) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, host->actions) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer && (reinterpret_cast<uintptr_t>(attr.devicePointer) & 7u) == 0) {
+            p.act_host0 = static_cast<const float*>(attr.devicePointer);
+            zero_copy_act = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     bool zero_copy_arena = false;
     if (zero_copy && (host->reserved0 & 2) && host->arena_host && host->arena_dev && host->arena_bytes > 0) {
         cudaPointerAttributes attr;
@@ -498,8 +510,9 @@ int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void
         const int lo = (int)((int64_t)E * c / n), hi = (int)((int64_t)E * (c + 1) / n), m = hi - lo;
         if (m <= 0) continue;
         H_CUDA(h, cudaStreamWaitEvent(st, h->hevent[8], 0));
-        H_CUDA(h, cudaMemcpyAsync(dev_act + 2 * (size_t)lo, host->actions + 2 * (size_t)lo, (size_t)m * 2 * sizeof(float),
-                                  cudaMemcpyHostToDevice, st));
+        if (!zero_copy_act)
+            H_CUDA(h, cudaMemcpyAsync(dev_act + 2 * (size_t)lo, host->actions + 2 * (size_t)lo, (size_t)m * 2 * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
         if (host->selfplay) {  // car 1: obs block [E + lo, E + hi), action block likewise (agent-major)
             if (launch_policy_act(host->opponent_params, D, io->obs + ((size_t)E + lo) * D, D, m, host->seed,
                                   host->counter * 64 + (uint64_t)c, dev_act + 2 * ((size_t)E + lo), 2, nullptr, nullptr,

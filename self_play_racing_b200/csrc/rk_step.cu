@@ -565,8 +565,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     if (p.mode == 0) {
         // ---- D: vehicle dynamics (car.py:45-80) ---------------------------------
         const bool moving = stepping && !(flags & F_CRASHED);  // car.py:51-52
+        // (zero-copy host face: car 0's pair comes straight from the caller's pinned buffer, 8 coalesced bytes per env,
+        //  and is written through so that the device array stays current -- also for envs that ignore it this step)
+        float2 av = make_float2(0.f, 0.f);
+        if (p.act_host0 != nullptr && is_car && a == 0) {
+            av = *reinterpret_cast<const float2*>(p.act_host0 + 2 * (size_t)e);
+            *reinterpret_cast<float2*>(const_cast<float*>(p.io.actions) + 2 * ci) = av;
+        } else if (stepping) {
+            av = *reinterpret_cast<const float2*>(p.io.actions + 2 * ci);
+        }
         if (stepping) {
-            const float a0 = p.io.actions[2 * ci], a1 = p.io.actions[2 * ci + 1];
+            const float a0 = av.x, a1 = av.y;
             const float steer_f = fminf(fmaxf(a0, -1.f), 1.f);  // racing_env.py:106
             float thr_f;
             if (KIND == RK_ENV_SINGLE)

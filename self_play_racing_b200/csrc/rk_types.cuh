@@ -92,6 +92,7 @@ struct StepParams {
     // at +arena_delta bytes (the caller's pinned host arena, same layout)
     const char *arena_lo, *arena_hi;
     long long arena_delta;
+    const float* act_host0;  // optional: car 0's actions [E, 2] read straight from mapped pinned host memory
     float* obs_host0;  // optional: car 0's observation block [E, D] in mapped pinned HOST memory; each warp then also
                        // writes the complete row there with one coalesced store, so that the rows cross PCIe
                        // while the kernel is still running (culled queries, A <= 2, A*R <= 32 only)

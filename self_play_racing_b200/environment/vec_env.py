@@ -169,7 +169,7 @@ class BatchedRacingVecEnv:
                                       actions=self._h_actions.data_ptr(), obs=self._h_obs.data_ptr(),
                                       arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
                                       arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
-                                      reserved0=int(os.environ.get('RK_B200_ZEROCOPY_OBS', '3')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
+                                      reserved0=int(os.environ.get('RK_B200_ZEROCOPY_OBS', '7')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
