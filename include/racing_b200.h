@@ -177,6 +177,10 @@ RK_API int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* hos
 
 /* RacingEnv.speed_weight (racing_env.py:26; annealed by agent/ppo.py:256-258) */
 RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
+/* Re-key the Philox stream of the start-grid shuffles (rk_config::seed); what `reset(seed=...)` of the vector
+ * env forwards (gymnasium call site agent/ppo.py:230; the reference's envs draw the shuffle from the global
+ * np.random stream, multi_racing_env.py:127-128). */
+RK_API int rk_set_seed(rk_handle h, uint64_t seed);
 
 /* parity harness: raw state.  host_car_f64 [E,A,6] = x, y, angle, vx, vy,
  * last_steering; host_car_i32 [E,A,4] = progress_idx, last_progress_idx, flags

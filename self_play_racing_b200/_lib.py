@@ -85,6 +85,7 @@ SIGNATURES = {
     'rk_step': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.c_void_p]),
     'rk_step_host': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.POINTER(RkHostIO), C.c_void_p]),
     'rk_set_speed_weight': (C.c_int, [C.c_void_p, C.c_double]),
+    'rk_set_seed': (C.c_int, [C.c_void_p, C.c_uint64]),
     'rk_get_state': (C.c_int, [C.c_void_p] * 5),
     'rk_set_state': (C.c_int, [C.c_void_p] * 5),
     'rk_observe': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

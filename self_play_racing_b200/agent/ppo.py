@@ -216,6 +216,12 @@ class PPO:
         self.query = query
         self.world = torch.distributed.get_world_size() if _dist_ready() else 1
         self.rank = torch.distributed.get_rank() if _dist_ready() else 0
+        n_batch = config['num_envs'] * config['num_steps']
+        if n_batch % config['num_minibatches'] != 0:
+            # the reference's `range(0, batch_size, minibatch_size)` (agent/ppo.py:169) would run a final, smaller
+            # minibatch; the captured update works on equal minibatches, so such a shape is rejected, not truncated
+            raise ValueError(f"num_envs * num_steps = {n_batch} must be divisible by num_minibatches = "
+                             f"{config['num_minibatches']} (equal minibatches only)")
         self.envs = self._make_vec_env(env_fn)
         random.seed(config['seed'])
         np.random.seed(config['seed'])

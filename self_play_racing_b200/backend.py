@@ -198,6 +198,9 @@ class RacingBackend:
     def set_speed_weight(self, w):
         _lib.check(self.lib.rk_set_speed_weight(self.h, float(w)), self.h, 'set_speed_weight')
 
+    def set_seed(self, seed):
+        _lib.check(self.lib.rk_set_seed(self.h, int(seed) & (2 ** 64 - 1)), self.h, 'set_seed')
+
     def get_state(self):
         E, A = self.E, self.A
         car_f = np.zeros((E, A, 6))

@@ -29,6 +29,14 @@ const double* pool_ctrl(const PoolBuffers* p);
 static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static std::atomic<uint64_t> g_attr_done[4];   // bit d of slot s: attribute set on device d
+bool first_use_on_device(int slot) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const uint64_t bit = 1ull << dev;
+    return (g_attr_done[slot & 3].fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 }  // namespace rk
 
 using namespace rk;
@@ -436,8 +444,22 @@ int rk_step(rk_handle h, const rk_step_io* io, void* stream) {
     return 0;
 }
 
+static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream);
+
 int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream) {
     if (!h) return 1;
+    const int rc = step_host_impl(h, io, host, caller_stream);
+    if (rc) {
+        // an error after work was queued on the internal streams: drain them, so that the caller may free or
+        // reuse its buffers as soon as the call has returned (the error text in h->err is kept)
+        for (cudaStream_t st : h->hstream)
+            if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream) {
     if (!io || io->struct_size != (int32_t)sizeof(rk_step_io) || !host ||
         host->struct_size != (int32_t)sizeof(rk_host_io)) {
         snprintf(h->err, sizeof(h->err), "rk_step_host: bad io structs (struct_size mismatch)");
@@ -562,6 +584,12 @@ int rk_observe(rk_handle h, float* dev_obs, int32_t layout, void* stream) {
 int rk_set_speed_weight(rk_handle h, double w) {
     if (!h) return 1;
     h->cfg.speed_weight = w;
+    return 0;
+}
+
+int rk_set_seed(rk_handle h, uint64_t seed) {
+    if (!h) return 1;
+    h->cfg.seed = seed;
     return 0;
 }
 

@@ -356,11 +356,8 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
     if ((reinterpret_cast<uintptr_t>(params) & 15u) != 0) return 2;  // the bulk copy needs a 16-byte aligned source
     if (block_policy != nullptr && (block_len <= 0 || block_len % kPolicyCols != 0 || (pool_stride & 3) != 0)) return 2;
     const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(0))  // the attribute is per device, not per process
         cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     policy_act_kernel<<<(B + kPolicyCols - 1) / kPolicyCols, kPolicyThreads, smem, stream>>>(
         params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean, block_policy,
         block_len, pool_stride);

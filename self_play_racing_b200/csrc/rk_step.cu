@@ -894,14 +894,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         }
     }
 
-    // zero-copy rows: S.vx / S.vy are dead from here on; they become the per-environment store of car 0's non-ray
-    // values ([8][16] floats), picked up by the lanes that write the complete host row after the raycast
+    // zero-copy rows: S.vx / S.vy are dead from here on; their 128 floats become the per-environment store of car 0's
+    // 4A non-ray values ([4A][32/A] floats: 4 x 32 single-car, 8 x 16 two-car), picked up by the lanes that write the
+    // complete host row after the raycast
     float* nr_sh = reinterpret_cast<float*>(S.vx);
+    const int nr_stride = 32 / A;   // >= epw
     if (p.obs_host0 != nullptr) {
         __syncwarp();   // every lane has finished reading S.vx / S.vy
         if (want_obs && a == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) nr_sh[k * 16 + g] = nrv[k];
+            for (int k = 0; k < 8; ++k)
+                if (k < 4 * A) nr_sh[k * nr_stride + g] = nrv[k];
         }
         __syncwarp();
     }
@@ -986,7 +989,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (p.obs_host0 != nullptr) {
                     // the complete row of car 0 (rays from lanes 0..R-1, the rest from shared memory) in ONE coalesced store
                     bool st = live && ca == 0;
-                    if (lane >= R && lane < D) { hval = nr_sh[(lane - R) * 16 + gg]; st = true; }
+                    if (lane >= R && lane < D) { hval = nr_sh[(lane - R) * nr_stride + gg]; st = true; }
                     if (st) p.obs_host0[(size_t)ee * D + lane] = hval;
                 }
             }

@@ -1125,18 +1125,12 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     g.partial = reinterpret_cast<float*>(g.kl_partial + ((ncta + 1) & ~1));
     if ((size_t)((ncta + 1) & ~1) * sizeof(double) + 2 * (size_t)ncta * kNetStride * sizeof(float) > io.workspace_bytes) return 3;
     const size_t smem = kTrainSmemFloats * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(1))  // the attribute is per device, not per process
         cudaFuncSetAttribute(ppo_mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     if (io.tensor_cores) {
         const size_t smem_tc = kTrainTcSmemFloats * sizeof(float);
-        static bool tc_attr_set = false;
-        if (!tc_attr_set) {
+        if (first_use_on_device(2))
             cudaFuncSetAttribute(ppo_mlp_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
-            tc_attr_set = true;
-        }
         ppo_mlp_grad_tc_kernel<<<dim3(ncta, 2), kNT2, smem_tc, stream>>>(g);
     } else {
         ppo_mlp_grad_kernel<<<dim3(ncta, 2), kNT, smem, stream>>>(g);

@@ -120,6 +120,9 @@ __host__ __device__ inline double u01d(uint32_t hi, uint32_t lo) {
 
 // launch bookkeeping (rk_launch_count)
 void count_launch(int n = 1);
+// true exactly once per (kernel slot, current device): function attributes such as the dynamic shared-memory
+// limit are per device, so a process that drives several GPUs must set them on each
+bool first_use_on_device(int slot);
 
 // host-side launchers implemented in the .cu files
 int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t stream);

@@ -176,8 +176,12 @@ class BatchedRacingVecEnv:
     # ---- reference-facing attributes ------------------------------------------
     @property
     def envs(self):
-        specs = self._specs or [None] * self.num_envs
-        return [_EnvProxy(self, i, s) for i, s in enumerate(specs)]
+        # built once: reference-style loops `for i in range(num_envs): setattr(vec.envs[i], ...)`
+        # (agent/ppo.py:256-258) would otherwise create E proxies per access
+        if getattr(self, '_proxies', None) is None:
+            specs = self._specs or [None] * self.num_envs
+            self._proxies = [_EnvProxy(self, i, s) for i, s in enumerate(specs)]
+        return self._proxies
 
     @property
     def speed_weight(self):
@@ -222,6 +226,10 @@ class BatchedRacingVecEnv:
             else:
                 flats.append(flatten_agent(pol.state_dict() if hasattr(pol, 'state_dict') else pol))
         pool = torch.stack([f.to(self.be.device, torch.float32) for f in flats]).contiguous()
+        from ..backend import POLICY_BLOCK
+        if block_len <= 0 or block_len % POLICY_BLOCK != 0:
+            raise ValueError(f'set_opponents: block_len must be a positive multiple of {POLICY_BLOCK} '
+                             f'(one inference CTA serves {POLICY_BLOCK} consecutive environments), got {block_len}')
         n_blocks = (self.num_envs + block_len - 1) // block_len
         if block_policy is None:
             rs = np.random.RandomState(self.seed if seed is None else seed)
@@ -290,9 +298,21 @@ class BatchedRacingVecEnv:
 
     # ---- Gymnasium face ------------------------------------------------------------
     def reset(self, seed=None, options=None):
+        """SyncVectorEnv.reset.  `seed` re-keys the Philox stream of the start-grid shuffles (the
+        reference's envs ignore their seed -- RacingEnv.reset only forwards it to gym.Env, and the grid
+        shuffle reads the global np.random stream -- so any value is accepted and none changes the
+        single-car envs); `options` must be empty."""
+        if options:
+            raise ValueError('BatchedRacingVecEnv.reset: options are not supported')
+        if seed is not None:
+            if isinstance(seed, (list, tuple, np.ndarray)):
+                seed = int(np.asarray(seed).reshape(-1)[0])
+            self.be.set_seed(int(seed))
         obs = self.reset_device()
         self._h_obs.copy_(obs, non_blocking=True)
         torch.cuda.current_stream(self.be.device).synchronize()
+        import time
+        self._t_reset, self._ep_t0 = time.perf_counter(), None
         out = self._h_obs.numpy()
         return (out.copy() if self.copy else out), {}
 
@@ -323,8 +343,17 @@ class BatchedRacingVecEnv:
             term = term | trunc
         infos = {}
         if self._np_ep_mask.any():
-            infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy()}
-            infos['_episode'] = self._np_ep_mask.copy()
+            # RecordEpisodeStatistics' keys: return, length and elapsed wall time of the episode ('t' is measured
+            # from the environment's previous reset on the host clock, as the wrapper does)
+            import time
+            now = time.perf_counter()
+            mask = self._np_ep_mask.copy()
+            if getattr(self, '_ep_t0', None) is None:
+                self._ep_t0 = np.full(self.num_envs, getattr(self, '_t_reset', now))
+            t = np.where(mask, np.round(now - self._ep_t0, 6), 0.0)
+            self._ep_t0[mask] = now
+            infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy(), 't': t}
+            infos['_episode'] = mask
         if self.copy:
             return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
         return obs, rew, term, trunc, infos

@@ -17,6 +17,7 @@ torch = pytest.importorskip('torch')
 pytestmark = pytest.mark.gpu
 
 from oracle import racing_oracle as O  # noqa: E402
+from tests import _finish_line as FL  # noqa: E402
 
 
 @pytest.fixture(scope='module')
@@ -90,10 +91,14 @@ def test_generated_tracks_are_valid(B):
 
 # ------------------------------------------------- golden trajectories (reference)
 @pytest.mark.parametrize('query', QUERY_MODES)
-@pytest.mark.parametrize('name', ['single_default_10k', 'single_proc0', 'single_proc1', 'single_proc2', 'single_proc3'])
+@pytest.mark.parametrize('name', ['single_default_10k', 'single_proc0', 'single_proc1', 'single_proc2', 'single_proc3',
+                                  'single_laps_default', 'single_laps_proc1'])
 def test_single_env_golden(B, golden, name, query):
     """BASELINE config 1: lock-step with the reference over a free-running
-    trajectory (10k steps on the default track), identical actions."""
+    trajectory (10k steps on the default track), identical actions.  The *_laps_*
+    recordings are driven by a pure-pursuit script and run the whole reward state
+    machine: checkpoints, finish + time bonus, both wraps, 3000-step truncation
+    (racing_env.py:112-162)."""
     g = golden(name)
     be = B.RacingBackend(1, kind='single', num_sensors=11, query=query)
     be.set_tracks_from_waypoints([g['waypoints']], [float(g['width'])])
@@ -107,12 +112,13 @@ def test_single_env_golden(B, golden, name, query):
     TRUNC = torch.zeros(n, dtype=torch.uint8, device='cuda')
     ST = torch.zeros(n, 4, dtype=torch.float64, device='cuda')
     PIDX = torch.zeros(n, dtype=torch.int32, device='cuda')
+    INFO = torch.zeros(n, 4, dtype=torch.int32, device='cuda')
     for k in range(n):
         be.actions[0, 0].copy_(acts[k])
         be.step()
         OBS[k] = be.obs[0, 0]; REW[k] = be.reward64[0, 0]
         TERM[k] = be.terminated[0]; TRUNC[k] = be.truncated[0]
-        ST[k, :2] = be.info_f64[0, 0, :2]; PIDX[k] = be.info_i32[0, 0, 3]
+        ST[k, :2] = be.info_f64[0, 0, :2]; PIDX[k] = be.info_i32[0, 0, 3]; INFO[k] = be.info_i32[0, 0]
     np.testing.assert_array_equal(TERM.cpu().numpy().astype(bool), g['terminated'])
     np.testing.assert_array_equal(TRUNC.cpu().numpy().astype(bool), g['truncated'])
     np.testing.assert_allclose(OBS.cpu().numpy(), g['obs'], rtol=0, atol=OBS_ATOL)
@@ -121,12 +127,21 @@ def test_single_env_golden(B, golden, name, query):
     prev_done = np.concatenate([[False], (g['terminated'] | g['truncated'])[:-1]])
     np.testing.assert_allclose(ST.cpu().numpy()[~prev_done, :2], g['state'][~prev_done, :2], rtol=0, atol=STATE_ATOL)
     np.testing.assert_array_equal(PIDX.cpu().numpy()[~prev_done], g['progress_idx'][~prev_done])
+    if 'finished' in g:   # scripted-driver recordings: the finish line was crossed, a crawl was truncated
+        info = INFO.cpu().numpy()
+        np.testing.assert_array_equal(info[~prev_done, 0].astype(bool), g['crashed'][~prev_done])
+        np.testing.assert_array_equal(info[~prev_done, 1].astype(bool), g['finished'][~prev_done])
+        assert g['finished'].sum() >= 3 and (g['truncated'] & ~g['terminated']).sum() >= 1
     be.close()
 
 
 @pytest.mark.parametrize('query', QUERY_MODES)
-@pytest.mark.parametrize('name,A', [('multi2_default', 2), ('multi2_proc1', 2), ('multi2_proc2', 2), ('multi3_proc2', 3)])
+@pytest.mark.parametrize('name,A', [('multi2_default', 2), ('multi2_proc1', 2), ('multi2_proc2', 2), ('multi3_proc2', 3),
+                                    ('multi2_laps_default', 2), ('multi2_laps_proc2', 2), ('multi3_laps_proc1', 3)])
 def test_multi_env_golden(B, golden, name, A, query):
+    """Free-running against the reference's recordings.  The *_laps_* files hold laps driven by a
+    pure-pursuit script: checkpoints, finish + time bonus, finished_step-driven placement, +250 on
+    termination and truncation, wraps, cars bumping (multi_racing_env.py:155-211,222-259)."""
     g = golden(name)
     trk = O.TrackTables(g['control_points'], float(g['width']))
     be = B.RacingBackend(1, kind='multi', num_agents=A, num_sensors=11, query=query)
@@ -158,6 +173,9 @@ def test_multi_env_golden(B, golden, name, A, query):
     prev_done = np.concatenate([[False], ended[:-1]])
     np.testing.assert_array_equal(info[~prev_done, :, 0].astype(bool), g['flags'][~prev_done, :, 0])
     np.testing.assert_array_equal(info[~prev_done, :, 1].astype(bool), g['flags'][~prev_done, :, 1])
+    if 'progress_idx' in g:
+        np.testing.assert_array_equal(info[~prev_done, :, 3], g['progress_idx'][~prev_done])
+        assert g['flags'][..., 1].any() and (g['placement'] == 1).sum() == ended.sum()
     be.close()
 
 
@@ -502,3 +520,68 @@ def test_extreme_track_shapes(B):
             np.testing.assert_allclose(be.obs.cpu().numpy(), oobs, rtol=0, atol=OBS_ATOL, err_msg=f'step {k}')
             np.testing.assert_allclose(be.reward64.cpu().numpy(), orew, rtol=0, atol=STATE_ATOL, err_msg=f'step {k}')
         be.close()
+
+
+# ------------------------------------------------ injected states: one reward/termination branch each
+@pytest.mark.parametrize('query', QUERY_MODES)
+def test_injected_single_branches(B, golden, query):
+    """Hand-built states (rk_set_state) recorded on the unmodified reference: finish + time bonus and
+    its floor, finish on the truncation step, both wraps with and without checkpoints, checkpoint order
+    and upper edges, crash on the truncation step, speed clamp (racing_env.py:112-162)."""
+    g = golden('injected_single')
+    S = len(g['names'])
+    be = B.RacingBackend(S, kind='single', num_sensors=11, query=query)
+    be.set_tracks_from_waypoints([g['waypoints']], [float(g['width'])])
+    be.reset()
+    car_f, car_i, env_i = FL.backend_state_single(g)
+    be.set_state(car_f64=car_f, car_i32=car_i, env_i32=env_i, env_f64=np.zeros(S))
+    for t in range(g['actions'].shape[0]):
+        be.actions[:, 0].copy_(torch.from_numpy(g['actions'][t]))
+        be.step()
+        names = [f'{n} (step {t})' for n in g['names']]
+        np.testing.assert_array_equal(be.terminated.cpu().numpy().astype(bool), g['terminated'][t], err_msg=str(names))
+        np.testing.assert_array_equal(be.truncated.cpu().numpy().astype(bool), g['truncated'][t])
+        np.testing.assert_allclose(be.obs[:, 0].cpu().numpy(), g['obs'][t], rtol=0, atol=OBS_ATOL)
+        np.testing.assert_allclose(be.reward64[:, 0].cpu().numpy(), g['reward'][t], rtol=0, atol=STATE_ATOL)
+        st, sti = _state(be)
+        ended_before = (g['terminated'][t - 1] | g['truncated'][t - 1]) if t else np.zeros(S, bool)
+        np.testing.assert_allclose(st[:, 0], g['state'][t], rtol=0, atol=STATE_ATOL)
+        np.testing.assert_array_equal(sti[:, 0, 0], g['progress_idx'][t])
+        fl = sti[:, 0, 2]
+        np.testing.assert_array_equal((fl & FL.F_FINISHED) != 0, g['finished'][t])
+        np.testing.assert_array_equal((fl & FL.F_CRASHED) != 0, g['crashed'][t])
+        np.testing.assert_array_equal(np.stack([(fl & m) != 0 for m in (FL.F_CP25, FL.F_CP50, FL.F_CP75)], 1), g['checkpoints'][t])
+        if t == 0:
+            np.testing.assert_allclose(be.info_f64[:, 0, 3].cpu().numpy(), g['info_progress'][t], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(be.info_f64[:, 0, 4].cpu().numpy(), g['info_delta'][t], rtol=0, atol=1e-12)
+        del ended_before
+    be.close()
+
+
+@pytest.mark.parametrize('query', QUERY_MODES)
+def test_injected_multi_branches(B, golden, query):
+    """Placement with exact ties (higher index wins), +250 on truncation and on termination, finished_step,
+    finish against a crashed car, all-crashed termination, -160 only once, checkpoints collected by a
+    crashed car, touching penalty (multi_racing_env.py:155-211,222-259)."""
+    g = golden('injected_multi2')
+    S = len(g['names'])
+    be = B.RacingBackend(S, kind='multi', num_agents=2, num_sensors=11, query=query)
+    be.set_tracks_from_waypoints([g['waypoints']], [float(g['width'])])
+    be.reset(start_slot=torch.from_numpy(np.tile([0, 1], (S, 1)).astype(np.int32)).cuda())
+    car_f, car_i, env_i = FL.backend_state_multi(g)
+    be.set_state(car_f64=car_f, car_i32=car_i, env_i32=env_i, env_f64=np.zeros(S))
+    for t in range(g['actions'].shape[0]):
+        be.actions.copy_(torch.from_numpy(g['actions'][t]))
+        be.step(start_slot=torch.from_numpy(g['start_order'][t].astype(np.int32)).cuda())
+        np.testing.assert_array_equal(be.terminated.cpu().numpy().astype(bool), g['terminated'][t], err_msg=str(list(g['names'])))
+        np.testing.assert_array_equal(be.truncated.cpu().numpy().astype(bool), g['truncated'][t])
+        np.testing.assert_allclose(be.obs.cpu().numpy(), g['obs'][t], rtol=0, atol=OBS_ATOL)
+        np.testing.assert_allclose(be.reward64.cpu().numpy(), g['reward'][t], rtol=0, atol=STATE_ATOL)
+        np.testing.assert_array_equal(be.info_i32[..., 2].cpu().numpy(), g['placement'][t])
+        st, sti = _state(be)
+        np.testing.assert_allclose(st, g['state'][t], rtol=0, atol=STATE_ATOL)
+        fl = sti[..., 2]
+        np.testing.assert_array_equal(np.stack([(fl & FL.F_CRASHED) != 0, (fl & FL.F_FINISHED) != 0], 2), g['flags'][t])
+        np.testing.assert_array_equal(np.stack([(fl & m) != 0 for m in (FL.F_CP25, FL.F_CP50, FL.F_CP75)], 2), g['checkpoints'][t])
+        np.testing.assert_array_equal(sti[..., 3], g['finished_step'][t])
+    be.close()

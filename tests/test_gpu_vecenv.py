@@ -518,3 +518,82 @@ def test_batched_evaluation_protocol(pkg):
     assert mres['num_episodes'] == 6
     for m in mres['all_episodes']:
         assert 1 <= m['steps'] <= 400 and ('placement' in m) and 0 <= m['progress'] <= 1
+
+
+# ------------------------------------------------ the Gymnasium face at benchmark size (zero-copy host rows)
+@pytest.mark.parametrize('kind,E', [('single', 131072), ('single', 65536 + 37), ('multi', 65536)])
+def test_gym_face_at_scale_equals_device_face(pkg, kind, E):
+    """The path bench.py times as `e2e` -- rk_step_host with host_chunks = 4, the step kernel reading the
+    actions from and writing car 0's rows into pinned host memory -- against the device-resident arrays of
+    the SAME step, and against a second batch stepped through the plain device face.  131,072 single-car
+    envs keep 32 environments per warp (the `nr_sh` scratch of the zero-copy rows is indexed by 32 / A);
+    65,536 two-car self-play envs are the benchmark's own configuration."""
+    env_mod, agent_mod, _ = pkg
+    selfplay = kind == 'multi'
+    mk = lambda: env_mod.BatchedRacingVecEnv.synthetic(kind, E, n_tracks=16, num_agents=2, num_sensors=11,
+                                                       selfplay=selfplay, seed=77, copy=True)
+    vec, ref = mk(), mk()
+    assert vec.host_chunks == 4 and vec._host_io.reserved0 == 7
+    ref.host_chunks = 0                       # torch-level path: plain copies, one launch
+    if selfplay:
+        torch.manual_seed(3)
+        opp = agent_mod.Agent(vec.single_observation_space, vec.single_action_space)
+        vec.set_opponent(opp); ref.set_opponent(opp)
+    o1, _ = vec.reset(); o2, _ = ref.reset()
+    np.testing.assert_array_equal(o1, o2)
+    rs = np.random.RandomState(0)
+    n_done = 0
+    for k in range(12):
+        a = rs.uniform(-1, 1, size=(E, 2)).astype(np.float32)
+        a[:, 1] = np.abs(a[:, 1])
+        obs, rew, term, trunc, infos = vec.step(a)
+        be = vec.be
+        # host rows == the device arrays the same kernel wrote
+        np.testing.assert_array_equal(obs, be.obs[0].cpu().numpy())
+        np.testing.assert_array_equal(rew, be.reward64[0].cpu().numpy())
+        np.testing.assert_array_equal(be.actions[0].cpu().numpy(), a)          # actions were written through
+        dterm, dtrunc = be.terminated.cpu().numpy().astype(bool), be.truncated.cpu().numpy().astype(bool)
+        np.testing.assert_array_equal(term, (dterm | dtrunc) if selfplay else dterm)
+        np.testing.assert_array_equal(trunc, dtrunc)
+        if not selfplay:
+            # ... and == an independent batch stepped through the plain path (the opponent's Philox counters differ
+            # between the chunked and the one-launch path, so the two-car batches are not comparable step by step)
+            obs2, rew2, term2, trunc2, infos2 = ref.step(a)
+            np.testing.assert_array_equal(obs, obs2)
+            np.testing.assert_array_equal(rew, rew2)
+            np.testing.assert_array_equal(term, term2)
+            assert ('episode' in infos) == ('episode' in infos2)
+            if 'episode' in infos:
+                np.testing.assert_array_equal(infos['_episode'], infos2['_episode'])
+                np.testing.assert_array_equal(infos['episode']['r'], infos2['episode']['r'])
+                np.testing.assert_array_equal(infos['episode']['l'], infos2['episode']['l'])
+                assert set(infos['episode']) == {'r', 'l', 't'}
+        n_done += int(term.sum())
+    assert np.abs(obs).max() <= 1.0 and np.isfinite(rew).all()
+    vec.close(); ref.close()
+
+
+def test_vec_env_reference_style_attribute_loop_and_seed(pkg):
+    """agent/ppo.py:256-258 writes speed_weight through `envs.envs[i]` for every i: the proxy list is built once;
+    reset(seed=...) re-keys the start-grid shuffle and is reproducible; bad opponent block lengths are rejected
+    where they are given."""
+    env_mod, agent_mod, _ = pkg
+    vec = env_mod.BatchedRacingVecEnv.synthetic('multi', 2048, n_tracks=4, selfplay=True, seed=5)
+    assert vec.envs is vec.envs and len(vec.envs) == 2048
+    for i in range(vec.num_envs):
+        setattr(vec.envs[i], 'speed_weight', 11.0)
+    assert vec.speed_weight == 11.0
+    o1, _ = vec.reset(seed=123)
+    s1 = vec.be.get_state()['car_f64'][..., :2].copy()
+    vec.reset(seed=124)
+    s2 = vec.be.get_state()['car_f64'][..., :2].copy()
+    vec.reset(seed=123)
+    s3 = vec.be.get_state()['car_f64'][..., :2].copy()
+    assert not np.array_equal(s1, s2)
+    np.testing.assert_array_equal(s1, s3)
+    with pytest.raises(ValueError, match='options'):
+        vec.reset(options={'x': 1})
+    pol = agent_mod.Agent(vec.single_observation_space, vec.single_action_space)
+    with pytest.raises(ValueError, match='multiple of 256'):
+        vec.set_opponents([pol, pol], block_len=100)
+    vec.close()
