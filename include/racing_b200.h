@@ -175,6 +175,35 @@ typedef struct rk_host_io {
 } rk_host_io;
 RK_API int rk_step_host(rk_handle h, const rk_step_io* io, const rk_host_io* host, void* caller_stream);
 
+/* A whole T-step rollout in ONE call: PPO.collect_rollout (agent/ppo.py:97-132) with the vector env's step inside,
+ * for a handle with RK_LAYOUT_AGENT_MAJOR buffers.  Per step t the library enqueues (a) one inference launch that
+ * carries the learner's Agent.get_action_and_value on obs[t][0] -> actions[t][0], logprobs[t], values[t] and, for
+ * self-play (2 cars, environment/wrappers.py:29-45), the frozen opponent's action on car 1's latest observation ->
+ * actions[t][1], and (b) the fused step kernel writing obs[t+1], rewards[t], dones[t+1] in place.  All 2T launches are
+ * issued back to back from native code on `stream`; nothing synchronises with the host.  Philox counters of step t are
+ * counter0 + t.  `base` supplies the step's remaining outputs (terminated, truncated, ep_stats, ...) exactly as for
+ * rk_step; its actions / obs / reward_f32 / done_f32 are overridden per step. */
+typedef struct rk_rollout_io {
+    int32_t struct_size;
+    int32_t T;                       /* steps                                                               */
+    int32_t selfplay;                /* != 0: car 1 is driven by the opponent (requires num_agents == 2)    */
+    int32_t block_len;               /* opponent pool: consecutive envs per pool row (multiple of RK_POLICY_BLOCK) */
+    const float* learner_params;     /* device, packed Agent (see rk_policy_act)                            */
+    const float* opponent_params;    /* device, packed Agent / pool base, or NULL = uniform Box samples     */
+    const int32_t* block_policy;     /* device int32 [ceil(E / block_len)] or NULL (single opponent)        */
+    int64_t pool_stride;             /* floats between pool rows                                            */
+    const float* opponent_obs0;      /* device [E,D]: car 1's observation for step 0, or NULL = obs[0][1]   */
+    uint64_t learner_seed, learner_counter0;
+    uint64_t opponent_seed, opponent_counter0;
+    float* obs;                      /* device [T+1,A,E,D]: slot 0 holds the learner's current observation  */
+    float* actions;                  /* device [T,A,E,2]                                                    */
+    float* logprobs;                 /* device [T,E]                                                        */
+    float* values;                   /* device [T,E]                                                        */
+    float* rewards;                  /* device [T,A,E] float32                                              */
+    float* dones;                    /* device [T+1,E] float32: slot t+1 = done after step t                */
+} rk_rollout_io;
+RK_API int rk_rollout(rk_handle h, const rk_step_io* base, const rk_rollout_io* r, void* stream);
+
 /* RacingEnv.speed_weight (racing_env.py:26; annealed by agent/ppo.py:256-258) */
 RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
 /* Re-key the Philox stream of the start-grid shuffles (rk_config::seed); what `reset(seed=...)` of the vector

@@ -66,6 +66,16 @@ class RkHostIO(C.Structure):
                 ('seed', C.c_uint64), ('counter', C.c_uint64)]
 
 
+class RkRolloutIO(C.Structure):
+    _fields_ = [('struct_size', C.c_int32), ('T', C.c_int32), ('selfplay', C.c_int32), ('block_len', C.c_int32),
+                ('learner_params', C.c_void_p), ('opponent_params', C.c_void_p), ('block_policy', C.c_void_p),
+                ('pool_stride', C.c_int64), ('opponent_obs0', C.c_void_p),
+                ('learner_seed', C.c_uint64), ('learner_counter0', C.c_uint64),
+                ('opponent_seed', C.c_uint64), ('opponent_counter0', C.c_uint64),
+                ('obs', C.c_void_p), ('actions', C.c_void_p), ('logprobs', C.c_void_p), ('values', C.c_void_p),
+                ('rewards', C.c_void_p), ('dones', C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/racing_b200.h declares
 SIGNATURES = {
     'rk_create': (C.c_int, [C.POINTER(RkConfig), C.POINTER(C.c_void_p)]),
@@ -84,6 +94,7 @@ SIGNATURES = {
     'rk_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'rk_step': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.c_void_p]),
     'rk_step_host': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.POINTER(RkHostIO), C.c_void_p]),
+    'rk_rollout': (C.c_int, [C.c_void_p, C.POINTER(RkStepIO), C.POINTER(RkRolloutIO), C.c_void_p]),
     'rk_set_speed_weight': (C.c_int, [C.c_void_p, C.c_double]),
     'rk_set_seed': (C.c_int, [C.c_void_p, C.c_uint64]),
     'rk_get_state': (C.c_int, [C.c_void_p] * 5),

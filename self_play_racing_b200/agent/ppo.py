@@ -302,10 +302,19 @@ class PPO:
         T = c['num_steps']
         params = flatten_agent(self.agent.state_dict()).to(be.device)
         be.ep_stats.zero_()
+        seed = c['seed'] * 2654435761 + self.rank
+        self.rollout_mode = 'native loop (rk_rollout: 2 launches per step)' if c.get('native_rollout', True) else \
+            'python loop (3 launches per step)'
+        if c.get('native_rollout', True):
+            # the whole loop below as one C call: launches are issued back to back from native code, learner and
+            # opponent inference share one grid ('native_rollout': False keeps the per-step Python loop)
+            envs.rollout_into(buf, params, seed, self._act_counter + 1, T)
+            self._act_counter += T
+            T = 0
         with torch.no_grad():
             for t in range(T):
                 self._act_counter += 1
-                policy_act(params, buf['obs'][t, 0], buf['actions'][t, 0], seed=c['seed'] * 2654435761 + self.rank,
+                policy_act(params, buf['obs'][t, 0], buf['actions'][t, 0], seed=seed,
                            counter=self._act_counter, logprob=buf['logprobs'][t], value=buf['values'][t])
                 envs.step_into(buf['actions'][t], buf['obs'][t + 1], buf['rewards'][t], buf['dones'][t + 1])
         n, ret, length = (float(v) for v in (be.ep_stats[2], be.ep_stats[0], be.ep_stats[1]))  # one sync per rollout

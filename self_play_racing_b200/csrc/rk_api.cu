@@ -563,6 +563,61 @@ static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* h
     return 0;
 }
 
+int rk_rollout(rk_handle h, const rk_step_io* base, const rk_rollout_io* r, void* stream_) {
+    if (!h) return 1;
+    if (!base || base->struct_size != (int32_t)sizeof(rk_step_io) || !r || r->struct_size != (int32_t)sizeof(rk_rollout_io)) {
+        snprintf(h->err, sizeof(h->err), "rk_rollout: bad io structs (struct_size mismatch)");
+        return 1;
+    }
+    const int E = h->cfg.num_envs, A = h->cfg.num_agents, D = h->D;
+    if (r->T <= 0 || !r->learner_params || !r->obs || !r->actions || !r->logprobs || !r->values || !r->rewards ||
+        !r->dones || !base->terminated || !base->truncated || base->layout != RK_LAYOUT_AGENT_MAJOR ||
+        (r->selfplay && A != 2) || (r->block_policy && !r->opponent_params)) {
+        snprintf(h->err, sizeof(h->err),
+                 "rk_rollout: needs T > 0, learner parameters, the six rollout buffers, terminated/truncated, the "
+                 "agent-major layout (and 2 cars for self-play)");
+        return 1;
+    }
+    StepParams p;
+    if (fill_params(h, p, "rk_rollout")) return 1;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    p.mode = 0;
+    p.io = *base;
+    p.io.env_begin = 0;
+    p.io.env_count = 0;
+    const size_t obs_slot = (size_t)A * E * D, act_slot = (size_t)A * E * 2, rew_slot = (size_t)A * E;
+    for (int t = 0; t < r->T; ++t) {
+        float* obs_t = r->obs + (size_t)t * obs_slot;
+        float* act_t = r->actions + (size_t)t * act_slot;
+        PolicyJobs jobs{};
+        // learner: car 0's block of the agent-major slot (agent/ppo.py:109-112)
+        jobs.job[0] = PolicyJob{r->learner_params, obs_t, D, E, r->learner_seed, r->learner_counter0 + (uint64_t)t, act_t, 2,
+                                r->logprobs + (size_t)t * E, r->values + (size_t)t * E, nullptr, nullptr, 0, 0};
+        int n_jobs = 1;
+        if (r->selfplay) {  // opponent: car 1's block (wrappers.py:30-39)
+            const float* oobs = (t == 0 && r->opponent_obs0) ? r->opponent_obs0 : obs_t + (size_t)E * D;
+            jobs.job[1] = PolicyJob{r->opponent_params, oobs, D, E, r->opponent_seed, r->opponent_counter0 + (uint64_t)t,
+                                    act_t + (size_t)E * 2, 2, nullptr, nullptr, nullptr, r->block_policy, r->block_len,
+                                    r->pool_stride};
+            n_jobs = 2;
+        }
+        if (launch_policy_jobs(jobs, n_jobs, D, stream)) {
+            snprintf(h->err, sizeof(h->err), "rk_rollout: inference launch failed at step %d: %s (parameter blocks must be "
+                     "16-byte aligned, block_len a multiple of %d)", t, cudaGetErrorString(cudaGetLastError()), RK_POLICY_BLOCK);
+            return 1;
+        }
+        p.io.actions = act_t;
+        p.io.obs = obs_t + obs_slot;
+        p.io.reward_f32 = r->rewards + (size_t)t * rew_slot;
+        p.io.done_f32 = r->dones + (size_t)(t + 1) * E;
+        if (launch_step(p, h->cfg.query_mode, h->cfg.env_kind, stream)) {
+            snprintf(h->err, sizeof(h->err), "rk_rollout: step launch failed at step %d: %s", t, cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+    }
+    return 0;
+}
+
 int rk_observe(rk_handle h, float* dev_obs, int32_t layout, void* stream) {
     if (!h) return 1;
     if (!dev_obs) {

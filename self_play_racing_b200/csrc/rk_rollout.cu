@@ -117,12 +117,36 @@ __device__ __forceinline__ void stage_obs(float* xs, const float* __restrict__ o
 // Fused Agent.get_action_and_value(obs) (agent/ppo.py:43-56).  The packed
 // parameter block arrives in shared memory through ONE bulk asynchronous copy
 // (cp.async.bulk -> mbarrier) while the threads stage their observations.
+//
+// The launch carries up to two independent jobs (blockIdx.y): the rollout runs the learner's forward pass and the
+// frozen opponent's (self_play: agent/ppo.py:109 and environment/wrappers.py:35-39 of the same step) as ONE grid, so
+// that the 256-sample CTAs of both fill the 148 SMs together.  A job without parameters draws the pool-empty
+// opponent's uniform Box actions (wrappers.py:30-32).
 __global__ void __launch_bounds__(kPolicyThreads, 2)
-policy_act_kernel(const float* __restrict__ params, int obs_dim, const float* __restrict__ obs, int64_t obs_stride,
-                  int B, uint64_t seed, uint64_t counter, float* __restrict__ action, int64_t act_stride,
-                  float* __restrict__ logprob, float* __restrict__ value, float* __restrict__ mean,
-                  const int32_t* __restrict__ block_policy, int block_len, int64_t pool_stride) {
+policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     extern __shared__ __align__(128) float sm[];
+    const PolicyJob& jb = jobs.job[blockIdx.y];
+    const int B = jb.B;
+    if (blockIdx.x * kPolicyCols >= B) return;
+    const float* __restrict__ params = jb.params;
+    const float* __restrict__ obs = jb.obs;
+    const int64_t obs_stride = jb.obs_stride, act_stride = jb.act_stride, pool_stride = jb.pool_stride;
+    const uint64_t seed = jb.seed, counter = jb.counter;
+    float* __restrict__ action = jb.action;
+    float* __restrict__ logprob = jb.logprob;
+    float* __restrict__ value = jb.value;
+    float* __restrict__ mean = jb.mean;
+    const int32_t* __restrict__ block_policy = jb.block_policy;
+    const int block_len = jb.block_len;
+    if (params == nullptr) {   // uniform Box([-1,0],[1,1]) samples, the same stream as random_act_kernel
+        for (int b = blockIdx.x * kPolicyCols + threadIdx.x; b < min(B, (int)(blockIdx.x + 1) * kPolicyCols); b += kPolicyThreads) {
+            uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x72616e64u};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            action[(size_t)b * act_stride] = 2.f * u01(c[0]) - 1.f;
+            action[(size_t)b * act_stride + 1] = u01(c[1]);
+        }
+        return;
+    }
     // a pool of stacked parameter blocks: this CTA's samples all belong to one block of `block_len` samples,
     // whose policy id selects the block it stages (self-play against several snapshots in one launch)
     if (block_policy != nullptr) params += (int64_t)block_policy[(blockIdx.x * kPolicyCols) / block_len] * pool_stride;
@@ -343,6 +367,23 @@ int launch_ppo_loss_grad(const float* mu, const float* v, const float* act, cons
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+int launch_policy_jobs(const PolicyJobs& jobs, int n_jobs, int obs_dim, cudaStream_t stream) {
+    int maxB = 0;
+    for (int k = 0; k < n_jobs; ++k) {
+        const PolicyJob& j = jobs.job[k];
+        maxB = j.B > maxB ? j.B : maxB;
+        if (j.params != nullptr && (reinterpret_cast<uintptr_t>(j.params) & 15u) != 0) return 2;  // the bulk copy needs a 16-byte aligned source
+        if (j.block_policy != nullptr && (j.block_len <= 0 || j.block_len % kPolicyCols != 0 || (j.pool_stride & 3) != 0)) return 2;
+    }
+    if (maxB <= 0) return 0;
+    const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
+    if (first_use_on_device(0))  // the attribute is per device, not per process
+        cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    policy_act_kernel<<<dim3((maxB + kPolicyCols - 1) / kPolicyCols, n_jobs), kPolicyThreads, smem, stream>>>(jobs, obs_dim);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_t obs_stride, int B, uint64_t seed,
                       uint64_t counter, float* action, int64_t act_stride, float* logprob, float* value,
                       float* mean, cudaStream_t stream, const int32_t* block_policy, int block_len,
@@ -353,16 +394,10 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
         count_launch();
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
-    if ((reinterpret_cast<uintptr_t>(params) & 15u) != 0) return 2;  // the bulk copy needs a 16-byte aligned source
-    if (block_policy != nullptr && (block_len <= 0 || block_len % kPolicyCols != 0 || (pool_stride & 3) != 0)) return 2;
-    const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
-    if (first_use_on_device(0))  // the attribute is per device, not per process
-        cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    policy_act_kernel<<<(B + kPolicyCols - 1) / kPolicyCols, kPolicyThreads, smem, stream>>>(
-        params, obs_dim, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean, block_policy,
-        block_len, pool_stride);
-    count_launch();
-    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    PolicyJobs jobs{};
+    jobs.job[0] = PolicyJob{params, obs, obs_stride, B, seed, counter, action, act_stride, logprob, value, mean,
+                            block_policy, block_len, pool_stride};
+    return launch_policy_jobs(jobs, 1, obs_dim, stream);
 }
 
 }  // namespace rk

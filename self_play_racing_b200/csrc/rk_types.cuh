@@ -134,6 +134,22 @@ int launch_policy_act(const float* params, int obs_dim, const float* obs, int64_
                       float* value, float* mean, cudaStream_t stream, const int32_t* block_policy = nullptr,
                       int block_len = 0, int64_t pool_stride = 0);
 int policy_param_count(int obs_dim);
+// one inference job of policy_act_kernel; a launch carries one or two (blockIdx.y)
+struct PolicyJob {
+    const float* params;         // packed block (or pool base); NULL = uniform Box actions
+    const float* obs;
+    int64_t obs_stride;
+    int B;
+    uint64_t seed, counter;
+    float* action;
+    int64_t act_stride;
+    float *logprob, *value, *mean;
+    const int32_t* block_policy;
+    int block_len;
+    int64_t pool_stride;
+};
+struct PolicyJobs { PolicyJob job[2]; };
+int launch_policy_jobs(const PolicyJobs& jobs, int n_jobs, int obs_dim, cudaStream_t stream);
 int launch_gather_minibatch(const int64_t* idx, int n, int obs_dim, const float* obs, const float* act,
                             const float* logp, const float* adv, const float* ret, const float* val, float* o_obs,
                             float* o_act, float* o_logp, float* o_adv, float* o_ret, float* o_val, cudaStream_t stream);

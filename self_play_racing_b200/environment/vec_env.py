@@ -282,6 +282,45 @@ class BatchedRacingVecEnv:
             be._bind_io()
         self._obs_cur = obs_out
 
+    def rollout_into(self, buf, learner_params, learner_seed, learner_counter0, T):
+        """PPO.collect_rollout's loop (agent/ppo.py:104-120) as ONE native call (rk_rollout): per step one inference
+        launch (learner + frozen opponent together) and the step kernel, written straight into the [T(+1), ...] rollout
+        buffers `buf` (PPO.alloc_buffers).  Bit-identical to T x (policy_act, step_into); no host synchronisation."""
+        import ctypes as C
+        from .. import _lib
+        be = self.be
+        r = _lib.RkRolloutIO(struct_size=C.sizeof(_lib.RkRolloutIO), T=int(T), selfplay=1 if self.selfplay else 0)
+        r.learner_params = learner_params.data_ptr()
+        r.learner_seed, r.learner_counter0 = int(learner_seed) & (2 ** 64 - 1), int(learner_counter0)
+        keep = [learner_params]
+        if self.selfplay:
+            pool = getattr(self, '_opp_pool', None)
+            if pool is not None:
+                params_pool, block_policy, block_len = pool
+                r.opponent_params, r.block_policy = params_pool.data_ptr(), block_policy.data_ptr()
+                r.block_len, r.pool_stride = int(block_len), int(params_pool.stride(0))
+                keep += [params_pool, block_policy]
+            elif self._opp_params is not None:
+                r.opponent_params = self._opp_params.data_ptr()
+                keep.append(self._opp_params)
+            r.opponent_seed, r.opponent_counter0 = (self.seed ^ 0x5eed0bb) & (2 ** 64 - 1), self._opp_counter + 1
+            self._opp_counter += int(T)
+            # car 1's observation for step 0 is the environment's CURRENT one (e.g. fresh after update_opponent's
+            # reset), not slot 0 of the buffer, which carries the learner's previous next_obs (SURVEY quirk 10)
+            if self._obs_cur.data_ptr() != buf['obs'][0].data_ptr():
+                r.opponent_obs0 = self._obs_cur[1].data_ptr()
+                keep.append(self._obs_cur)
+        for name in ('obs', 'actions', 'logprobs', 'values', 'rewards', 'dones'):
+            t = buf[name]
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise ValueError(f'rollout_into: buffer {name!r} must be a contiguous float32 CUDA tensor')
+            setattr(r, name, t.data_ptr())
+        be._io.start_slot = None
+        be._io.env_begin, be._io.env_count = 0, 0
+        _lib.check(be.lib.rk_rollout(be.h, C.byref(be._io), C.byref(r), be._stream()), be.h, 'rk_rollout')
+        self._obs_cur = buf['obs'][T]
+        del keep
+
     def step_device(self, actions, start_slot=None):
         """actions: CUDA float32 [E, 2] (learner).  Returns views (obs [E,D],
         reward float32 [E], done float32 [E]) valid until the next step; no

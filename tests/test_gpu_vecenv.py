@@ -543,7 +543,7 @@ def test_gym_face_at_scale_equals_device_face(pkg, kind, E):
     np.testing.assert_array_equal(o1, o2)
     rs = np.random.RandomState(0)
     n_done = 0
-    for k in range(12):
+    for k in range(90):                      # random drivers leave the track within 50-90 steps: auto-resets are covered
         a = rs.uniform(-1, 1, size=(E, 2)).astype(np.float32)
         a[:, 1] = np.abs(a[:, 1])
         obs, rew, term, trunc, infos = vec.step(a)
@@ -569,7 +569,9 @@ def test_gym_face_at_scale_equals_device_face(pkg, kind, E):
                 np.testing.assert_array_equal(infos['episode']['l'], infos2['episode']['l'])
                 assert set(infos['episode']) == {'r', 'l', 't'}
         n_done += int(term.sum())
-    assert np.abs(obs).max() <= 1.0 and np.isfinite(rew).all()
+    # (single-car ray readings are not clamped at the sensor range -- SURVEY quirk 2 -- so only the 2-car rows are <= 1)
+    assert np.isfinite(obs).all() and np.isfinite(rew).all() and (selfplay is False or np.abs(obs).max() <= 1.0)
+    assert n_done > 0
     vec.close(); ref.close()
 
 
@@ -597,3 +599,53 @@ def test_vec_env_reference_style_attribute_loop_and_seed(pkg):
     with pytest.raises(ValueError, match='multiple of 256'):
         vec.set_opponents([pol, pol], block_len=100)
     vec.close()
+
+
+@pytest.mark.parametrize('mode', ['selfplay_random', 'selfplay_snapshot', 'selfplay_pool', 'single'])
+def test_native_rollout_equals_python_loop(pkg, mode):
+    """rk_rollout (one C call per T-step rollout: the learner's and the opponent's inference in one launch + the step
+    kernel, 2 launches per step) against the per-step Python loop (3 launches per step) on twin trainers: every rollout
+    buffer is bit-identical over two consecutive rollouts, including the stale slot 0 after update_opponent's reset
+    (SURVEY quirk 10)."""
+    env_mod, agent_mod, configs = pkg
+    np.random.seed(1)
+    pool = env_mod.gen_tracks(num_tracks=8, seed=1)
+    widths = [int(np.random.randint(6, 10)) for _ in range(8)]
+    E, T = 768, 24
+    out = []
+    for native in (True, False):
+        if mode == 'single':
+            cfg = configs.base_config(num_envs=E, num_steps=T, total_timesteps=10 ** 9, native_rollout=native)
+            env_fn = lambda i: env_mod.RacingEnv(num_sensors=11, track_pool=pool, track_id=i % 8, track_width=widths)
+            tr = agent_mod.PPO(env_fn, cfg, device='cuda')
+        else:
+            cfg = configs.self_play_config(num_envs=E, num_steps=T, total_timesteps=10 ** 9, native_rollout=native,
+                                           opponents_per_update='pool' if mode == 'selfplay_pool' else 'one')
+            env_fn = lambda i: env_mod.MultiRacingEnv(num_agents=2, num_sensors=11, track_pool=pool, track_id=i % 8,
+                                                      track_width=widths)
+            tr = agent_mod.SelfPlayPPO(env_fn, cfg, device='cuda')
+            if mode != 'selfplay_random':
+                torch.manual_seed(5)
+                for k in range(3):
+                    snap = tr.snapshot_agent()
+                    for p_ in snap.parameters():
+                        p_.data.add_(0.05 * torch.randn_like(p_))
+                    tr.opponent_pool.append(snap)
+        buf = tr.alloc_buffers()
+        buf['obs'][0].copy_(tr._reset_all())
+        snaps = []
+        for it in range(2):
+            if mode != 'single':
+                np.random.seed(11 + it)
+                tr.update_opponent()
+            stats = tr.collect_rollout(buf)
+            snaps.append(({k: v.clone() for k, v in buf.items()}, stats))
+            buf['obs'][0].copy_(buf['obs'][T]); buf['dones'][0].copy_(buf['dones'][T])
+        assert ('native' in tr.rollout_mode) == native
+        out.append(snaps)
+        tr.envs.close()
+    for (b1, s1), (b2, s2) in zip(*out):
+        assert s1 == s2
+        for k in b1:
+            assert torch.equal(b1[k], b2[k]), k
+        assert float(b1['dones'].sum()) > 0 and torch.isfinite(b1['values']).all()
