@@ -213,6 +213,18 @@ def ppo_cpu_baseline(num_steps=48):
     import contextlib
     import io
     import torch
+    if torch.cuda.is_available():
+        # the reference's SelfPlayWrapper puts the opponent's observations on "cuda if available" whatever device
+        # the trainer was given (environment/wrappers.py:17): the host-only baseline therefore runs the unmodified
+        # code in a child process that sees no GPU
+        import subprocess
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+        for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+            env.pop(k, None)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--ppo-cpu-baseline', str(num_steps)],
+                             env=env, capture_output=True, text=True, timeout=900)
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+        return json.loads(lines[-1]) if lines else {'error': (out.stderr or 'no output')[-400:]}
     from agent.self_play_ppo import SelfPlayPPO
     from configs.self_play_config import hyperparams_config
     from environment.multi_racing_env import MultiRacingEnv
@@ -608,6 +620,9 @@ def pin_rank_to_cores(local, world):
 
 
 def main():
+    if len(sys.argv) >= 2 and sys.argv[1] == '--ppo-cpu-baseline':   # child of ppo_cpu_baseline(): no GPU visible
+        print(json.dumps(ppo_cpu_baseline(int(sys.argv[2]) if len(sys.argv) > 2 else 48)))
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=500)
@@ -619,7 +634,7 @@ def main():
     ap.add_argument('--envs', type=int, default=None)
     ap.add_argument('--tracks', type=int, default=None, help='size of the procedural track pool (default 16)')
     ap.add_argument('--factor', type=int, default=None, help='waypoints per control point (reference: 30); S = 2 * n_ctrl * factor')
-    ap.add_argument('--query', default='culled', choices=['culled', 'exact'])
+    ap.add_argument('--query', default='culled', choices=['culled', 'exact', 'grid'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaled block (65,536 envs in total)')
     ap.add_argument('--ppo-updates', type=int, default=5,

@@ -45,10 +45,17 @@ enum { RK_ENV_SINGLE = 0,   /* environment/racing_env.py  RacingEnv          */
        RK_ENV_MULTI = 1 };  /* environment/multi_racing_env.py MultiRacingEnv */
 /* autoreset_mode: gymnasium 1.x SyncVectorEnv semantics (agent/ppo.py:70,114) */
 enum { RK_AUTORESET_NEXT_STEP = 0, RK_AUTORESET_SAME_STEP = 1, RK_AUTORESET_DISABLED = 2 };
-/* query_mode: how waypoint-argmin and raycast candidates are found.  Both give
- * the reference's float64 result; CULLED finds candidates in fp32 over
- * bounding-circle chunks and re-evaluates the winners in float64. */
-enum { RK_QUERY_EXACT_F64 = 0, RK_QUERY_CULLED = 1 };
+/* query_mode: how waypoint-argmin and raycast candidates are found.  Every mode decides the discrete events
+ * (progress index, wall test) exactly as the reference's float64 arithmetic does.
+ *   EXACT_F64: float64 brute force over the whole tables (the in-library reference); ray distances are the
+ *              reference's correctly rounded float64 quotients.
+ *   CULLED:    warp-per-environment; candidates found in fp32 over bounding-circle chunks and an angular sweep.
+ *   GRID:      thread-per-car waypoint search and thread-per-ray traversal of a per-track uniform grid over the
+ *              boundary segments.
+ * CULLED and GRID pick each ray's nearest segment in fp32 (two candidates within fp32 rounding of each other are
+ * both re-evaluated) and compute its distance in float64 with a Newton reciprocal (<= 2 ulp): readings agree with
+ * the reference to ~1e-15 relative, far inside the 1e-6 the observations are compared at. */
+enum { RK_QUERY_EXACT_F64 = 0, RK_QUERY_CULLED = 1, RK_QUERY_GRID = 2 };
 
 typedef struct rk_config {
     int32_t struct_size;        /* sizeof(rk_config), for ABI checking                */
@@ -206,7 +213,8 @@ RK_API int rk_rollout(rk_handle h, const rk_step_io* base, const rk_rollout_io* 
 
 /* RacingEnv.speed_weight (racing_env.py:26; annealed by agent/ppo.py:256-258) */
 RK_API int rk_set_speed_weight(rk_handle h, double speed_weight);
-/* Re-key the Philox stream of the start-grid shuffles (rk_config::seed); what `reset(seed=...)` of the vector
+/* Re-key and restart the Philox stream of the start-grid shuffles (rk_config::seed; the per-environment reset
+ * counters return to zero, so the same seed reproduces the same grids); what `reset(seed=...)` of the vector
  * env forwards (gymnasium call site agent/ppo.py:230; the reference's envs draw the shuffle from the global
  * np.random stream, multi_racing_env.py:127-128). */
 RK_API int rk_set_seed(rk_handle h, uint64_t seed);

@@ -13,13 +13,13 @@ LIB_PATH = os.environ.get('RK_B200_LIB') or os.path.join(_HERE, 'librk_b200.so')
 
 RK_ENV_SINGLE, RK_ENV_MULTI = 0, 1
 RK_AUTORESET_NEXT_STEP, RK_AUTORESET_SAME_STEP, RK_AUTORESET_DISABLED = 0, 1, 2
-RK_QUERY_EXACT_F64, RK_QUERY_CULLED = 0, 1
+RK_QUERY_EXACT_F64, RK_QUERY_CULLED, RK_QUERY_GRID = 0, 1, 2
 RK_MAX_AGENTS, RK_MAX_SENSORS = 8, 64
 RK_LAYOUT_ENV_MAJOR, RK_LAYOUT_AGENT_MAJOR = 0, 1
 
 AUTORESET = {'next_step': RK_AUTORESET_NEXT_STEP, 'same_step': RK_AUTORESET_SAME_STEP,
              'disabled': RK_AUTORESET_DISABLED}
-QUERY = {'exact': RK_QUERY_EXACT_F64, 'culled': RK_QUERY_CULLED}
+QUERY = {'exact': RK_QUERY_EXACT_F64, 'culled': RK_QUERY_CULLED, 'grid': RK_QUERY_GRID}
 
 
 class RkConfig(C.Structure):

@@ -99,7 +99,7 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
     if (cfg->num_envs <= 0 || cfg->num_agents <= 0 || cfg->num_agents > RK_MAX_AGENTS || cfg->num_sensors <= 0 ||
         cfg->num_sensors > RK_MAX_SENSORS || (single && cfg->num_agents != 1) ||
         (cfg->env_kind != RK_ENV_SINGLE && cfg->env_kind != RK_ENV_MULTI) || cfg->autoreset_mode < 0 ||
-        cfg->autoreset_mode > RK_AUTORESET_DISABLED || cfg->query_mode < 0 || cfg->query_mode > RK_QUERY_CULLED) {
+        cfg->autoreset_mode > RK_AUTORESET_DISABLED || cfg->query_mode < 0 || cfg->query_mode > RK_QUERY_GRID) {
         snprintf(g_create_err, sizeof(g_create_err),
                  "rk_create: invalid config (E=%d A=%d R=%d kind=%d autoreset=%d query=%d)", cfg->num_envs,
                  cfg->num_agents, cfg->num_sensors, cfg->env_kind, cfg->autoreset_mode, cfg->query_mode);
@@ -127,6 +127,7 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
          dev_alloc(h, &h->st.fstep, C) || dev_alloc(h, &h->st.steps, (size_t)E) ||
          dev_alloc(h, &h->st.needs_reset, (size_t)E) || dev_alloc(h, &h->st.ep_return, (size_t)E) ||
          dev_alloc(h, &h->st.ep_length, (size_t)E) || dev_alloc(h, &h->st.reset_count, (size_t)E) ||
+         dev_alloc(h, &h->st.ray_order, C) ||
          dev_alloc(h, &h->sensor_angles, (size_t)3 * R);
     if (rc) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_create: %s", h->err[0] ? h->err : "cudaSetDevice failed");
@@ -265,6 +266,16 @@ static int set_tracks_common(rk_handle h, const double* ctrl, const int32_t* n_c
     if (build_pool(*h->pool, n_tracks, ctrl ? n_ctrl : nullptr, ctrl ? off.data() : nullptr, total_ctrl, ctrl,
                    n_wp.data(), wp, widths, e2t, h->cfg.num_envs, h->err, sizeof(h->err)))
         return 1;
+    if (h->cfg.query_mode != RK_QUERY_EXACT_F64)
+        for (int t = 0; t < n_tracks; ++t) {
+            const TrackMeta& m = *pool_host_meta(h->pool, t);
+            if (m.n_bchunk > kListMax || m.n_wchunk > kListMax) {
+                snprintf(h->err, sizeof(h->err),
+                         "set_tracks: track %d has %d waypoints; the culled / grid query modes handle at most %d per track "
+                         "(use RK_QUERY_EXACT_F64 or fewer waypoints per control point)", t, m.n_wp, kListMax / 2 * kRaySegs);
+                return 1;
+            }
+        }
     return plan_staged_launch(h, e2t);
 }
 
@@ -482,7 +493,7 @@ static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* h
     // address space) the step kernel also writes car 0's complete rows straight into it, one coalesced store per
     // environment, so that they cross PCIe while the kernel is still running and no device->host copy follows
     bool zero_copy = false;
-    if ((host->reserved0 & 1) && h->cfg.query_mode == RK_QUERY_CULLED && A <= 2 && A * h->cfg.num_sensors <= 32 && D <= 32) {
+    if ((host->reserved0 & 1) && h->cfg.query_mode != RK_QUERY_EXACT_F64 && A <= 2 && A * h->cfg.num_sensors <= 32 && D <= 32) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, host->obs) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
             p.obs_host0 = static_cast<float*>(attr.devicePointer);
@@ -644,7 +655,11 @@ int rk_set_speed_weight(rk_handle h, double w) {
 
 int rk_set_seed(rk_handle h, uint64_t seed) {
     if (!h) return 1;
+    cudaSetDevice(h->cfg.device);
     h->cfg.seed = seed;
+    // the stream restarts: the shuffle of an environment's k-th reset is Philox(seed; env, k)
+    H_CUDA(h, cudaDeviceSynchronize());
+    H_CUDA(h, cudaMemset(h->st.reset_count, 0, (size_t)h->cfg.num_envs * sizeof(uint32_t)));
     return 0;
 }
 

@@ -89,7 +89,7 @@ __device__ __forceinline__ int warp_argmin_d(double d, int idx) {
 #define RK_L2_UNROLL 1
 #endif
 constexpr int kLevel2Unroll = RK_L2_UNROLL;
-constexpr int kListCap = 512;  // chunk work items per warp batch
+constexpr int kListCap = 512;  // chunk work items per warp batch (tracks are limited to kListMax chunks, rk_types.cuh)
 
 // Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
 // one column per lane: conflict free) and the scratch of the culled queries.
@@ -113,8 +113,14 @@ __device__ __forceinline__ void out_store(const StepParams& p, T* ptr, size_t i,
         if (q >= p.arena_lo && q < p.arena_hi) *reinterpret_cast<T*>(q + p.arena_delta) = v;
     }
 }
+// (the per-slot area behind CarS holds the culled mode's ray directions and keys, or -- grid mode, zero-copy host rows --
+//  car 0's rays of up to 32 / A environments)
+__host__ __device__ inline size_t slot_area_bytes(int A, int R) {
+    const size_t per_slot = (size_t)A * R * (16 + 8 + 8), rows = (size_t)(32 / A) * R * 4;
+    return ((per_slot > rows ? per_slot : rows) + 15) / 16 * 16;
+}
 __host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
-    return (sizeof(CarS) + (size_t)A * R * (16 + 8 + 8) + kListCap * 2 + 15) / 16 * 16;
+    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -147,6 +153,17 @@ __device__ __forceinline__ void argmin_exact(const TrackPool& tp, const TrackMet
 // One ray against one segment, the reference's test (track.py:176-195 /
 // multi_track.py:28-44): hit iff |dotp| large enough, t = cross/dotp >= 0 and
 // 0 <= s = dv/dotp <= 1.  Returns t if hit, +inf otherwise.
+// FAST: the returned distance (an observation, tolerance 1e-6 on the normalised reading) comes from a Newton
+// reciprocal (<= 2 ulp) instead of the IEEE division routine; WHETHER the segment is hit is decided exactly either way.
+__device__ __forceinline__ double ddiv_fast(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));   // ~20 good bits
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+template <bool FAST = false>
 __device__ __forceinline__ double ray_segment(double v1x, double v1y, double v2x, double v2y, double cross,
                                               double v3x, double v3y, double min_abs_dot) {
     const double dotp = dadd(dmul(v2x, v3x), dmul(v2y, v3y));
@@ -159,7 +176,7 @@ __device__ __forceinline__ double ray_segment(double v1x, double v1y, double v2x
         const bool neg = dotp < 0.0;
         const bool t_ok = (cross == 0.0) || ((cross < 0.0) == neg);
         const bool s_ok = (dv == 0.0) || ((dv < 0.0) == neg);
-        if (t_ok && s_ok && (adv <= adot || ddiv(dv, dotp) <= 1.0)) return ddiv(cross, dotp);
+        if (t_ok && s_ok && (adv <= adot || ddiv(dv, dotp) <= 1.0)) return FAST ? ddiv_fast(cross, dotp) : ddiv(cross, dotp);
     }
     return INFINITY;
 }
@@ -205,6 +222,7 @@ __device__ RK_MAYBE_NOINLINE double raycast_wall_exact_one(const TrackPool& tp, 
 }
 
 // The four edges of every other car (multi_track.py:10-24), exact, for ONE ray.
+template <bool FAST = false>
 __device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int A, double ox, double oy,
                                                     double v3x, double v3y) {
     double t = INFINITY;
@@ -220,7 +238,7 @@ __device__ __forceinline__ double raycast_car_edges(const CarS& S, int base, int
             const double ex0 = S.cx[ed][l], ey0 = S.cy[ed][l];
             const double ax = dsub(S.cx[(ed + 1) & 3][l], ex0), ay = dsub(S.cy[(ed + 1) & 3][l], ey0);
             const double v1x = dsub(ox, ex0), v1y = dsub(oy, ey0);
-            t = fmin(t, ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kEdgeMinDot));
+            t = fmin(t, ray_segment<FAST>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kEdgeMinDot));
         }
     }
     return t;
@@ -239,11 +257,15 @@ constexpr float kPerpSlack = 3e-4f;    // bound on the fp32 error of a point-to-
 constexpr float kFrontSlack = 1e-3f;
 constexpr unsigned long long kNoKey = ~0ull;
 
-// Waypoint argmin for the car centre + 4 corners: one bounding-circle pass picks
+// Waypoint argmin for the car centre + 4 corners, float64 scan: one bounding-circle pass picks
 // the chunks that can hold the nearest waypoint of ANY of the five points, then
-// those chunks are scanned exactly in float64 (half a warp per chunk).
-__device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackMeta& tm, const double* qx,
-                                               const double* qy, int lane, unsigned short* list, int* out_idx) {
+// those chunks are scanned exactly in float64 (half a warp per chunk).  This is the slow path of
+// argmin_culled5 / argmin_lane5 below (taken when the fp32 search leaves more than one candidate for a point).
+struct CarS;
+__device__ __noinline__ void argmin_culled5_f64(const TrackPool& tp, const TrackMeta& tm, const CarS& S, int l,
+                                                int lane, unsigned short* list, int* out_idx);
+__device__ __forceinline__ void argmin_culled5_f64_body(const TrackPool& tp, const TrackMeta& tm, const double* qx,
+                                                const double* qy, int lane, unsigned short* list, int* out_idx) {
     const float4* wch = tp.wchunk + tm.wchunk_off;
     const float cx0 = (float)(qx[0] - tm.org_x), cy0 = (float)(qy[0] - tm.org_y);
     const int nwc = tm.n_wchunk;
@@ -303,6 +325,86 @@ __device__ __forceinline__ void argmin_culled5(const TrackPool& tp, const TrackM
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 5; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
+}
+
+// Waypoint argmin for the car centre + 4 corners (track.py:150-152, five times per car.py:79-80 / track.py:163-171).
+// The result must be numpy's float64 argmin, first index on ties, because it decides progress, checkpoints and the
+// wall test.  The search itself runs in fp32:
+//   1. the distance from the centre to ANY waypoint bounds the nearest distance from above; the waypoint found one
+//      step earlier (`hint`) is within a few indices of the new one, so the bound is tight.  One pass over the
+//      bounding circles keeps the chunks that can hold the nearest waypoint of the centre or of a corner
+//      (corners lie within kHalfDiag of the centre);
+//   2. fp32 squared distances of the five points to the kept chunks' waypoints (half a warp per chunk), every lane
+//      remembering its best and second-best per point;
+//   3. a point whose fp32 minimum is separated from every other waypoint by more than the rounding bound `eps` has
+//      exactly one candidate, and that candidate IS the float64 argmin -- no float64 arithmetic needed.  Otherwise
+//      (near ties: the point is within ~1e-4 of the bisector of two waypoints) the float64 scan above decides.
+// eps: table and query are rounded to fp32 relative to the bbox centre (|coordinate| <= diag/2, so each is off by at
+// most diag * 2^-25), hence |d32 - d64| <= 4 sqrt(2) diag 2^-25 d + 4e-7 d^2 for a squared distance; two such
+// errors meet in a comparison.  The bound used below is more than twice that.
+// Returns true (warp-uniform) when the float64 scan has to decide.
+__device__ __forceinline__ bool argmin_culled5(const TrackPool& tp, const TrackMeta& tm, const double* qx,
+                                               const double* qy, int hint, int lane, unsigned short* list,
+                                               int* out_idx) {
+    const float4* wch = tp.wchunk + tm.wchunk_off;
+    const float2* wpt = tp.wpt + tm.wp_off;
+    float fx[5], fy[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { fx[q] = (float)(qx[q] - tm.org_x); fy[q] = (float)(qy[q] - tm.org_y); }
+    const int nwc = tm.n_wchunk;
+    const float2 wh = wpt[min(max(hint, 0), tm.n_wp - 1)];
+    const float hx = wh.x - fx[0], hy = wh.y - fy[0];
+    const float thr = sqrt_fast(hx * hx + hy * hy) + 2.f * kHalfDiag + 2e-2f;
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nwc; c0 += 32) {
+        const int ci = c0 + lane;
+        bool keep = false;
+        if (ci < nwc) {
+            const float4 cc = wch[ci];
+            const float dx = cc.x - fx[0], dy = cc.y - fy[0];
+            keep = sqrt_fast(dx * dx + dy * dy) - cc.z <= thr;
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (keep) list[count + __popc(m & lt)] = (unsigned short)ci;
+        count += __popc(m);
+    }
+    __syncwarp();
+    float best[5], second[5];
+    int bi[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { best[q] = INFINITY; second[q] = INFINITY; bi[q] = 0; }
+    const int half = lane >> 4, j = lane & 15;
+#pragma unroll 1
+    for (int it = 0; it < count; it += 2) {
+        const int my = it + half;
+        const int i = (my < count) ? (int)list[my] * kChunk + j : tm.n_wp;
+        if (i < tm.n_wp) {
+            const float2 P = wpt[i];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float dx = P.x - fx[q], dy = P.y - fy[q];
+                const float d = fmaf(dx, dx, dy * dy);
+                second[q] = fminf(second[q], fmaxf(d, best[q]));
+                if (d < best[q]) { best[q] = d; bi[q] = i; }
+            }
+        }
+    }
+    __syncwarp();
+    const float c_err = (float)tm.max_track_distance * 6e-7f;   // > 2 * 4 sqrt(2) * 2^-25 * diag
+    bool exact = false;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const float m = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(best[q])));   // d >= 0: ordered like its bits
+        const float lim = m + c_err * sqrt_fast(m) + 2e-6f * m + 1e-9f;
+        const bool cand = best[q] <= lim;
+        const unsigned b = __ballot_sync(kFull, cand);
+        const unsigned amb = __ballot_sync(kFull, cand && second[q] <= lim);
+        out_idx[q] = __shfl_sync(kFull, bi[q], __ffs(b) - 1);
+        exact = exact || (b & (b - 1)) != 0u || amb != 0u;
+    }
+    return exact;
 }
 
 // atan2 for the angular sweep: Abramowitz & Stegun 4.4.49 (|error| <= 2e-8 on
@@ -447,6 +549,153 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Grid queries (RK_QUERY_GRID): every lane works on its own car / its own ray.
+// ---------------------------------------------------------------------------
+// Waypoint argmin of the car centre + 4 corners, ONE CAR PER LANE.  Same contract and the same fp32 reasoning as
+// argmin_culled5 (bound from the previous index, bounding circles, fp32 distances with best / second-best, a unique
+// fp32 candidate IS the float64 argmin), but nothing is shared between lanes: the lane walks the bounding circles
+// itself, remembers up to six chunks that can hold a nearest waypoint and scans them.  Returns false when the lane
+// needs the cooperative float64 scan instead (near ties, more than six chunks).
+__device__ __forceinline__ bool argmin_lane5(const TrackPool& tp, const TrackMeta* tm, double x, double y,
+                                             const double* cxs, const double* cys, int hint, int* out_idx) {
+    const float4* wch = tp.wchunk + tm->wchunk_off;
+    const float2* wpt = tp.wpt + tm->wp_off;
+    const int n_wp = tm->n_wp, nwc = tm->n_wchunk;
+    const double orgx = tm->org_x, orgy = tm->org_y;
+    float fx[5], fy[5];
+    fx[0] = (float)(x - orgx); fy[0] = (float)(y - orgy);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { fx[q + 1] = (float)(cxs[q] - orgx); fy[q + 1] = (float)(cys[q] - orgy); }
+    const float2 wh = wpt[min(max(hint, 0), n_wp - 1)];
+    const float hx = wh.x - fx[0], hy = wh.y - fy[0];
+    const float thr = sqrt_fast(hx * hx + hy * hy) + 2.f * kHalfDiag + 2e-2f;
+    unsigned long long keep = 0ull;   // up to six 10-bit chunk ids
+    int nkeep = 0;
+#pragma unroll 1
+    for (int c = 0; c < nwc; ++c) {
+        const float4 cc = wch[c];
+        const float dx = cc.x - fx[0], dy = cc.y - fy[0];
+        const float lim = thr + cc.z;
+        if (dx * dx + dy * dy <= lim * lim) {
+            if (nkeep < 6) keep |= (unsigned long long)c << (10 * nkeep);
+            ++nkeep;
+        }
+    }
+    float best[5], second[5];
+    int bi[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { best[q] = INFINITY; second[q] = INFINITY; bi[q] = 0; }
+    const int nscan = min(nkeep, 6);
+#pragma unroll 1
+    for (int k = 0; k < nscan; ++k) {
+        const int i0 = (int)((keep >> (10 * k)) & 1023ull) * kChunk;
+        const int i1 = min(i0 + kChunk, n_wp);
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+            const float2 P = wpt[i];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float dx = P.x - fx[q], dy = P.y - fy[q];
+                const float d = fmaf(dx, dx, dy * dy);
+                second[q] = fminf(second[q], fmaxf(d, best[q]));
+                if (d < best[q]) { best[q] = d; bi[q] = i; }
+            }
+        }
+    }
+    const float c_err = (float)tm->max_track_distance * 6e-7f;
+    bool ok = nkeep >= 1 && nkeep <= 6;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const float m = best[q];
+        ok = ok && second[q] > m + c_err * sqrt_fast(m) + 2e-6f * m + 1e-9f;
+        out_idx[q] = bi[q];
+    }
+    return ok;
+}
+
+// One ray through the track's uniform grid (Amanatides & Woo traversal), ONE RAY PER LANE: returns the two nearest
+// fp32 hits (distance, segment id) among the boundary segments listed in the cells the ray crosses.  The hit test is
+// the reference's (track.py:176-195) with slack: t >= -eps, -eps <= s <= 1 + eps, so rounding can only add
+// candidates; the caller re-evaluates them in float64.  The walk ends once the best hit lies inside the cells
+// already visited, at `tmax`, or at the grid's edge.  inside = false: the origin is outside the grid.
+struct RayHit { float t0, t1; int s0, s1; bool inside; };
+__device__ __forceinline__ RayHit grid_ray(const TrackPool& tp, const TrackMeta* tm, float ox, float oy, float dx,
+                                           float dy, float tmax) {
+    RayHit h;
+    h.t0 = INFINITY; h.t1 = INFINITY; h.s0 = -1; h.s1 = -1;
+    const float cell = tm->gcell, inv = tm->ginv, gx0 = tm->gx0, gy0 = tm->gy0;
+    const int nx = tm->gnx, ny = tm->gny;
+    int ix = (int)floorf((ox - gx0) * inv), iy = (int)floorf((oy - gy0) * inv);
+    h.inside = (unsigned)ix < (unsigned)nx && (unsigned)iy < (unsigned)ny;
+    if (!h.inside) return h;
+    const uint32_t* cells = tp.gcell + tm->gcell_off;
+    const uint16_t* lst = tp.glist + tm->glist_off;
+    const float4* segs = tp.bseg + 2 * (size_t)tm->wp_off;
+    const int stx = dx >= 0.f ? 1 : -1, sty = dy >= 0.f ? 1 : -1;
+    const float rdx = fabsf(dx) > 1e-20f ? 1.f / dx : copysignf(1e20f, dx), rdy = fabsf(dy) > 1e-20f ? 1.f / dy : copysignf(1e20f, dy);
+    float tmx = (gx0 + (float)(ix + (stx > 0)) * cell - ox) * rdx;   // ray parameter at the next x / y cell boundary
+    float tmy = (gy0 + (float)(iy + (sty > 0)) * cell - oy) * rdy;
+    const float tdx = cell * fabsf(rdx), tdy = cell * fabsf(rdy);
+    // Outer iteration = one NON-EMPTY cell: a tight loop first walks over the empty cells in between (the inside of
+    // the corridor holds no segments), a second tight loop tests the cell's segments.  Lanes of a warp run rays of
+    // similar length of different cars (see the ray order below), so both inner loops have similar trip counts.
+    bool stop = false;
+    uint32_t c = cells[iy * nx + ix];
+    float t_exit = fminf(tmx, tmy);
+#pragma unroll 1
+    while (!stop) {
+#pragma unroll 1
+        while ((c & 1023u) == 0u) {
+            const bool xstep = tmx < tmy;   // branch-free step
+            ix += xstep ? stx : 0;  iy += xstep ? 0 : sty;
+            tmx += xstep ? tdx : 0.f;  tmy += xstep ? 0.f : tdy;
+            if (t_exit > tmax || (unsigned)ix >= (unsigned)nx || (unsigned)iy >= (unsigned)ny) { stop = true; break; }
+            c = cells[iy * nx + ix];
+            t_exit = fminf(tmx, tmy);
+        }
+        if (stop) break;
+#pragma unroll 1
+        for (uint32_t k = c >> 10, e = (c >> 10) + (c & 1023u); k < e; ++k) {
+            const int sg = lst[k];
+            const float4 S = segs[sg];
+            const float wx = S.x - ox, wy = S.y - oy;
+            const float den = dx * S.w - dy * S.z;        // d x v   (= the reference's dotp)
+            const float aden = fabsf(den), sgn = copysignf(1.f, den);
+            const float tn = (wx * S.w - wy * S.z) * sgn;  // (w x v) sign(den): t = tn / |den|
+            const float sn = (wx * dy - wy * dx) * sgn;    // (w x d) sign(den): s = sn / |den|
+            // slack: |w| <~ 300, products carry <~ 1e-4 of absolute error
+            if (aden > 1e-12f && tn >= -2e-4f && sn >= -2e-4f && sn <= aden + 2e-4f) {
+                const float t = fmaxf(__fdividef(tn, aden), 0.f);
+                if (t < h.t0) { h.t1 = h.t0; h.s1 = h.s0; h.t0 = t; h.s0 = sg; }
+                else if (t < h.t1 && sg != h.s0) { h.t1 = t; h.s1 = sg; }
+            }
+        }
+        if (h.t0 <= t_exit || t_exit > tmax) break;
+        const bool xstep = tmx < tmy;
+        ix += xstep ? stx : 0;  iy += xstep ? 0 : sty;
+        tmx += xstep ? tdx : 0.f;  tmy += xstep ? 0.f : tdy;
+        if ((unsigned)ix >= (unsigned)nx || (unsigned)iy >= (unsigned)ny) break;
+        c = cells[iy * nx + ix];
+        t_exit = fminf(tmx, tmy);
+    }
+    return h;
+}
+
+// Out-of-line slow path of argmin_culled5 / argmin_lane5: the five query points are re-read from the warp's shared
+// pose table and the indices come back through shared memory, so that the caller's registers never spill for its sake.
+__device__ __noinline__ void argmin_culled5_f64(const TrackPool& tp, const TrackMeta& tm, const CarS& S, int l,
+                                                int lane, unsigned short* list, int* out_idx) {
+    double qx[5], qy[5];
+    qx[0] = S.x[l]; qy[0] = S.y[l];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[k][l]; qy[k + 1] = S.cy[k][l]; }
+    int idx[5];
+    argmin_culled5_f64_body(tp, tm, qx, qy, lane, list, idx);
+    if (lane < 5) out_idx[lane] = lane == 0 ? idx[0] : lane == 1 ? idx[1] : lane == 2 ? idx[2] : lane == 3 ? idx[3] : idx[4];
+    __syncwarp();
+}
+
 // Philox Fisher-Yates over the A car ids of an environment; returns the grid
 // slot of car `a` (multi_racing_env.py:127-133).  Every lane of the environment
 // draws the same numbers, so no communication is needed.
@@ -524,7 +773,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     cv.dir64 = reinterpret_cast<double2*>(wbase + sizeof(CarS));
     cv.ray_key = reinterpret_cast<unsigned long long*>(cv.dir64 + A * R);
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
-    cv.list = reinterpret_cast<unsigned short*>(cv.dir32 + A * R);
+    cv.list = reinterpret_cast<unsigned short*>(wbase + sizeof(CarS) + slot_area_bytes(A, R));
 
     // ---- lane = one car -------------------------------------------------------
     const int g = lane / A, a = lane - g * A;     // environment within the warp, car within the environment
@@ -630,6 +879,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         //         all lanes cooperating (track.py:150-152) ---------------------------
         int cidx1 = 0, cidx2 = 0, cidx3 = 0, cidx4 = 0;
         unsigned todo = __ballot_sync(kFull, moving);
+        if (QUERY == RK_QUERY_GRID) {
+            // every moving car searches on its own lane; the few that end in a near tie go through the cooperative
+            // float64 scan below, one at a time
+            bool solved = true;
+            if (moving) {
+                const double cxs[4] = {S.cx[0][lane], S.cx[1][lane], S.cx[2][lane], S.cx[3][lane]};
+                const double cys[4] = {S.cy[0][lane], S.cy[1][lane], S.cy[2][lane], S.cy[3][lane]};
+                int idx[5];
+                solved = argmin_lane5(tp, tmp, x, y, cxs, cys, lpidx, idx);
+                pidx = idx[0]; cidx1 = idx[1]; cidx2 = idx[2]; cidx3 = idx[3]; cidx4 = idx[4];
+            }
+            todo = __ballot_sync(kFull, moving && !solved);
+        }
         while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -639,9 +901,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
 #pragma unroll
             for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[k][l]; qy[k + 1] = S.cy[k][l]; }
             int idx[5];
-            if (QUERY == RK_QUERY_CULLED)
-                argmin_culled5(tp, tm, qx, qy, lane, cv.list, idx);
-            else
+            if (QUERY == RK_QUERY_GRID) {
+                int* res = reinterpret_cast<int*>(cv.list + kListCap - 16);   // past any chunk list (lists hold <= kListMax)
+                argmin_culled5_f64(tp, tm, S, l, lane, cv.list, res);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) idx[q] = res[q];
+                __syncwarp();
+            } else if (QUERY == RK_QUERY_CULLED) {
+                if (argmin_culled5(tp, tm, qx, qy, __shfl_sync(kFull, lpidx, l), lane, cv.list, idx)) {
+                    int* res = reinterpret_cast<int*>(cv.list + kListCap - 16);
+                    argmin_culled5_f64(tp, tm, S, l, lane, cv.list, res);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) idx[q] = res[q];
+                    __syncwarp();
+                }
+            } else
                 argmin_exact<5>(tp, tm, qx, qy, lane, idx);
             if (lane == l) { pidx = idx[0]; cidx1 = idx[1]; cidx2 = idx[2]; cidx3 = idx[3]; cidx4 = idx[4]; }  // car.py:79
         }
@@ -919,6 +1193,103 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     // rays: the warp walks over its environments, all lanes cooperating on one
     const unsigned obs_envs = __ballot_sync(kFull, want_obs && a == 0);
     const int nslot = A * R;
+    if (QUERY == RK_QUERY_GRID) {
+        // ---- rays: every lane casts the R rays of ITS car, one after the other ------------------------------------
+        float* row_sh = reinterpret_cast<float*>(cv.dir64);   // car 0's rays of every environment, for the host rows
+        const TrackMeta* tmr = tmp;
+        const float o32x = (float)(x - tmr->org_x), o32y = (float)(y - tmr->org_y);
+        const double* sx = tp.sx + 2 * (size_t)tmr->wp_off;
+        const double* sy = tp.sy + 2 * (size_t)tmr->wp_off;
+        const double* v2x = tp.v2x + 2 * (size_t)tmr->wp_off;
+        const double* v2y = tp.v2y + 2 * (size_t)tmr->wp_off;
+        float* orow = obs + ci * D;
+        // Pass j works on each car's j-th LONGEST ray of the previous step (p.st.ray_order): the lanes of a warp then
+        // walk rays of similar length at the same time and the traversal loops stay converged.  Only a schedule: every
+        // ray is cast exactly once whatever the order.
+        unsigned long long order = (is_car && R <= 15) ? p.st.ray_order[c] : 0ull;
+        const bool ordered = (order >> 60) == 0xFull;
+#pragma unroll 1
+        for (int j = 0; j < R; ++j) {
+            const int r = ordered ? min((int)((order >> (4 * j)) & 15ull), R - 1) : j;
+            double v3x = 0.0, v3y = 1.0, wall = INFINITY;
+            bool redo = false;
+            if (want_obs) {
+                // ray direction by angle addition from the car's (cos, sin)
+                const double rc = p.sensor_cos[r], rs = p.sensor_sin[r];
+                const double dcs = dsub(dmul(cs, rc), dmul(sn, rs)), dsn = dadd(dmul(sn, rc), dmul(cs, rs));
+                v3x = -dsn; v3y = dcs;  // track.py:178
+                const RayHit hit = grid_ray(tp, tmr, o32x, o32y, (float)dcs, (float)dsn,
+                                            (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY);
+                redo = !hit.inside;
+                if (hit.s0 >= 0) {
+                    {
+                        const int i = hit.s0;
+                        const double ax = v2x[i], ay = v2y[i];
+                        const double v1x = dsub(x, sx[i]), v1y = dsub(y, sy[i]);
+                        wall = ray_segment<true>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
+                    }
+                    // the runner-up decides when float64 rejects the fp32 winner or the two are within fp32 rounding
+                    const bool close = hit.s1 >= 0 && hit.t1 <= hit.t0 + 2e-4f * (1.f + hit.t0);
+                    if (hit.s1 >= 0 && (wall == INFINITY || close)) {
+                        const int i = hit.s1;
+                        const double ax = v2x[i], ay = v2y[i];
+                        const double v1x = dsub(x, sx[i]), v1y = dsub(y, sy[i]);
+                        wall = fmin(wall, ray_segment<true>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot));
+                    }
+                    redo = redo || wall == INFINITY;  // fp32 candidates rejected by the float64 test
+                }
+            }
+            unsigned fb = __ballot_sync(kFull, redo);
+            while (fb) {  // rare: that ray against every wall, exactly, with the whole warp
+                const int b = __ffs(fb) - 1;
+                fb &= fb - 1;
+                const TrackMeta tmb = tp.meta[__shfl_sync(kFull, tid, b)];
+                const double t = raycast_wall_exact_one(tp, tmb, __shfl_sync(kFull, x, b), __shfl_sync(kFull, y, b),
+                                                        __shfl_sync(kFull, v3x, b), __shfl_sync(kFull, v3y, b), lane);
+                if (lane == b) wall = t;
+            }
+            if (want_obs) {
+                double t = wall;
+                if (KIND == RK_ENV_MULTI)
+                    t = fmin(fmin(t, raycast_car_edges<true>(S, base, A, x, y, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
+                else if (t == INFINITY)
+                    t = kMaxRange;  // track.py:196-197
+                const float hval = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+                orow[r] = hval;
+                if (p.obs_host0 != nullptr && a == 0) row_sh[g * R + r] = hval;
+            }
+        }
+        if (want_obs && R <= 15 && p.mode != 2) {
+            // next step's order: rank the fresh readings (re-read from the row just written: static indexing)
+            float hv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) hv[k] = k < R ? orow[k] : -1.f;
+            unsigned long long next = 0xFull << 60;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                int rank = 0;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) rank += (hv[m] > hv[k] || (hv[m] == hv[k] && m < k)) ? 1 : 0;
+                if (k < R) next |= (unsigned long long)k << (4 * rank);
+            }
+            p.st.ray_order[c] = next;
+        }
+        if (p.obs_host0 != nullptr) {
+            // car 0's complete rows of the warp's consecutive environments form ONE contiguous run of n_env * D floats
+            // in the caller's pinned buffer: full-width coalesced stores
+            __syncwarp();
+            const int run = n_env * D;
+            for (int f0 = 0; f0 < run; f0 += 32) {
+                const int f = f0 + lane;
+                if (f < run) {
+                    const int gg = f / D, col = f - gg * D;
+                    if ((obs_envs >> (gg * A)) & 1u)
+                        p.obs_host0[(size_t)(e_base + gg) * D + col] = col < R ? row_sh[gg * R + col] : nr_sh[(col - R) * nr_stride + gg];
+                }
+            }
+        }
+        return;
+    }
     for (int gg = 0; gg < n_env; ++gg) {
         const int gbase = gg * A;
         if (!((obs_envs >> gbase) & 1u)) continue;
@@ -963,7 +1334,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                         const int i = (int)(key & 0xffffffffu);
                         const double ax = v2x[i], ay = v2y[i];
                         const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
-                        wall = ray_segment(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
+                        wall = ray_segment<true>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
                         redo = (wall == INFINITY);  // fp32 candidate rejected by the float64 test
                     }
                 }
@@ -979,7 +1350,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (live) {
                     double t = wall;
                     if (KIND == RK_ENV_MULTI)
-                        t = fmin(fmin(t, raycast_car_edges(S, gbase, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
+                        t = fmin(fmin(t, raycast_car_edges<true>(S, gbase, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
                     else if (t == INFINITY)
                         t = kMaxRange;  // track.py:196-197
                     const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
@@ -1042,7 +1413,9 @@ int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t 
     using Kern = void (*)(const StepParams);
     const bool single = env_kind == RK_ENV_SINGLE, culled = query_mode == RK_QUERY_CULLED;
     Kern k;
-    if (staged && culled)
+    if (query_mode == RK_QUERY_GRID)
+        k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_GRID, false> : step_kernel<RK_ENV_MULTI, RK_QUERY_GRID, false>;
+    else if (staged && culled)
         k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED, true> : step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED, true>;
     else if (culled)
         k = single ? step_kernel<RK_ENV_SINGLE, RK_QUERY_CULLED, false> : step_kernel<RK_ENV_MULTI, RK_QUERY_CULLED, false>;

@@ -14,6 +14,7 @@
 // reference's tables.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -315,10 +316,13 @@ struct PoolBuffers {
     double* ctrl = nullptr;
     float2 *wpt = nullptr, *bpt = nullptr;
     float4 *wchunk = nullptr, *bchunk = nullptr;
+    float4* bseg = nullptr;
+    uint32_t* gcell = nullptr;
+    uint16_t* glist = nullptr;
     std::vector<TrackMeta> host_meta;
 
     void release() {
-        void* ptrs[] = {meta, env_to_track, wx, wy, nx, ny, sx, sy, v2x, v2y, ctrl, wpt, bpt, wchunk, bchunk};
+        void* ptrs[] = {meta, env_to_track, wx, wy, nx, ny, sx, sy, v2x, v2y, ctrl, wpt, bpt, wchunk, bchunk, bseg, gcell, glist};
         for (void* p : ptrs)
             if (p) cudaFree(p);
         *this = PoolBuffers();
@@ -329,6 +333,7 @@ struct PoolBuffers {
         v.wx = wx; v.wy = wy; v.nx = nx; v.ny = ny;
         v.sx = sx; v.sy = sy; v.v2x = v2x; v.v2y = v2y;
         v.wpt = wpt; v.bpt = bpt; v.wchunk = wchunk; v.bchunk = bchunk;
+        v.bseg = bseg; v.gcell = gcell; v.glist = glist;
         return v;
     }
 };
@@ -341,6 +346,94 @@ struct PoolBuffers {
             return 1;                                                                     \
         }                                                                                 \
     } while (0)
+
+// Uniform grids over the boundary segments (RK_QUERY_GRID), built on the host from the fp32 boundary rows the
+// device has just produced -- a one-off at pool creation.  Cell size RK_B200_GRID_CELL (default 3 track units).
+// A segment is listed in every cell that its bounding box, grown by kGridMargin, overlaps: a ray that crosses the
+// segment inside a cell (or within fp32 rounding of it) therefore finds it in that cell's list.  The grid covers the
+// boundary's bounding box plus 8 units, so every car position that can occur (cars stop at the wall) lies inside; the
+// kernel falls back to the exact scan for origins outside.
+static int build_grids(PoolBuffers& pb, size_t bpts, char* err, size_t errlen) {
+    float cell = 3.0f;
+    if (const char* env = getenv("RK_B200_GRID_CELL")) cell = (float)atof(env);
+    if (!(cell >= 0.5f && cell <= 64.f)) cell = 3.0f;
+    std::vector<float2> pts(bpts);
+    RK_CUDA(cudaMemcpy(pts.data(), pb.bpt, bpts * sizeof(float2), cudaMemcpyDeviceToHost));
+    std::vector<float4> segs(2 * pb.total_wp);
+    std::vector<uint32_t> cells;
+    std::vector<uint16_t> list;
+    std::vector<uint32_t> count, fill;
+    const float pad = 8.0f;
+    for (int t = 0; t < pb.n_tracks; ++t) {
+        TrackMeta& m = pb.host_meta[t];
+        const int N = m.n_wp;
+        if (2 * N > 65535) {
+            snprintf(err, errlen, "track %d has %d waypoints (segment ids are 16-bit: at most 32767)", t, N);
+            return 1;
+        }
+        const float2* row[2] = {pts.data() + m.bpt_off, pts.data() + m.bpt_off + (N + 1)};
+        float x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+        for (int sd = 0; sd < 2; ++sd)
+            for (int k = 0; k <= N; ++k) {
+                x0 = fminf(x0, row[sd][k].x); x1 = fmaxf(x1, row[sd][k].x);
+                y0 = fminf(y0, row[sd][k].y); y1 = fmaxf(y1, row[sd][k].y);
+            }
+        m.gx0 = x0 - pad; m.gy0 = y0 - pad; m.gcell = cell; m.ginv = 1.0f / cell;
+        m.gnx = (int)ceilf((x1 + pad - m.gx0) / cell) + 1;
+        m.gny = (int)ceilf((y1 + pad - m.gy0) / cell) + 1;
+        m.gcell_off = (int32_t)cells.size();
+        m.glist_off = (int32_t)list.size();
+        const size_t ncell = (size_t)m.gnx * m.gny;
+        if (cells.size() + ncell > 0x7fffffffu) {
+            snprintf(err, errlen, "track pool too large for the ray grid (cells)");
+            return 1;
+        }
+        count.assign(ncell, 0);
+        auto range = [&](float a, float b, float org, int n, int& lo, int& hi) {
+            lo = (int)floorf((fminf(a, b) - kGridMargin - org) * m.ginv);
+            hi = (int)floorf((fmaxf(a, b) + kGridMargin - org) * m.ginv);
+            lo = lo < 0 ? 0 : lo; hi = hi > n - 1 ? n - 1 : hi;
+        };
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int sg = 0; sg < 2 * N; ++sg) {
+                const int sd = sg >= N, k = sg - sd * N;
+                const float2 p = row[sd][k], q = row[sd][k + 1];
+                if (pass == 0) segs[2 * (size_t)m.wp_off + sg] = make_float4(p.x, p.y, q.x - p.x, q.y - p.y);
+                int cx0, cx1, cy0, cy1;
+                range(p.x, q.x, m.gx0, m.gnx, cx0, cx1);
+                range(p.y, q.y, m.gy0, m.gny, cy0, cy1);
+                for (int cy = cy0; cy <= cy1; ++cy)
+                    for (int cx = cx0; cx <= cx1; ++cx) {
+                        const size_t c = (size_t)cy * m.gnx + cx;
+                        if (pass == 0) ++count[c];
+                        else list[m.glist_off + fill[c]++] = (uint16_t)sg;
+                    }
+            }
+            if (pass == 0) {
+                fill.assign(ncell, 0);
+                uint32_t run = 0;
+                for (size_t c = 0; c < ncell; ++c) {
+                    if (count[c] > 1023 || run >= (1u << 22)) {
+                        snprintf(err, errlen, "track %d is too dense for the ray grid (%u segments in one %.1f-unit cell)", t, count[c], cell);
+                        return 1;
+                    }
+                    cells.push_back((run << 10) | count[c]);
+                    fill[c] = run;
+                    run += count[c];
+                }
+                list.resize(list.size() + run);
+            }
+        }
+    }
+    RK_CUDA(cudaMalloc(&pb.bseg, segs.size() * sizeof(float4)));
+    RK_CUDA(cudaMalloc(&pb.gcell, (cells.size() + 1) * sizeof(uint32_t)));
+    RK_CUDA(cudaMalloc(&pb.glist, (list.size() + 1) * sizeof(uint16_t)));
+    RK_CUDA(cudaMemcpy(pb.bseg, segs.data(), segs.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    RK_CUDA(cudaMemcpy(pb.gcell, cells.data(), cells.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    RK_CUDA(cudaMemcpy(pb.glist, list.data(), list.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    RK_CUDA(cudaMemcpy(pb.meta, pb.host_meta.data(), pb.n_tracks * sizeof(TrackMeta), cudaMemcpyHostToDevice));
+    return 0;
+}
 
 // n_wp[t] waypoints per track; exactly one of (dev_ctrl != nullptr) or
 // (host_wp != nullptr) supplies the geometry.
@@ -431,7 +524,7 @@ int build_pool(PoolBuffers& pb, int n_tracks, const int32_t* n_ctrl, const int32
     RK_CUDA(cudaGetLastError());
     RK_CUDA(cudaDeviceSynchronize());
     RK_CUDA(cudaMemcpy(pb.host_meta.data(), pb.meta, n_tracks * sizeof(TrackMeta), cudaMemcpyDeviceToHost));
-    return 0;
+    return build_grids(pb, bpts, err, errlen);
 }
 
 // Procedural control points on the device, returned to the host so that the

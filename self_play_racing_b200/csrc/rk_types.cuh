@@ -10,6 +10,8 @@ namespace rk {
 constexpr int kChunk = 16;          // waypoints per bounding-circle chunk
 constexpr int kRaySegs = 15;        // boundary segments per chunk (16 points: one half-warp, lane j+1 holds lane j's end point)
 constexpr int kMaxKnots = 130;      // n_ctrl + 1 <= kMaxKnots
+constexpr float kGridMargin = 0.02f;  // a segment is listed in every cell its bounding box, grown by this, overlaps
+constexpr int kListMax = 480;       // chunks of one kind per track: the culled queries keep per-warp chunk lists of 512 entries
 #ifndef RK_WARPS
 #define RK_WARPS 4
 #endif
@@ -37,6 +39,11 @@ struct TrackMeta {
     double start_x, start_y, start_angle;  // track.py:154-157
     double start_nx, start_ny;  // normals[0] (multi_racing_env.py:123)
     double org_x, org_y;        // bbox centre: origin of the fp32 tables
+    // uniform grid over the boundary segments (RK_QUERY_GRID): cell (ix, iy) covers
+    // [gx0 + ix*gcell, gx0 + (ix+1)*gcell) x [gy0 + iy*gcell, ...) in fp32 table coordinates
+    float gx0, gy0, gcell, ginv;
+    int32_t gnx, gny;
+    int32_t gcell_off, glist_off;  // offsets into TrackPool::gcell / glist
 };
 
 struct TrackPool {
@@ -50,6 +57,10 @@ struct TrackPool {
     const float2* bpt;     // [sum 2(N+1)] boundary points, per track: left row then right row, each closed
     const float4* wchunk;  // (cx, cy, r, -) bounding circle of kChunk waypoints
     const float4* bchunk;  // (cx, cy, r, -) bounding circle of kRaySegs boundary segments
+    // RK_QUERY_GRID: per track a uniform grid whose cells list the boundary segments that come within kGridMargin
+    const float4* bseg;      // [sum 2N] (px, py, vx, vy): segment start and vector, fp32, same numbering as sx/sy
+    const uint32_t* gcell;   // per cell: first list entry << 10 | number of entries
+    const uint16_t* glist;   // segment ids, cell after cell
 };
 
 struct EnvState {
@@ -63,6 +74,9 @@ struct EnvState {
     double* ep_return;
     int32_t* ep_length;
     uint32_t* reset_count;
+    // per car (RK_QUERY_GRID, R <= 15): this car's ray indices ordered by the previous step's readings, longest first,
+    // 4 bits each, bits 60..63 = 0xF when valid.  A scheduling hint only -- results do not depend on it.
+    unsigned long long* ray_order;
 };
 
 struct StepParams {

@@ -611,7 +611,7 @@ def test_native_rollout_equals_python_loop(pkg, mode):
     np.random.seed(1)
     pool = env_mod.gen_tracks(num_tracks=8, seed=1)
     widths = [int(np.random.randint(6, 10)) for _ in range(8)]
-    E, T = 768, 24
+    E, T = 768, 112
     out = []
     for native in (True, False):
         if mode == 'single':
@@ -645,7 +645,7 @@ def test_native_rollout_equals_python_loop(pkg, mode):
         out.append(snaps)
         tr.envs.close()
     for (b1, s1), (b2, s2) in zip(*out):
-        assert s1 == s2
+        assert s1[0] == s2[0] and np.allclose(s1[1:], s2[1:], rtol=1e-12)   # (episode sums are atomic adds: order-dependent ulps)
         for k in b1:
             assert torch.equal(b1[k], b2[k]), k
         assert float(b1['dones'].sum()) > 0 and torch.isfinite(b1['values']).all()
