@@ -327,86 +327,6 @@ __device__ __forceinline__ void argmin_culled5_f64_body(const TrackPool& tp, con
     for (int q = 0; q < 5; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
-// Waypoint argmin for the car centre + 4 corners (track.py:150-152, five times per car.py:79-80 / track.py:163-171).
-// The result must be numpy's float64 argmin, first index on ties, because it decides progress, checkpoints and the
-// wall test.  The search itself runs in fp32:
-//   1. the distance from the centre to ANY waypoint bounds the nearest distance from above; the waypoint found one
-//      step earlier (`hint`) is within a few indices of the new one, so the bound is tight.  One pass over the
-//      bounding circles keeps the chunks that can hold the nearest waypoint of the centre or of a corner
-//      (corners lie within kHalfDiag of the centre);
-//   2. fp32 squared distances of the five points to the kept chunks' waypoints (half a warp per chunk), every lane
-//      remembering its best and second-best per point;
-//   3. a point whose fp32 minimum is separated from every other waypoint by more than the rounding bound `eps` has
-//      exactly one candidate, and that candidate IS the float64 argmin -- no float64 arithmetic needed.  Otherwise
-//      (near ties: the point is within ~1e-4 of the bisector of two waypoints) the float64 scan above decides.
-// eps: table and query are rounded to fp32 relative to the bbox centre (|coordinate| <= diag/2, so each is off by at
-// most diag * 2^-25), hence |d32 - d64| <= 4 sqrt(2) diag 2^-25 d + 4e-7 d^2 for a squared distance; two such
-// errors meet in a comparison.  The bound used below is more than twice that.
-// Returns true (warp-uniform) when the float64 scan has to decide.
-__device__ __forceinline__ bool argmin_culled5(const TrackPool& tp, const TrackMeta& tm, const double* qx,
-                                               const double* qy, int hint, int lane, unsigned short* list,
-                                               int* out_idx) {
-    const float4* wch = tp.wchunk + tm.wchunk_off;
-    const float2* wpt = tp.wpt + tm.wp_off;
-    float fx[5], fy[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) { fx[q] = (float)(qx[q] - tm.org_x); fy[q] = (float)(qy[q] - tm.org_y); }
-    const int nwc = tm.n_wchunk;
-    const float2 wh = wpt[min(max(hint, 0), tm.n_wp - 1)];
-    const float hx = wh.x - fx[0], hy = wh.y - fy[0];
-    const float thr = sqrt_fast(hx * hx + hy * hy) + 2.f * kHalfDiag + 2e-2f;
-    int count = 0;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-    for (int c0 = 0; c0 < nwc; c0 += 32) {
-        const int ci = c0 + lane;
-        bool keep = false;
-        if (ci < nwc) {
-            const float4 cc = wch[ci];
-            const float dx = cc.x - fx[0], dy = cc.y - fy[0];
-            keep = sqrt_fast(dx * dx + dy * dy) - cc.z <= thr;
-        }
-        const unsigned m = __ballot_sync(kFull, keep);
-        if (keep) list[count + __popc(m & lt)] = (unsigned short)ci;
-        count += __popc(m);
-    }
-    __syncwarp();
-    float best[5], second[5];
-    int bi[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) { best[q] = INFINITY; second[q] = INFINITY; bi[q] = 0; }
-    const int half = lane >> 4, j = lane & 15;
-#pragma unroll 1
-    for (int it = 0; it < count; it += 2) {
-        const int my = it + half;
-        const int i = (my < count) ? (int)list[my] * kChunk + j : tm.n_wp;
-        if (i < tm.n_wp) {
-            const float2 P = wpt[i];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const float dx = P.x - fx[q], dy = P.y - fy[q];
-                const float d = fmaf(dx, dx, dy * dy);
-                second[q] = fminf(second[q], fmaxf(d, best[q]));
-                if (d < best[q]) { best[q] = d; bi[q] = i; }
-            }
-        }
-    }
-    __syncwarp();
-    const float c_err = (float)tm.max_track_distance * 6e-7f;   // > 2 * 4 sqrt(2) * 2^-25 * diag
-    bool exact = false;
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        const float m = __uint_as_float(__reduce_min_sync(kFull, __float_as_uint(best[q])));   // d >= 0: ordered like its bits
-        const float lim = m + c_err * sqrt_fast(m) + 2e-6f * m + 1e-9f;
-        const bool cand = best[q] <= lim;
-        const unsigned b = __ballot_sync(kFull, cand);
-        const unsigned amb = __ballot_sync(kFull, cand && second[q] <= lim);
-        out_idx[q] = __shfl_sync(kFull, bi[q], __ffs(b) - 1);
-        exact = exact || (b & (b - 1)) != 0u || amb != 0u;
-    }
-    return exact;
-}
-
 // atan2 for the angular sweep: Abramowitz & Stegun 4.4.49 (|error| <= 2e-8 on
 // [0, 1]) plus octant reconstruction; the result only bins points between rays
 // and its error is part of the binning slack.
@@ -482,7 +402,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 const float dc = sqrt_fast(rx * rx + ry * ry), dmin = dc - rr;   // no point of the chunk is closer than dmin
                 keep = (p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr) &&   // circle reaches into the cone |angle| <= H
                        dmin > lo && dmin <= hi;
-                if (keep && pass > 0 && dc > rr) {
+                if (keep && (pass > 0 || p.seeded) && dc > rr) {
                     // per-ray pruning: the circle subtends <= asin(rr/dc) <= (pi/2) rr/dc around its centre;
                     // keep it only if a ray in that fan has no candidate yet or one farther than dmin
                     const float uc = sweep_atan2(ly, lx) * inv_dphi + u_off;
@@ -552,11 +472,21 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
 // ---------------------------------------------------------------------------
 // Grid queries (RK_QUERY_GRID): every lane works on its own car / its own ray.
 // ---------------------------------------------------------------------------
-// Waypoint argmin of the car centre + 4 corners, ONE CAR PER LANE.  Same contract and the same fp32 reasoning as
-// argmin_culled5 (bound from the previous index, bounding circles, fp32 distances with best / second-best, a unique
-// fp32 candidate IS the float64 argmin), but nothing is shared between lanes: the lane walks the bounding circles
-// itself, remembers up to six chunks that can hold a nearest waypoint and scans them.  Returns false when the lane
-// needs the cooperative float64 scan instead (near ties, more than six chunks).
+// Waypoint argmin of the car centre + 4 corners (track.py:150-152, five times per car.py:79-80 / track.py:163-171),
+// ONE CAR PER LANE.  The result must be numpy's float64 argmin, first index on ties, because it decides progress,
+// checkpoints and the wall test.  The search itself runs in fp32:
+//   1. the distance from the centre to ANY waypoint bounds the nearest distance from above; the waypoint found one
+//      step earlier (`hint`) is within a few indices of the new one, so the bound is tight.  The lane walks the
+//      bounding circles and remembers up to six chunks that can hold the nearest waypoint of the centre or of a
+//      corner (corners lie within kHalfDiag of the centre);
+//   2. fp32 squared distances of the five points to those chunks' waypoints, with best and second-best per point;
+//   3. a point whose fp32 minimum is separated from every other waypoint by more than the rounding bound has exactly
+//      one candidate, and that candidate IS the float64 argmin -- no float64 arithmetic needed.  Otherwise (near
+//      ties: the point is within ~1e-4 of the bisector of two waypoints; more than six chunks) the function returns
+//      false and the cooperative float64 scan (argmin_culled5_f64) decides.
+// Rounding bound: table and query are rounded to fp32 relative to the bbox centre (|coordinate| <= diag/2, so each is
+// off by at most diag * 2^-25), hence |d32 - d64| <= 4 sqrt(2) diag 2^-25 d + 4e-7 d^2 for a squared distance; two
+// such errors meet in a comparison.  The bound used below is more than twice that.
 __device__ __forceinline__ bool argmin_lane5(const TrackPool& tp, const TrackMeta* tm, double x, double y,
                                              const double* cxs, const double* cys, int hint, int* out_idx) {
     const float4* wch = tp.wchunk + tm->wchunk_off;
@@ -879,7 +809,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         //         all lanes cooperating (track.py:150-152) ---------------------------
         int cidx1 = 0, cidx2 = 0, cidx3 = 0, cidx4 = 0;
         unsigned todo = __ballot_sync(kFull, moving);
-        if (QUERY == RK_QUERY_GRID) {
+        if (QUERY != RK_QUERY_EXACT_F64) {
             // every moving car searches on its own lane; the few that end in a near tie go through the cooperative
             // float64 scan below, one at a time
             bool solved = true;
@@ -901,20 +831,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
 #pragma unroll
             for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[k][l]; qy[k + 1] = S.cy[k][l]; }
             int idx[5];
-            if (QUERY == RK_QUERY_GRID) {
+            if (QUERY != RK_QUERY_EXACT_F64) {
                 int* res = reinterpret_cast<int*>(cv.list + kListCap - 16);   // past any chunk list (lists hold <= kListMax)
                 argmin_culled5_f64(tp, tm, S, l, lane, cv.list, res);
 #pragma unroll
                 for (int q = 0; q < 5; ++q) idx[q] = res[q];
                 __syncwarp();
-            } else if (QUERY == RK_QUERY_CULLED) {
-                if (argmin_culled5(tp, tm, qx, qy, __shfl_sync(kFull, lpidx, l), lane, cv.list, idx)) {
-                    int* res = reinterpret_cast<int*>(cv.list + kListCap - 16);
-                    argmin_culled5_f64(tp, tm, S, l, lane, cv.list, res);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) idx[q] = res[q];
-                    __syncwarp();
-                }
             } else
                 argmin_exact<5>(tp, tm, qx, qy, lane, idx);
             if (lane == l) { pidx = idx[0]; cidx1 = idx[1]; cidx2 = idx[2]; cidx3 = idx[3]; cidx4 = idx[4]; }  // car.py:79
@@ -1310,6 +1232,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 }
             }
             __syncwarp();
+            if (p.seeded) {
+                // Seeds: the segment each ray hit one step ago (p.st.ray_seg) and its two neighbours are tested first.
+                // A hit there is a valid upper bound on the ray's distance, and level 1 below drops every chunk that
+                // lies farther than the bounds of all rays passing through it -- typically everything but the chunks
+                // around the actual hits.  Only a hint: a seed that no longer hits changes nothing.
+                const float2* bpt = tp.bpt + tm.bpt_off;
+                const int N = tm.n_wp;
+                for (int s0 = 0; s0 < nslot; s0 += 32) {
+                    const int slot = s0 + lane;
+                    if (slot < nslot) {
+                        const int ca = slot / R;
+                        const unsigned sd = p.st.ray_seg[((size_t)ee * A + ca) * R + (slot - ca * R)];
+                        if (sd < (unsigned)(2 * N)) {
+                            const int side = sd >= (unsigned)N, pt = (int)sd - side * N;
+                            const float ox = (float)(S.x[gbase + ca] - tm.org_x), oy = (float)(S.y[gbase + ca] - tm.org_y);
+                            const float2 d = cv.dir32[slot];
+#pragma unroll 1
+                            for (int o = -1; o <= 1; ++o) {
+                                int q = pt + o;
+                                q = q < 0 ? q + N : (q >= N ? q - N : q);
+                                const float2 P = bpt[side * (N + 1) + q], Q = bpt[side * (N + 1) + q + 1];
+                                const float px = P.x - ox, py = P.y - oy, vx = Q.x - P.x, vy = Q.y - P.y;
+                                const float den = d.x * vy - d.y * vx;
+                                const float aden = fabsf(den), sgn = copysignf(1.f, den);
+                                const float tn = (px * vy - py * vx) * sgn, sn = (px * d.y - py * d.x) * sgn;
+                                if (aden > 1e-12f && tn >= -2e-4f && sn >= -2e-4f && sn <= aden + 2e-4f)
+                                    atomicMin(&cv.ray_key[slot], ((unsigned long long)__float_as_uint(fmaxf(__fdividef(tn, aden), 0.f)) << 32) |
+                                                                     (unsigned)(side * N + q));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
             for (int ca = 0; ca < A; ++ca)
                 raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
                                            S.s[gbase + ca], ca * R, lane, cv);
@@ -1330,6 +1286,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     const double2 d = cv.dir64[slot];
                     v3x = -d.y; v3y = d.x;  // track.py:178
                     const unsigned long long key = cv.ray_key[slot];
+                    if (p.seeded && p.mode != 2)
+                        p.st.ray_seg[((size_t)ee * A + ca) * R + r] = key != kNoKey ? (unsigned short)(key & 0xffffu) : (unsigned short)0xffffu;
                     if (key != kNoKey) {
                         const int i = (int)(key & 0xffffffffu);
                         const double ax = v2x[i], ay = v2y[i];
