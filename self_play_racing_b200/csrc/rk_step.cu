@@ -402,7 +402,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 const float dc = sqrt_fast(rx * rx + ry * ry), dmin = dc - rr;   // no point of the chunk is closer than dmin
                 keep = (p.cone_cos * fabsf(ly) - p.cone_sin * lx <= rr) &&   // circle reaches into the cone |angle| <= H
                        dmin > lo && dmin <= hi;
-                if (keep && (pass > 0 || p.seeded) && dc > rr) {
+                if (keep && pass > 0 && dc > rr) {
                     // per-ray pruning: the circle subtends <= asin(rr/dc) <= (pi/2) rr/dc around its centre;
                     // keep it only if a ray in that fan has no candidate yet or one farther than dmin
                     const float uc = sweep_atan2(ly, lx) * inv_dphi + u_off;
@@ -1232,40 +1232,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 }
             }
             __syncwarp();
-            if (p.seeded) {
-                // Seeds: the segment each ray hit one step ago (p.st.ray_seg) and its two neighbours are tested first.
-                // A hit there is a valid upper bound on the ray's distance, and level 1 below drops every chunk that
-                // lies farther than the bounds of all rays passing through it -- typically everything but the chunks
-                // around the actual hits.  Only a hint: a seed that no longer hits changes nothing.
-                const float2* bpt = tp.bpt + tm.bpt_off;
-                const int N = tm.n_wp;
-                for (int s0 = 0; s0 < nslot; s0 += 32) {
-                    const int slot = s0 + lane;
-                    if (slot < nslot) {
-                        const int ca = slot / R;
-                        const unsigned sd = p.st.ray_seg[((size_t)ee * A + ca) * R + (slot - ca * R)];
-                        if (sd < (unsigned)(2 * N)) {
-                            const int side = sd >= (unsigned)N, pt = (int)sd - side * N;
-                            const float ox = (float)(S.x[gbase + ca] - tm.org_x), oy = (float)(S.y[gbase + ca] - tm.org_y);
-                            const float2 d = cv.dir32[slot];
-#pragma unroll 1
-                            for (int o = -1; o <= 1; ++o) {
-                                int q = pt + o;
-                                q = q < 0 ? q + N : (q >= N ? q - N : q);
-                                const float2 P = bpt[side * (N + 1) + q], Q = bpt[side * (N + 1) + q + 1];
-                                const float px = P.x - ox, py = P.y - oy, vx = Q.x - P.x, vy = Q.y - P.y;
-                                const float den = d.x * vy - d.y * vx;
-                                const float aden = fabsf(den), sgn = copysignf(1.f, den);
-                                const float tn = (px * vy - py * vx) * sgn, sn = (px * d.y - py * d.x) * sgn;
-                                if (aden > 1e-12f && tn >= -2e-4f && sn >= -2e-4f && sn <= aden + 2e-4f)
-                                    atomicMin(&cv.ray_key[slot], ((unsigned long long)__float_as_uint(fmaxf(__fdividef(tn, aden), 0.f)) << 32) |
-                                                                     (unsigned)(side * N + q));
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
             for (int ca = 0; ca < A; ++ca)
                 raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
                                            S.s[gbase + ca], ca * R, lane, cv);
@@ -1286,8 +1252,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     const double2 d = cv.dir64[slot];
                     v3x = -d.y; v3y = d.x;  // track.py:178
                     const unsigned long long key = cv.ray_key[slot];
-                    if (p.seeded && p.mode != 2)
-                        p.st.ray_seg[((size_t)ee * A + ca) * R + r] = key != kNoKey ? (unsigned short)(key & 0xffffu) : (unsigned short)0xffffu;
                     if (key != kNoKey) {
                         const int i = (int)(key & 0xffffffffu);
                         const double ax = v2x[i], ay = v2y[i];

@@ -77,9 +77,6 @@ struct EnvState {
     // per car (RK_QUERY_GRID, R <= 15): this car's ray indices ordered by the previous step's readings, longest first,
     // 4 bits each, bits 60..63 = 0xF when valid.  A scheduling hint only -- results do not depend on it.
     unsigned long long* ray_order;
-    // per (car, ray) (RK_QUERY_CULLED): the boundary segment the ray hit one step ago (0xffff: none): seeds the sweep's
-    // per-ray pruning.  A hint as well.
-    unsigned short* ray_seg;
 };
 
 struct StepParams {
@@ -113,7 +110,6 @@ struct StepParams {
     float* obs_host0;  // optional: car 0's observation block [E, D] in mapped pinned HOST memory; each warp then also
                        // writes the complete row there with one coalesced store, so that the rows cross PCIe
                        // while the kernel is still running (culled queries, A <= 2, A*R <= 32 only)
-    int32_t seeded;    // RK_QUERY_CULLED: seed the sweep with last step's winners and prune per ray at level 1 (RK_B200_SEEDS=0 disables)
     int32_t mode;  // 0 = step, 1 = reset(mask), 2 = observe only
 };
 
