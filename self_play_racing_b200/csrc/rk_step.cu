@@ -119,8 +119,9 @@ __host__ __device__ inline size_t slot_area_bytes(int A, int R) {
     const size_t per_slot = (size_t)A * R * (16 + 8 + 8), rows = (size_t)(32 / A) * R * 4;
     return ((per_slot > rows ? per_slot : rows) + 15) / 16 * 16;
 }
+// behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode)
 __host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
-    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + 15) / 16 * 16;
+    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -1115,8 +1116,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     // rays: the warp walks over its environments, all lanes cooperating on one
     const unsigned obs_envs = __ballot_sync(kFull, want_obs && a == 0);
     const int nslot = A * R;
-    if (QUERY == RK_QUERY_GRID) {
-        // ---- rays: every lane casts the R rays of ITS car, one after the other ------------------------------------
+    if (QUERY != RK_QUERY_EXACT_F64) {
+        unsigned short* win_sh = cv.list + kListCap;   // [32][R]: fp32 winner of every ray of the warp's cars (culled mode)
+        if (QUERY == RK_QUERY_CULLED) {
+            // ---- candidate search, environment by environment, all lanes cooperating (angular sweep) ------------------
+            for (int gg = 0; gg < n_env; ++gg) {
+                const int gbase = gg * A;
+                if (!((obs_envs >> gbase) & 1u)) continue;
+                const TrackMeta tm = STAGED ? stm : tp.meta[__shfl_sync(kFull, tid, gbase)];
+                // fp32 ray directions by angle addition from the car's (cos, sin): one lane per (car, ray) slot
+                for (int s0 = 0; s0 < nslot; s0 += 32) {
+                    const int slot = s0 + lane;
+                    if (slot < nslot) {
+                        const int ca = slot / R, r = slot - ca * R;
+                        const float cc = (float)S.c[gbase + ca], ss = (float)S.s[gbase + ca];
+                        const float rc = (float)p.sensor_cos[r], rs = (float)p.sensor_sin[r];
+                        cv.dir32[slot] = make_float2(cc * rc - ss * rs, ss * rc + cc * rs);
+                        cv.ray_key[slot] = kNoKey;
+                    }
+                }
+                __syncwarp();
+                for (int ca = 0; ca < A; ++ca)
+                    raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
+                                               S.s[gbase + ca], ca * R, lane, cv);
+                for (int s0 = 0; s0 < nslot; s0 += 32) {
+                    const int slot = s0 + lane;
+                    if (slot < nslot) {
+                        const unsigned long long key = cv.ray_key[slot];
+                        win_sh[gbase * R + slot] = key != kNoKey ? (unsigned short)(key & 0xffffu) : (unsigned short)0xffffu;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- float64 distances: every lane finishes the R rays of ITS car, one after the other (full warp width: the
+        //      re-evaluation of the fp32 winners, the other cars' edges, the stores) ------------------------------------
         float* row_sh = reinterpret_cast<float*>(cv.dir64);   // car 0's rays of every environment, for the host rows
         const TrackMeta* tmr = tmp;
         const float o32x = (float)(x - tmr->org_x), o32y = (float)(y - tmr->org_y);
@@ -1125,10 +1159,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         const double* v2x = tp.v2x + 2 * (size_t)tmr->wp_off;
         const double* v2y = tp.v2y + 2 * (size_t)tmr->wp_off;
         float* orow = obs + ci * D;
-        // Pass j works on each car's j-th LONGEST ray of the previous step (p.st.ray_order): the lanes of a warp then
-        // walk rays of similar length at the same time and the traversal loops stay converged.  Only a schedule: every
-        // ray is cast exactly once whatever the order.
-        unsigned long long order = (is_car && R <= 15) ? p.st.ray_order[c] : 0ull;
+        // Grid mode: pass j works on each car's j-th LONGEST ray of the previous step (p.st.ray_order): the lanes of a
+        // warp then walk rays of similar length at the same time and the traversal loops stay converged.  Only a
+        // schedule: every ray is cast exactly once whatever the order.
+        unsigned long long order = (QUERY == RK_QUERY_GRID && is_car && R <= 15) ? p.st.ray_order[c] : 0ull;
         const bool ordered = (order >> 60) == 0xFull;
 #pragma unroll 1
         for (int j = 0; j < R; ++j) {
@@ -1140,8 +1174,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const double rc = p.sensor_cos[r], rs = p.sensor_sin[r];
                 const double dcs = dsub(dmul(cs, rc), dmul(sn, rs)), dsn = dadd(dmul(sn, rc), dmul(cs, rs));
                 v3x = -dsn; v3y = dcs;  // track.py:178
-                const RayHit hit = grid_ray(tp, tmr, o32x, o32y, (float)dcs, (float)dsn,
-                                            (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY);
+                RayHit hit;
+                if (QUERY == RK_QUERY_GRID) {
+                    hit = grid_ray(tp, tmr, o32x, o32y, (float)dcs, (float)dsn, (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY);
+                } else {
+                    const unsigned w = win_sh[lane * R + r];
+                    hit.s0 = w == 0xffffu ? -1 : (int)w; hit.s1 = -1; hit.t0 = 0.f; hit.t1 = INFINITY; hit.inside = true;
+                }
                 redo = !hit.inside;
                 if (hit.s0 >= 0) {
                     {
@@ -1181,7 +1220,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (p.obs_host0 != nullptr && a == 0) row_sh[g * R + r] = hval;
             }
         }
-        if (want_obs && R <= 15 && p.mode != 2) {
+        if (QUERY == RK_QUERY_GRID && want_obs && R <= 15 && p.mode != 2) {
             // next step's order: rank the fresh readings (re-read from the row just written: static indexing)
             float hv[16];
 #pragma unroll
@@ -1217,77 +1256,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         if (!((obs_envs >> gbase) & 1u)) continue;
         const int ee = STAGED ? genv[gg] : e_base + gg;
         const TrackMeta tm = STAGED ? stm : tp.meta[__shfl_sync(kFull, tid, gbase)];
-        if (QUERY == RK_QUERY_CULLED) {
-            // ray directions by angle addition from the car's (cos, sin): one lane per (car, ray) slot
-            for (int s0 = 0; s0 < nslot; s0 += 32) {
-                const int slot = s0 + lane;
-                if (slot < nslot) {
-                    const int ca = slot / R, r = slot - ca * R;
-                    const double cc = S.c[gbase + ca], ss = S.s[gbase + ca];
-                    const double rc = p.sensor_cos[r], rs = p.sensor_sin[r];
-                    const double dcs = dsub(dmul(cc, rc), dmul(ss, rs)), dsn = dadd(dmul(ss, rc), dmul(cc, rs));
-                    cv.dir64[slot] = make_double2(dcs, dsn);
-                    cv.dir32[slot] = make_float2((float)dcs, (float)dsn);
-                    cv.ray_key[slot] = kNoKey;
-                }
-            }
-            __syncwarp();
-            for (int ca = 0; ca < A; ++ca)
-                raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
-                                           S.s[gbase + ca], ca * R, lane, cv);
-            // float64 re-evaluation of every winner + the other cars' edges, one lane per slot
-            const double* sx = tp.sx + 2 * (size_t)tm.wp_off;
-            const double* sy = tp.sy + 2 * (size_t)tm.wp_off;
-            const double* v2x = tp.v2x + 2 * (size_t)tm.wp_off;
-            const double* v2y = tp.v2y + 2 * (size_t)tm.wp_off;
-            for (int s0 = 0; s0 < nslot; s0 += 32) {
-                const int slot = s0 + lane;
-                const bool live = slot < nslot;
-                const int ca = live ? slot / R : 0, r = live ? slot - ca * R : 0;
-                const double ox = S.x[gbase + ca], oy = S.y[gbase + ca];
-                double v3x = 0.0, v3y = 1.0, wall = INFINITY;
-                bool redo = false;
-                float hval = 0.f;
-                if (live) {
-                    const double2 d = cv.dir64[slot];
-                    v3x = -d.y; v3y = d.x;  // track.py:178
-                    const unsigned long long key = cv.ray_key[slot];
-                    if (key != kNoKey) {
-                        const int i = (int)(key & 0xffffffffu);
-                        const double ax = v2x[i], ay = v2y[i];
-                        const double v1x = dsub(ox, sx[i]), v1y = dsub(oy, sy[i]);
-                        wall = ray_segment<true>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
-                        redo = (wall == INFINITY);  // fp32 candidate rejected by the float64 test
-                    }
-                }
-                unsigned fb = __ballot_sync(kFull, redo);
-                while (fb) {  // rare: re-scan that ray exactly with the whole warp
-                    const int b = __ffs(fb) - 1;
-                    fb &= fb - 1;
-                    const int bs = s0 + b, ba = bs / R;
-                    const double2 d = cv.dir64[bs];
-                    const double t = raycast_wall_exact_one(tp, tm, S.x[gbase + ba], S.y[gbase + ba], -d.y, d.x, lane);
-                    if (lane == b) wall = t;
-                }
-                if (live) {
-                    double t = wall;
-                    if (KIND == RK_ENV_MULTI)
-                        t = fmin(fmin(t, raycast_car_edges<true>(S, gbase, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
-                    else if (t == INFINITY)
-                        t = kMaxRange;  // track.py:196-197
-                    const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
-                    hval = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
-                    obs[oi * D + r] = hval;
-                }
-                if (p.obs_host0 != nullptr) {
-                    // the complete row of car 0 (rays from lanes 0..R-1, the rest from shared memory) in ONE coalesced store
-                    bool st = live && ca == 0;
-                    if (lane >= R && lane < D) { hval = nr_sh[(lane - R) * nr_stride + gg]; st = true; }
-                    if (st) p.obs_host0[(size_t)ee * D + lane] = hval;
-                }
-            }
-            __syncwarp();
-        } else {
+        {
             for (int ca = 0; ca < A; ++ca) {
                 const double ox = S.x[gbase + ca], oy = S.y[gbase + ca];
                 const double oang = __shfl_sync(kFull, ang, gbase + ca);
