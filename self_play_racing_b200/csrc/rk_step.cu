@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const double cxs[4] = {S.cx[0][lane], S.cx[1][lane], S.cx[2][lane], S.cx[3][lane]};
                 const double cys[4] = {S.cy[0][lane], S.cy[1][lane], S.cy[2][lane], S.cy[3][lane]};
                 int idx[5];
-                solved = argmin_lane5(tp, tmp, x, y, cxs, cys, lpidx, idx);
+                solved = argmin_lane5(tp, STAGED ? &stm : tmp, x, y, cxs, cys, lpidx, idx);   // (staged: table offsets are re-based)
                 pidx = idx[0]; cidx1 = idx[1]; cidx2 = idx[2]; cidx3 = idx[3]; cidx4 = idx[4];
             }
             todo = __ballot_sync(kFull, moving && !solved);
