@@ -127,7 +127,7 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
          dev_alloc(h, &h->st.fstep, C) || dev_alloc(h, &h->st.steps, (size_t)E) ||
          dev_alloc(h, &h->st.needs_reset, (size_t)E) || dev_alloc(h, &h->st.ep_return, (size_t)E) ||
          dev_alloc(h, &h->st.ep_length, (size_t)E) || dev_alloc(h, &h->st.reset_count, (size_t)E) ||
-         dev_alloc(h, &h->st.ray_order, C) || dev_alloc(h, &h->st.ray_rmax, C) ||
+         dev_alloc(h, &h->st.ray_order, C) ||
          dev_alloc(h, &h->sensor_angles, (size_t)3 * R);
     if (rc) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_create: %s", h->err[0] ? h->err : "cudaSetDevice failed");
@@ -395,8 +395,6 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
         p.n_ctas = h->n_ctas;
         p.stage_bytes = h->stage_bytes;
         p.n_shells = ns;
-        p.shell_margin = 3.0f;
-        if (const char* env = getenv("RK_B200_SHELL_MARGIN")) p.shell_margin = (float)atof(env);
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;

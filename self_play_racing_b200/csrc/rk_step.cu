@@ -369,13 +369,10 @@ __device__ __forceinline__ float sweep_atan2(float y, float x) {
 // Segments seen under ~180 degrees or closer than 0.5 (the origin practically on
 // the wall) fall back to an explicit straddle test against every ray.
 
-// `r1`: data-driven radius of the first shell -- the car's farthest wall hit one step ago plus its possible change
-// (StepParams::st.ray_rmax; +inf when unknown).  If every ray finds a hit within r1 in the first pass, no chunk farther
-// than r1 can hold a nearer one and the second pass is skipped.
 template <int KIND>
 __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const TrackMeta& tm, const StepParams& p,
                                                      double oxd, double oyd, double hcd, double hsd, int slot0,
-                                                     int lane, const CullView& cv, float r1) {
+                                                     int lane, const CullView& cv) {
     const float4* bch = tp.bchunk + tm.bchunk_off;
     const float2* bpt = tp.bpt + tm.bpt_off;
     const float ox = (float)(oxd - tm.org_x), oy = (float)(oyd - tm.org_y);
@@ -388,10 +385,10 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     const float inv_dphi = p.inv_dphi, u_off = p.cone_half * inv_dphi;
     const float wrap_thr = 3.1405926f * inv_dphi;
     const float range = (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < p.n_shells; ++pass) {
         // shell of this pass: chunks whose nearest possible point lies in (lo, hi]
-        const float lo = (pass == 0) ? -INFINITY : r1;
-        const float hi = (pass == 0) ? fminf(r1, range) : range;
+        const float lo = (pass == 0) ? -INFINITY : p.shell[pass - 1];
+        const float hi = fminf(p.shell[pass], range);
         if (!(hi > lo)) break;
         // ---- level 1 ----
         int count = 0;
@@ -470,14 +467,6 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
             }
         }
         __syncwarp();
-        if (pass == 0) {   // every ray certified by a hit within the first shell?
-            bool open = false;
-            for (int k = lane; k < R; k += 32) {
-                const unsigned tb = (unsigned)(keys[k] >> 32);
-                open = open || tb == 0xffffffffu || !(__uint_as_float(tb) <= r1 - 1e-2f);
-            }
-            if (!__any_sync(kFull, open)) break;
-        }
     }
 }
 
@@ -1129,8 +1118,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     const int nslot = A * R;
     if (QUERY != RK_QUERY_EXACT_F64) {
         unsigned short* win_sh = cv.list + kListCap;   // [32][R]: fp32 winner of every ray of the warp's cars (culled mode)
-        const float rmax_prev = (QUERY == RK_QUERY_CULLED && is_car && p.shell_margin >= 0.f) ? p.st.ray_rmax[c] : 0.f;
-        float rmax_new = 0.f;
         if (QUERY == RK_QUERY_CULLED) {
             // ---- candidate search, environment by environment, all lanes cooperating (angular sweep) ------------------
             for (int gg = 0; gg < n_env; ++gg) {
@@ -1149,11 +1136,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                     }
                 }
                 __syncwarp();
-                for (int ca = 0; ca < A; ++ca) {
-                    const float rm = __shfl_sync(kFull, rmax_prev, gbase + ca);
+                for (int ca = 0; ca < A; ++ca)
                     raycast_walls_culled<KIND>(tp, tm, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
-                                               S.s[gbase + ca], ca * R, lane, cv, rm > 0.f ? rm + p.shell_margin : INFINITY);
-                }
+                                               S.s[gbase + ca], ca * R, lane, cv);
                 for (int s0 = 0; s0 < nslot; s0 += 32) {
                     const int slot = s0 + lane;
                     if (slot < nslot) {
@@ -1226,7 +1211,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
             }
             if (want_obs) {
                 double t = wall;
-                rmax_new = fmaxf(rmax_new, (float)wall);   // +inf when a ray saw no wall within range
                 if (KIND == RK_ENV_MULTI)
                     t = fmin(fmin(t, raycast_car_edges<true>(S, base, A, x, y, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
                 else if (t == INFINITY)
@@ -1236,8 +1220,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (p.obs_host0 != nullptr && a == 0) row_sh[g * R + r] = hval;
             }
         }
-        if (QUERY == RK_QUERY_CULLED && want_obs && p.mode != 2)
-            p.st.ray_rmax[c] = rmax_new < 1e30f ? rmax_new : 0.f;   // 0 = unknown: a single full-range pass next time
         if (QUERY == RK_QUERY_GRID && want_obs && R <= 15 && p.mode != 2) {
             // next step's order: rank the fresh readings (re-read from the row just written: static indexing)
             float hv[16];

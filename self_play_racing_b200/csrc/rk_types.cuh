@@ -77,9 +77,6 @@ struct EnvState {
     // per car (RK_QUERY_GRID, R <= 15): this car's ray indices ordered by the previous step's readings, longest first,
     // 4 bits each, bits 60..63 = 0xF when valid.  A scheduling hint only -- results do not depend on it.
     unsigned long long* ray_order;
-    // per car (RK_QUERY_CULLED): the farthest wall hit of the car's rays one step ago (0: unknown) -- the radius of the
-    // sweep's first shell.  A hint as well.
-    float* ray_rmax;
 };
 
 struct StepParams {
@@ -98,7 +95,6 @@ struct StepParams {
     int32_t epw;       // environments per warp (<= 32 / A): fewer means more warps for the cooperative queries
     int32_t n_shells;  // distance shells of the ray sweep: (-inf, shell[0]], (shell[0], shell[1]], ...
     float shell[4];
-    float shell_margin;  // culled mode: first shell = last step's farthest wall hit + this; < 0: one full-range pass
     int32_t E, A, R, D;
     int32_t env_begin, env_end;  // environments stepped by this launch (plain launch only)
     int32_t autoreset, max_steps;
