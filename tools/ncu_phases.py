@@ -8,7 +8,7 @@ import ncu_lines as nl
 
 MARKERS = [(r'__forceinline__ double dmul', 'f64 helpers / shuffles'), (r'void argmin_exact', 'argmin_exact'),
            (r'double ray_segment\(', 'ray_segment f64'), (r'void raycast_walls_exact', 'walls exact (fallback)'),
-           (r'double raycast_car_edges', 'car edges f64'), (r'void argmin_culled5', 'argmin culled'), (r'bool argmin_lane5', 'argmin lane (grid)'), (r'RayHit grid_ray', 'grid ray DDA'), (r'// ---- rays, one per lane', 'grid rays: setup / f64 winners / store'),
+           (r'double raycast_car_edges', 'car edges f64'), (r'void argmin_culled5_f64', 'argmin f64 slow path'), (r'float sweep_atan2', 'sweep atan2'), (r'bool argmin_lane5', 'argmin lane (grid)'), (r'RayHit grid_ray', 'grid ray DDA'), (r'// ---- candidate search, environment by environment', 'sweep: per-env dirs / keys / winners out'), (r'// ---- float64 distances: every lane finishes', 'lane-per-car ray loop: f64 winners, stores'),
            (r'void raycast_walls_culled', 'ray sweep setup'), (r'// ---- level 1 ----', 'ray level 1'),
            (r'// ---- level 2 ----', 'ray level 2'), (r'int philox_start_slot', 'philox'),
            (r'^__global__', 'prologue / load'), (r'// ---- D:', 'dynamics'), (r'// ---- W:', 'argmin loop glue'),
