@@ -266,13 +266,16 @@ class BatchedRacingVecEnv:
         policy_act(self._opp_params, obs[1] if self._opp_params is not None else None, actions[1],
                    seed=self.seed ^ 0x5eed0bb, counter=self._opp_counter)
 
-    def step_into(self, actions, obs_out, reward_out, done_out, start_slot=None):
+    def step_into(self, actions, obs_out, reward_out, done_out, start_slot=None, opponent_actions=None):
         """Zero-copy rollout step: `actions` [A,E,2] already holds the learner's
         action in actions[0]; the kernel writes the successor observation
         [A,E,D], reward [A,E] and done [E] (float32) straight into the caller's
-        rollout-buffer slots.  No host synchronisation."""
+        rollout-buffer slots.  No host synchronisation.  `opponent_actions` [E,2]
+        replaces the opponent's inference (replay of recorded trajectories)."""
         be, io = self.be, self.be._io
-        if self.selfplay:
+        if self.selfplay and opponent_actions is not None:
+            actions[1].copy_(opponent_actions)
+        elif self.selfplay:
             self._opponent_act(self._obs_cur, actions)
         io.actions, io.obs = actions.data_ptr(), obs_out.data_ptr()
         io.reward_f32, io.done_f32 = reward_out.data_ptr(), done_out.data_ptr()

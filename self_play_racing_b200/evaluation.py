@@ -32,7 +32,7 @@ def _aggregate(all_metrics):
 
 
 def evaluate_batched(kind, agent, track_pool, track_widths, num_tracks=20, num_runs=10, max_steps=None,
-                     num_sensors=11, device=None, seed=0, query='culled'):
+                     num_sensors=11, device=None, seed=0, query='culled', start_slot=None):
     """All num_tracks x num_runs episodes of `evaluate_single_agent_overall` /
     `evaluate_multi_agent_overall` at once.  Episode (t, r) runs on track t with
     width track_widths[r] (the reference indexes widths by run, SURVEY quirk 9);
@@ -57,7 +57,9 @@ def evaluate_batched(kind, agent, track_pool, track_widths, num_tracks=20, num_r
     be.set_tracks_from_control_points(cps, widths, env_to_track=e2t)
     dev = be.device
     params = flatten_agent(agent.state_dict()).to(dev)
-    obs = be.reset()                                              # [A, E, D]
+    if start_slot is not None:   # the grid slots of each episode's reset (int [E, A]); default: the backend's Philox shuffle
+        start_slot = torch.as_tensor(np.ascontiguousarray(start_slot, dtype=np.int32)).to(dev)
+    obs = be.reset(start_slot=start_slot)                        # [A, E, D]
     alive = torch.ones(E, dtype=torch.bool, device=dev)
     total_reward = torch.zeros(A, E, dtype=torch.float64, device=dev)
     distance = torch.zeros(A, E, dtype=torch.float64, device=dev)

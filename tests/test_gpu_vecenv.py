@@ -649,3 +649,93 @@ def test_native_rollout_equals_python_loop(pkg, mode):
         for k in b1:
             assert torch.equal(b1[k], b2[k]), k
         assert float(b1['dones'].sum()) > 0 and torch.isfinite(b1['values']).all()
+
+
+def test_rollout_buffers_match_reference_collect_rollout(pkg, golden):
+    """The reference's own SelfPlayPPO.collect_rollout (agent/ppo.py:97-132) over SyncVectorEnv(RecordEpisodeStatistics(
+    SelfPlayWrapper(MultiRacingEnv))) -- recorded by tools/make_golden.py record_rollout_buffers, two rollouts with
+    update_opponent() in between -- against the device rollout buffers: slot t of obs / dones holds next_obs / next_done
+    BEFORE step t, rewards / values / logprobs belong to step t, the rebuilt envs start fresh while slot 0 carries the
+    stale next_obs, episode statistics are those of RecordEpisodeStatistics.  The learner's and the
+    opponent's recorded actions and the recorded start slots are injected."""
+    env_mod, agent_mod, _ = pkg
+    g = golden('rollout_selfplay16')
+    cps = np.split(g['pool'], np.cumsum(g['pool_sizes'])[:-1])
+    widths = [float(w) for w in g['widths']]
+    T, E = g['actions0'].shape[:2]
+    fns = [(lambda i=i: env_mod.SelfPlayWrapper(env_mod.MultiRacingEnv(num_agents=2, num_sensors=11, track_pool=cps,
+                                                                      track_id=i % len(cps), track_width=widths), 0))
+           for i in range(E)]
+    vec = env_mod.BatchedRacingVecEnv(fns, query='culled')
+    be, dev = vec.be, vec.be.device
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('sd.')}
+    agent = agent_mod.Agent(vec.single_observation_space, vec.single_action_space).to(dev)
+    agent.load_state_dict(sd)
+    D = be.D
+    buf = dict(obs=torch.zeros(T + 1, 2, E, D, device=dev), actions=torch.zeros(T, 2, E, 2, device=dev),
+               dones=torch.zeros(T + 1, E, device=dev), rewards=torch.zeros(T, 2, E, device=dev))
+    t_ = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    for it in range(2):
+        # update_opponent(): the envs are rebuilt (fresh reset with new grid slots), slot 0 keeps the carried next_obs
+        vec.reset_device(start_slot=t_(g[f'slots_init{it}'], torch.int32))
+        be.ep_stats.zero_()
+        buf['obs'][0, 0].copy_(t_(g[f'obs{it}'][0]))
+        buf['dones'][0].copy_(t_(g[f'dones{it}'][0]))
+        buf['actions'][:, 0].copy_(t_(g[f'actions{it}']))
+        opp, slots = t_(g[f'opp_actions{it}']), t_(g[f'slots{it}'], torch.int32)
+        for t in range(T):
+            vec.step_into(buf['actions'][t], buf['obs'][t + 1], buf['rewards'][t], buf['dones'][t + 1],
+                          start_slot=slots[t], opponent_actions=opp[t])
+        obs = buf['obs'][:, 0].cpu().numpy()
+        np.testing.assert_allclose(obs[1:T], g[f'obs{it}'][1:], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(obs[T], g[f'next_obs{it}'], rtol=0, atol=1e-6)
+        np.testing.assert_array_equal(buf['dones'][1:T].cpu().numpy(), g[f'dones{it}'][1:])
+        np.testing.assert_array_equal(buf['dones'][T].cpu().numpy().astype(bool), g[f'next_done{it}'])
+        np.testing.assert_allclose(buf['rewards'][:, 0].cpu().numpy(), g[f'rewards{it}'], rtol=1e-6, atol=1e-5)  # float32 buffers
+        # a reset shows as reward 0 one step after a done (NEXT_STEP), exactly where the reference reset
+        np.testing.assert_array_equal((buf['dones'][:T] > 0).cpu().numpy() & (np.arange(T)[:, None] > 0), g[f'reset{it}'] & (np.arange(T)[:, None] > 0))
+        n, sr, sl = len(g[f'ep_r{it}']), g[f'ep_r{it}'].sum(), g[f'ep_l{it}'].sum()
+        st = be.ep_stats.cpu().numpy()
+        assert int(st[2]) == n and abs(st[0] - sr) < 1e-6 and int(st[1]) == int(sl)
+        # values / log-probs of the recorded (obs, action) pairs under the same weights (torch path of the host layer)
+        with torch.no_grad():
+            o = t_(g[f'obs{it}']).reshape(T * E, D)
+            _, lp, _, v = agent.get_action_and_value(o, t_(g[f'actions{it}']).reshape(T * E, 2))
+        np.testing.assert_allclose(v.reshape(T, E).cpu().numpy(), g[f'values{it}'], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(lp.reshape(T, E).cpu().numpy(), g[f'logprobs{it}'], rtol=0, atol=2e-4)
+        assert g[f'dones{it}'].sum() >= 5
+    vec.close()
+
+
+def test_batched_evaluation_matches_reference_metrics(pkg, golden):
+    """evaluate.py's protocol: utils/metrics.py eval_single_agent / eval_multi_agent run on the UNMODIFIED reference envs
+    (tools/make_golden.py record_eval) against evaluate_batched on the device.  The policy is a hand-wired, deterministic
+    Agent (log_std = -100: sampling returns the mean) that drives complete laps; both sides evaluate the same MLP in
+    float32 by different code, so actions agree to ~1e-6 and the episodes stay together: flags / placement exact, steps
+    within 1, totals within 2e-3 relative."""
+    env_mod, agent_mod, _ = pkg
+    from self_play_racing_b200.evaluation import evaluate_batched
+    g = golden('eval_protocol')
+    cps = np.split(g['pool'], np.cumsum(g['pool_sizes'])[:-1])
+    run_w = [float(w) for w in g['run_widths']]
+    for kind, key, sdk, nt in (('single', 'single', 'sd1.', 3), ('multi', 'multi', 'sd2.', 2)):
+        proto = env_mod.RacingEnv(num_sensors=11) if kind == 'single' else env_mod.MultiRacingEnv(num_agents=2, num_sensors=11)
+        osp = proto.observation_space if kind == 'single' else proto.observation_space['0']
+        asp = proto.action_space if kind == 'single' else proto.action_space['0']
+        agent = agent_mod.Agent(osp, asp)
+        agent.load_state_dict({k[len(sdk):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(sdk)})
+        kw = {}
+        if kind == 'multi':
+            kw['start_slot'] = g['multi_slots']
+        res = evaluate_batched(kind, agent, cps[:nt], run_w, num_tracks=nt, num_runs=len(run_w), **kw)
+        ref = g[key]
+        assert res['num_episodes'] == len(ref) and res['num_successful'] == int(ref[:, 3].sum()) == len(ref)
+        for m, r in zip(res['all_episodes'], ref):
+            assert m['finished'] == bool(r[3]) and m['crashed'] == bool(r[4])
+            assert abs(m['steps'] - r[1]) <= 1
+            assert abs(m['progress'] - r[2]) < 1e-9
+            assert abs(m['total_reward'] - r[0]) <= 2e-3 * abs(r[0])
+            assert abs(m['total_distance'] - r[6]) <= 2e-3 * r[6] and abs(m['speed'] - r[5]) < 2e-2
+            if kind == 'multi':
+                assert m['placement'] == int(r[7])
+        assert abs(res['avg_steps'] - ref[:, 1].mean()) <= 1 and res['success_rate'] == 1.0 and res['crash_rate'] == 0.0

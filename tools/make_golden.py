@@ -577,6 +577,179 @@ def record_injected_multi(name='injected_multi2'):
          truncated=TRUNC, state=ST, start_order=SO, placement=PL, flags=FLAGS, finished_step=FS, checkpoints=CP)
 
 
+# ------------------------------------------- rollout buffers through the reference's own PPO loop
+# The UNMODIFIED SelfPlayPPO.collect_rollout (agent/ppo.py:97-132) over SyncVectorEnv(RecordEpisodeStatistics(
+# SelfPlayWrapper(MultiRacingEnv))) (agent/self_play_ppo.py:19-29), two consecutive rollouts with update_opponent()
+# in between (the envs are rebuilt but next_obs is carried over: SURVEY quirk 10).  Observer subclasses record what
+# the device replay has to inject: the learner's and the opponent's sampled actions and the start slots of every
+# reset; they do not change any arithmetic.
+def record_rollout_buffers(name='rollout_selfplay16', T=96, E=16):
+    import gymnasium as gym
+    from agent.self_play_ppo import SelfPlayPPO
+    from configs.self_play_config import hyperparams_config
+    pool, widths = procedural_pool()
+    log = {'slots': [], 'opp': []}
+
+    class RecMulti(MultiRacingEnv):            # records the slot permutation of every reset
+        def reset(self, seed=None, options=None):
+            st = np.random.get_state()
+            out = super().reset(seed=seed, options=options)
+            rs = np.random.RandomState(); rs.set_state(st)
+            order = list(range(self.num_agents)); rs.shuffle(order)
+            self.last_slots = np.array([order.index(i) for i in range(self.num_agents)], np.int64)
+            self.n_resets = getattr(self, 'n_resets', 0) + 1
+            return out
+
+    class RecOpponent:                          # a frozen snapshot whose sampled actions are written down
+        def __init__(self, agent):
+            self.agent, self.last = agent, None
+        def get_action_and_value(self, obs):
+            out = self.agent.get_action_and_value(obs)
+            self.last = out[0].squeeze(0).numpy().copy()
+            return out
+
+    cfg = hyperparams_config()
+    cfg.update(num_envs=E, num_steps=T, cuda=False)
+    cfg['batch_size'] = T * E
+    cfg['minibatch_size'] = cfg['batch_size'] // cfg['num_minibatches']
+    env_fn = lambda i: RecMulti(num_agents=2, num_sensors=11, track_pool=pool, track_id=i % len(pool), track_width=widths)
+    np.random.seed(5)
+    trainer = SelfPlayPPO(env_fn, cfg, device='cpu')
+    for w in trainer.envs.envs:                 # the CPU arm: opponent tensors stay on the host
+        w.env.device = torch.device('cpu')
+    trainer.agent.log_std.data.fill_(-0.3)
+    torch.manual_seed(11)
+    c = cfg
+    z = lambda *sh: torch.zeros(*sh)
+    obs, actions = z(T, E, 19), z(T, E, 2)
+    logprobs, dones, rewards, values = (z(T, E) for _ in range(4))
+    init_obs, _ = trainer.envs.reset()
+    next_obs, next_done = torch.from_numpy(init_obs), torch.zeros(E, dtype=torch.bool)
+    out = {}
+    snap = trainer.snapshot_agent()
+    with torch.no_grad():
+        for p_ in snap.parameters():
+            p_.add_(0.3 * torch.randn_like(p_))    # an opponent that differs from the learner
+    for it in range(2):
+        trainer.opponent_pool = [] if it == 0 else [RecOpponent(snap)]   # rollout 0: pool-empty random opponent
+        trainer.update_opponent()                  # rebuilds the envs, does NOT reset next_obs (quirk 10)
+        envs = trainer.envs.envs                   # RecordEpisodeStatistics(SelfPlayWrapper(RecMulti))
+        for w in envs:
+            w.env.device = torch.device('cpu')
+        slots0 = np.stack([w.env.env.last_slots for w in envs])      # the rebuild's own reset
+        # observer of the vector env's step: which envs reset, with which slots; which opponent actions were used
+        opp_act = np.zeros((T, E, 2), np.float32)
+        slot_log = np.zeros((T, E, 2), np.int64)
+        reset_log = np.zeros((T, E), bool)
+        step_no = [0]
+        orig_samplers = []
+        for i, w in enumerate(envs):
+            sp = w.env.opponent_action_space
+            orig = sp.sample
+            def sample(orig=orig, i=i):
+                a = orig()
+                opp_act[step_no[0], i] = a
+                return a
+            sp.sample = sample
+        vec_step = trainer.envs.step
+        def step(acts):
+            t = step_no[0]
+            before = [w.env.env.n_resets for w in envs]
+            res = vec_step(acts)
+            for i, w in enumerate(envs):
+                if w.env.env.n_resets != before[i]:
+                    reset_log[t, i] = True
+                    slot_log[t, i] = w.env.env.last_slots
+                elif trainer.curr_opponent is not None:
+                    opp_act[t, i] = trainer.curr_opponent.last if False else opp_act[t, i]
+            step_no[0] += 1
+            return res
+        trainer.envs.step = step
+        if trainer.curr_opponent is not None:       # per-env opponent actions: wrap the wrapper's policy call
+            rec = trainer.curr_opponent
+            for i, w in enumerate(envs):
+                class PerEnv:
+                    def __init__(self, i): self.i = i
+                    def get_action_and_value(self, o):
+                        res = rec.agent.get_action_and_value(o)
+                        opp_act[step_no[0], self.i] = res[0].squeeze(0).numpy()
+                        return res
+                w.env.set_opponent(PerEnv(i))
+        res = trainer.collect_rollout(obs, actions, logprobs, dones, rewards, values, next_obs, next_done)
+        obs, actions, logprobs, dones, rewards, values, next_obs, next_done, ep_info = res
+        out.update({f'obs{it}': obs.numpy().copy(), f'actions{it}': actions.numpy().copy(),
+                    f'logprobs{it}': logprobs.numpy().copy(), f'dones{it}': dones.numpy().copy(),
+                    f'rewards{it}': rewards.numpy().copy(), f'values{it}': values.numpy().copy(),
+                    f'next_obs{it}': next_obs.numpy().copy(), f'next_done{it}': next_done.numpy().copy(),
+                    f'opp_actions{it}': opp_act.copy(), f'reset{it}': reset_log.copy(), f'slots{it}': slot_log.copy(),
+                    f'slots_init{it}': slots0,
+                    f'ep_r{it}': np.array([e['reward'] for e in ep_info]), f'ep_l{it}': np.array([e['length'] for e in ep_info])})
+        print(f'  rollout {it}: {len(ep_info)} episodes, dones {int(dones.sum())}, resets {int(reset_log.sum())}')
+    sd = {k: v.numpy() for k, v in trainer.agent.state_dict().items()}
+    save(name, pool_sizes=np.array([len(p) for p in pool]), pool=np.concatenate(pool), widths=np.array(widths, np.float64),
+         **out, **{'sd.' + k: v for k, v in sd.items()})
+
+
+# ------------------------------------------------ evaluate.py's protocol on the reference envs
+def wired_agent(obs_space, act_space, multi):
+    """An Agent (reference class, reference state_dict keys) whose weights are set by hand to a ray-balancing
+    controller: steer towards the side whose rays see farther, constant throttle.  Deterministic with log_std = -100
+    (Normal(mu, 4e-44).sample() == mu), so that the reference loop and the device batch act identically."""
+    ag = Agent(obs_space, act_space)
+    R = 11
+    with torch.no_grad():
+        for p_ in ag.actor_mu.parameters():
+            p_.zero_()
+        w = torch.linspace(-1.0, 1.0, R)            # ray i points to relative angle ~ w_i: positive = left
+        ag.actor_mu[0].weight[0, :R] = 0.05 * w      # h0 ~ 0.05 * sum_i w_i ray_i  (tanh in its linear range)
+        ag.actor_mu[2].weight[0, 0] = 1.0
+        ag.actor_mu[4].weight[0, 0] = 60.0           # steer = tanh(60 h)
+        ag.actor_mu[4].bias[1] = float(np.arctanh(0.35 if not multi else 2 * 0.35 - 1))   # throttle 0.35 after either mapping
+        ag.log_std.fill_(-100.0)
+    return ag
+
+
+def record_eval(name='eval_protocol'):
+    sys.path.insert(0, '/root/reference')
+    import types as _t
+    for mod in ('matplotlib', 'matplotlib.pyplot'):       # utils/metrics.py imports pyplot at module level; never called here
+        sys.modules.setdefault(mod, _t.ModuleType(mod))
+    from utils.metrics import eval_single_agent, eval_multi_agent
+    pool, widths = procedural_pool()
+    pool, runs_w = pool[:3], [7, 9]
+    out = {}
+    dev = torch.device('cpu')
+    env = RacingEnv(num_sensors=11)
+    ag1 = wired_agent(env.observation_space, env.action_space, multi=False)
+    rows = []
+    for t in range(len(pool)):
+        for r, w in enumerate(runs_w):      # evaluate.py:21-31: width indexed by RUN (SURVEY quirk 9)
+            m = eval_single_agent(RacingEnv(num_sensors=11, track_pool=pool, track_id=t, track_width=w), ag1, dev)
+            rows.append([m['total_reward'], m['steps'], m['progress'], m['finished'], m['crashed'], m['speed'], m['total_distance']])
+            print('  single', t, r, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in m.items()})
+    out['single'] = np.array(rows, np.float64)
+    menv = MultiRacingEnv(num_agents=2, num_sensors=11)
+    ag2 = wired_agent(menv.observation_space['0'], menv.action_space['0'], multi=True)
+    rows, slots = [], []
+    np.random.seed(9)
+    for t in range(2):
+        for r, w in enumerate(runs_w):
+            e = MultiRacingEnv(num_agents=2, num_sensors=11, track_pool=pool, track_id=t, track_width=w)
+            st = np.random.get_state()
+            m = eval_multi_agent(e, ag2, dev)
+            rs = np.random.RandomState(); rs.set_state(st)
+            order = [0, 1]; rs.shuffle(order)
+            slots.append([order.index(0), order.index(1)])
+            rows.append([m['total_reward'], m['steps'], m['progress'], m['finished'], m['crashed'], m['speed'], m['total_distance'],
+                         m['placement'] or 0])
+            print('  multi', t, r, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in m.items()})
+    out['multi'] = np.array(rows, np.float64)
+    out['multi_slots'] = np.array(slots, np.int64)
+    save(name, pool_sizes=np.array([len(p) for p in pool]), pool=np.concatenate(pool), run_widths=np.array(runs_w, np.float64),
+         **out, **{'sd1.' + k: v.numpy() for k, v in ag1.state_dict().items()},
+         **{'sd2.' + k: v.numpy() for k, v in ag2.state_dict().items()})
+
+
 # ------------------------------------------------------- GAE and Agent pins
 def record_gae_agent():
     rs = np.random.RandomState(0)
@@ -613,6 +786,12 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'laps':      # only the scripted-driver recordings
         record_laps()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'rollout':
+        record_rollout_buffers()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'eval':
+        record_eval()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'injected':  # only the injected-state recordings
         record_injected_single()
         record_injected_multi()
@@ -631,3 +810,5 @@ if __name__ == '__main__':
     record_laps()
     record_injected_single()
     record_injected_multi()
+    record_rollout_buffers()
+    record_eval()
