@@ -237,3 +237,28 @@ def test_injected_multi_branches(golden):
     assert list(g['placement'][0][tie]) == [2, 1] and list(g['reward'][0][tie]) == [0.0, 250.0]   # exact tie -> higher index
     both = names.index('both_finish_exact_tie')
     assert g['flags'][0][both][:, 1].all() and list(g['placement'][0][both]) == [2, 1]
+
+
+def test_rollout_buffers_of_the_reference_loop(golden):
+    """SelfPlayPPO.collect_rollout of the reference (tools/make_golden.py record_rollout_buffers) replayed through the
+    oracle: buffer slot semantics, NEXT_STEP resets inside SelfPlayWrapper envs, RecordEpisodeStatistics."""
+    g = golden('rollout_selfplay16')
+    cps = np.split(g['pool'], np.cumsum(g['pool_sizes'])[:-1])
+    tracks = O.make_pool(cps, list(g['widths']))
+    T, E = g['actions0'].shape[:2]
+    for it in range(2):
+        env = O.OracleVecEnv(tracks, np.arange(E) % len(tracks), kind='multi', num_agents=2, num_sensors=11)
+        env.reset(start_order=g[f'slots_init{it}'])
+        ep_r, ep_l = [], []
+        for t in range(T):
+            a = np.stack([g[f'actions{it}'][t], g[f'opp_actions{it}'][t]], axis=1)
+            obs, r, te, tr, info = env.step(a, start_order=g[f'slots{it}'][t])
+            o, rew, done, _ = O.OracleVecEnv.selfplay_view(obs, r, te, tr)
+            nxt = g[f'obs{it}'][t + 1] if t + 1 < T else g[f'next_obs{it}']
+            nd = g[f'dones{it}'][t + 1] if t + 1 < T else g[f'next_done{it}']
+            np.testing.assert_allclose(o, nxt, rtol=0, atol=1e-6, err_msg=f'rollout {it} step {t}')
+            np.testing.assert_array_equal(done, nd.astype(bool))
+            np.testing.assert_allclose(rew, g[f'rewards{it}'][t], rtol=1e-6, atol=1e-5)
+            ep_r += list(info['episode_r'][info['_episode']]); ep_l += list(info['episode_l'][info['_episode']])
+        np.testing.assert_allclose(ep_r, g[f'ep_r{it}'], rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(ep_l, g[f'ep_l{it}'])
