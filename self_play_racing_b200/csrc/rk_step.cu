@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         //         all lanes cooperating (track.py:150-152) ---------------------------
         int cidx1 = 0, cidx2 = 0, cidx3 = 0, cidx4 = 0;
         unsigned todo = __ballot_sync(kFull, moving);
-        if (QUERY != RK_QUERY_EXACT_F64) {
+        if (QUERY != RK_QUERY_EXACT_F64 && p.lane_argmin) {
             // every moving car searches on its own lane; the few that end in a near tie go through the cooperative
             // float64 scan below, one at a time
             bool solved = true;
@@ -866,8 +866,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 if (o == a) continue;
                 const int li = base + min(a, o), lj = base + max(a, o);  // the reference's (i, j), i < j
                 bool hit = true;  // multi_car.py:16-43: 4 axes, strict separation test
+                {   // both rectangles lie within sqrt(5) of their centres: farther apart than 2 sqrt(5) they cannot touch
+                    const double ddx = S.x[lj] - S.x[li], ddy = S.y[lj] - S.y[li];
+                    if (ddx * ddx + ddy * ddy > 20.001) hit = false;
+                }
 #pragma unroll 1
-                for (int ax = 0; ax < 4; ++ax) {
+                for (int ax = 0; hit && ax < 4; ++ax) {
                     const int lo = (ax < 2) ? li : lj, k0 = ax & 1;
                     const double ex = dsub(S.cx[k0 + 1][lo], S.cx[k0][lo]), ey = dsub(S.cy[k0 + 1][lo], S.cy[k0][lo]);
                     const double nx = -ey, ny = ex;
@@ -1149,9 +1153,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 __syncwarp();
             }
         }
-        // ---- float64 distances: every lane finishes the R rays of ITS car, one after the other (full warp width: the
-        //      re-evaluation of the fp32 winners, the other cars' edges, the stores) ------------------------------------
         float* row_sh = reinterpret_cast<float*>(cv.dir64);   // car 0's rays of every environment, for the host rows
+        if (QUERY == RK_QUERY_CULLED) {
+            // ---- float64 distances, one lane per (environment, car, ray) slot of the WHOLE warp: the re-evaluation of the
+            //      fp32 winners, the other cars' edges and the stores run at full width whatever the number of cars per
+            //      warp (small batches give a warp 2 environments: 44 slots are 2 passes, not 11 at 4 lanes)
+            const int total = n_env * nslot;
+            const float inv_nslot = 1.f / (float)nslot, inv_R = 1.f / (float)R;
+#pragma unroll 1
+            for (int s0 = 0; s0 < total; s0 += 32) {
+                const int slot = min(s0 + lane, total - 1);
+                const int gg = (int)(((float)slot + 0.5f) * inv_nslot);          // exact for these small integers
+                const int rem = slot - gg * nslot, ca = (int)(((float)rem + 0.5f) * inv_R), r = rem - ca * R;
+                const int lc = gg * A + ca;                                        // the lane that holds this ray's car
+                const bool live = s0 + lane < total && ((obs_envs >> (gg * A)) & 1u);
+                const int tidr = __shfl_sync(kFull, tid, lc);
+                const TrackMeta* tmr = STAGED ? &stm : tp.meta + tidr;
+                const double ox = S.x[lc], oy = S.y[lc];
+                double v3x = 0.0, v3y = 1.0, wall = INFINITY;
+                bool redo = false;
+                if (live) {
+                    const double cc = S.c[lc], ss = S.s[lc], rc = p.sensor_cos[r], rs = p.sensor_sin[r];
+                    v3x = -dadd(dmul(ss, rc), dmul(cc, rs)); v3y = dsub(dmul(cc, rc), dmul(ss, rs));  // track.py:178
+                    const unsigned w = win_sh[lc * R + r];
+                    if (w != 0xffffu) {
+                        const size_t i = 2 * (size_t)tmr->wp_off + w;
+                        const double ax = tp.v2x[i], ay = tp.v2y[i];
+                        const double v1x = dsub(ox, tp.sx[i]), v1y = dsub(oy, tp.sy[i]);
+                        wall = ray_segment<true>(v1x, v1y, ax, ay, dsub(dmul(ax, v1y), dmul(ay, v1x)), v3x, v3y, kWallMinDot);
+                        redo = wall == INFINITY;  // fp32 candidate rejected by the float64 test
+                    }
+                }
+                unsigned fb = __ballot_sync(kFull, redo);
+                while (fb) {  // rare: that ray against every wall, exactly, with the whole warp
+                    const int b = __ffs(fb) - 1;
+                    fb &= fb - 1;
+                    const TrackMeta tmb = STAGED ? stm : tp.meta[__shfl_sync(kFull, tidr, b)];
+                    const double t = raycast_wall_exact_one(tp, tmb, __shfl_sync(kFull, ox, b), __shfl_sync(kFull, oy, b),
+                                                            __shfl_sync(kFull, v3x, b), __shfl_sync(kFull, v3y, b), lane);
+                    if (lane == b) wall = t;
+                }
+                if (live) {
+                    double t = wall;
+                    if (KIND == RK_ENV_MULTI)
+                        t = fmin(fmin(t, raycast_car_edges<true>(S, gg * A, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
+                    else if (t == INFINITY)
+                        t = kMaxRange;  // track.py:196-197
+                    const int ee = STAGED ? genv[gg] : e_base + gg;
+                    const size_t oi = agent_major ? (size_t)ca * p.E + ee : (size_t)ee * A + ca;
+                    const float hval = __fdiv_rn((float)t, 50.0f);  // racing_env.py:46-53
+                    obs[oi * D + r] = hval;
+                    if (p.obs_host0 != nullptr && ca == 0) row_sh[gg * R + r] = hval;
+                }
+            }
+        }
+        // ---- grid mode: every lane casts and finishes the R rays of ITS car, one after the other --------------------
         const TrackMeta* tmr = tmp;
         const float o32x = (float)(x - tmr->org_x), o32y = (float)(y - tmr->org_y);
         const double* sx = tp.sx + 2 * (size_t)tmr->wp_off;
@@ -1165,7 +1221,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         unsigned long long order = (QUERY == RK_QUERY_GRID && is_car && R <= 15) ? p.st.ray_order[c] : 0ull;
         const bool ordered = (order >> 60) == 0xFull;
 #pragma unroll 1
-        for (int j = 0; j < R; ++j) {
+        for (int j = 0; QUERY == RK_QUERY_GRID && j < R; ++j) {
             const int r = ordered ? min((int)((order >> (4 * j)) & 15ull), R - 1) : j;
             double v3x = 0.0, v3y = 1.0, wall = INFINITY;
             bool redo = false;
@@ -1174,13 +1230,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const double rc = p.sensor_cos[r], rs = p.sensor_sin[r];
                 const double dcs = dsub(dmul(cs, rc), dmul(sn, rs)), dsn = dadd(dmul(sn, rc), dmul(cs, rs));
                 v3x = -dsn; v3y = dcs;  // track.py:178
-                RayHit hit;
-                if (QUERY == RK_QUERY_GRID) {
-                    hit = grid_ray(tp, tmr, o32x, o32y, (float)dcs, (float)dsn, (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY);
-                } else {
-                    const unsigned w = win_sh[lane * R + r];
-                    hit.s0 = w == 0xffffu ? -1 : (int)w; hit.s1 = -1; hit.t0 = 0.f; hit.t1 = INFINITY; hit.inside = true;
-                }
+                const RayHit hit = grid_ray(tp, tmr, o32x, o32y, (float)dcs, (float)dsn, (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY);
                 redo = !hit.inside;
                 if (hit.s0 >= 0) {
                     {
