@@ -19,6 +19,7 @@ whose inference is one fused kernel over all environments.
 from __future__ import annotations
 
 import os
+import time
 
 import numpy as np
 import torch
@@ -353,7 +354,6 @@ class BatchedRacingVecEnv:
         obs = self.reset_device()
         self._h_obs.copy_(obs, non_blocking=True)
         torch.cuda.current_stream(self.be.device).synchronize()
-        import time
         self._t_reset, self._ep_t0 = time.perf_counter(), None
         out = self._h_obs.numpy()
         return (out.copy() if self.copy else out), {}
@@ -385,17 +385,24 @@ class BatchedRacingVecEnv:
             term = term | trunc
         infos = {}
         if self._np_ep_mask.any():
-            # RecordEpisodeStatistics' keys: return, length and elapsed wall time of the episode ('t' is measured
-            # from the environment's previous reset on the host clock, as the wrapper does)
-            import time
+            # RecordEpisodeStatistics' keys: return, length and elapsed wall time of the episode ('t' is measured from the
+            # environment's previous reset on the host clock, as the wrapper does).  O(episodes ended) work per step.
             now = time.perf_counter()
-            mask = self._np_ep_mask.copy()
             if getattr(self, '_ep_t0', None) is None:
                 self._ep_t0 = np.full(self.num_envs, getattr(self, '_t_reset', now))
-            t = np.where(mask, np.round(now - self._ep_t0, 6), 0.0)
-            self._ep_t0[mask] = now
-            infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy(), 't': t}
-            infos['_episode'] = mask
+                self._ep_t = np.zeros(self.num_envs)
+                self._ep_t_idx = np.zeros(0, dtype=np.int64)
+            self._ep_t[self._ep_t_idx] = 0.0
+            idx = np.flatnonzero(self._np_ep_mask)
+            self._ep_t[idx] = np.round(now - self._ep_t0[idx], 6)
+            self._ep_t0[idx] = now
+            self._ep_t_idx = idx
+            if self.copy:
+                infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy(), 't': self._ep_t.copy()}
+                infos['_episode'] = self._np_ep_mask.copy()
+            else:   # views of the pinned result buffers, valid until the next step
+                infos['episode'] = {'r': self._np_ep_return, 'l': self._np_ep_length, 't': self._ep_t}
+                infos['_episode'] = self._np_ep_mask
         if self.copy:
             return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
         return obs, rew, term, trunc, infos
