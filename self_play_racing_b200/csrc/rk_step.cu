@@ -98,7 +98,7 @@ struct CarS {
     double cx[4][32], cy[4][32];  // corners FL, FR, RR, RL (car.py:31-36)
 };
 struct CullView {
-    double2* dir64;               // [A*R] (cos, sin) of each ray's world angle, current environment
+    float* rows;                  // the slot area seen as floats: car 0's rays of every environment (zero-copy host rows)
     unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment) of the best wall candidate
     float2* dir32;                // [A*R]
     unsigned short* list;         // [kListCap]
@@ -113,10 +113,10 @@ __device__ __forceinline__ void out_store(const StepParams& p, T* ptr, size_t i,
         if (q >= p.arena_lo && q < p.arena_hi) *reinterpret_cast<T*>(q + p.arena_delta) = v;
     }
 }
-// (the per-slot area behind CarS holds the culled mode's ray directions and keys, or -- grid mode, zero-copy host rows --
-//  car 0's rays of up to 32 / A environments)
+// (the per-slot area behind CarS holds the culled mode's fp32 ray directions and candidate keys of ONE environment (16 B
+//  per (car, ray) slot) and, once the sweeps are done, car 0's rays of up to 32 / A environments for the zero-copy host rows)
 __host__ __device__ inline size_t slot_area_bytes(int A, int R) {
-    const size_t per_slot = (size_t)A * R * (16 + 8 + 8), rows = (size_t)(32 / A) * R * 4;
+    const size_t per_slot = (size_t)A * R * (8 + 8), rows = (size_t)(32 / A) * R * 4;
     return ((per_slot > rows ? per_slot : rows) + 15) / 16 * 16;
 }
 // behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode)
@@ -700,9 +700,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
     CarS& S = *reinterpret_cast<CarS*>(wbase);
     CullView cv;
-    static_assert(sizeof(CarS) % 16 == 0, "dir64 must stay 16-byte aligned");
-    cv.dir64 = reinterpret_cast<double2*>(wbase + sizeof(CarS));
-    cv.ray_key = reinterpret_cast<unsigned long long*>(cv.dir64 + A * R);
+    static_assert(sizeof(CarS) % 16 == 0, "the slot area must stay 16-byte aligned");
+    cv.rows = reinterpret_cast<float*>(wbase + sizeof(CarS));
+    cv.ray_key = reinterpret_cast<unsigned long long*>(wbase + sizeof(CarS));
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(wbase + sizeof(CarS) + slot_area_bytes(A, R));
 
@@ -1153,7 +1153,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 __syncwarp();
             }
         }
-        float* row_sh = reinterpret_cast<float*>(cv.dir64);   // car 0's rays of every environment, for the host rows
+        float* row_sh = cv.rows;   // car 0's rays of every environment, for the host rows (the sweep's keys are dead by then)
         if (QUERY == RK_QUERY_CULLED) {
             // ---- float64 distances, one lane per (environment, car, ray) slot of the WHOLE warp: the re-evaluation of the
             //      fp32 winners, the other cars' edges and the stores run at full width whatever the number of cars per
