@@ -328,16 +328,24 @@ __device__ __forceinline__ void argmin_culled5_f64_body(const TrackPool& tp, con
     for (int q = 0; q < 5; ++q) out_idx[q] = warp_argmin_d(best[q], bi[q]);
 }
 
-// atan2 for the angular sweep: a 3-term odd minimax polynomial on [0, 1] (|error| <= 6.2e-4 rad) plus octant
-// reconstruction.  The result only bins boundary points between rays; kAtanErr is part of the binning slack, i.e.
-// a point within 6e-4 rad of a ray direction is offered to that ray as well (the float64 test decides).  (Round 1 used
-// the 8-term A&S 4.4.49 polynomial, 2e-8: five more FMAs for every boundary point of every kept chunk.)
-constexpr float kAtanErr = 6.5e-4f;
+// atan2 for the angular sweep: Abramowitz & Stegun 4.4.49 (|error| <= 2e-8 on
+// [0, 1]) plus octant reconstruction; the result only bins points between rays
+// and its error is part of the binning slack.  (A 3-term polynomial with 6e-4 rad of error was measured: five FMAs
+// fewer per boundary point, but every ray that passes within that angle of a boundary vertex then gets a false
+// candidate, float64 rejects the winner and the warp re-scans the ray exactly -- 0.290 -> 0.349 ms.)
 __device__ __forceinline__ float sweep_atan2(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
     const float a = __fdividef(mn, mx), s = a * a;
-    float r = fmaf(fmaf(0.07937379f, s, -0.28869041f), s, 0.99535795f) * a;
+    float r = 0.0028662257f;
+    r = fmaf(r, s, -0.0161657367f);
+    r = fmaf(r, s, 0.0429096138f);
+    r = fmaf(r, s, -0.0752896400f);
+    r = fmaf(r, s, 0.1065626393f);
+    r = fmaf(r, s, -0.1420889944f);
+    r = fmaf(r, s, 0.1999355085f);
+    r = fmaf(r, s, -0.3333314528f);
+    r = fmaf(r * s, a, a);
     if (ay > ax) r = 1.57079632679f - r;
     if (x < 0.f) r = 3.14159265359f - r;
     return copysignf(r, y);
@@ -378,7 +386,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     const float2* dirs = cv.dir32 + slot0;
     unsigned long long* keys = cv.ray_key + slot0;
     const float inv_dphi = p.inv_dphi, u_off = p.cone_half * inv_dphi;
-    const float wrap_thr = 3.139f * inv_dphi;   // (pi minus twice the atan error and then some)
+    const float wrap_thr = 3.1405926f * inv_dphi;
     const float range = (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY;
     for (int pass = 0; pass < p.n_shells; ++pass) {
         // shell of this pass: chunks whose nearest possible point lies in (lo, hi]
@@ -402,7 +410,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                     // per-ray pruning: the circle subtends <= asin(rr/dc) <= (pi/2) rr/dc around its centre;
                     // keep it only if a ray in that fan has no candidate yet or one farther than dmin
                     const float uc = sweep_atan2(ly, lx) * inv_dphi + u_off;
-                    const float du = (1.5708f * rr / dc + 1e-3f + kAtanErr) * inv_dphi;
+                    const float du = (1.5708f * rr / dc + 1e-3f) * inv_dphi;
                     const int klo = max(0, (int)ceilf(uc - du)), khi = min(R - 1, (int)floorf(uc + du));
                     bool open = false;
                     for (int k = klo; k <= khi; ++k) {
@@ -437,7 +445,7 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 const float m2 = fminf(px * px + py * py, qx * qx + qy * qy);
                 const bool slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
                 // angular error budget: table/origin rounding (<= 1.6e-5 / distance) + atan2 + heading rounding
-                const float slack = (kAtanErr + 3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
+                const float slack = (3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
                 int klo = 0, khi = R - 1;
                 if (!slow) {
                     klo = max(0, (int)ceilf(fminf(u, un) - slack));
