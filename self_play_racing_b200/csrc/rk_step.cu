@@ -394,18 +394,11 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
         const float hi = fminf(p.shell[pass], range);
         if (!(hi > lo)) break;
         // ---- level 1 ----
-        // Kept chunks go to one of two lists.  WIDE chunks (many rays pass through the circle: the walls next to the car)
-        // are swept by polar angle at level 2; NARROW ones (at most three rays, the far walls) are tested against just
-        // those rays, segment by segment, with the straddle test -- no atan2 per boundary point.  A chunk whose circle no
-        // ray passes through is dropped altogether.  (Narrow items pack 7 + 6 + 2 bits: tracks of up to 120 chunks.)
-        int count = 0, count_b = 0;
-        const bool use_narrow = nb <= 120;
-        unsigned short* list_b = cv.list + 128;
+        int count = 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < nb; c0 += 32) {
             const int ci = c0 + lane;
-            bool keep = false, narrow = false;
-            int item = 0;
+            bool keep = false;
             if (ci < nb) {
                 const float4 cc = bch[ci];
                 const float rx = cc.x - ox, ry = cc.y - oy, rr = cc.z;
@@ -426,59 +419,12 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                     }
                     keep = open;
                 }
-                if (keep && use_narrow && dc > 2.f * rr) {
-                    // rays through the circle: |angle to the centre| <= asin(rr/dc) <= x (1 + 0.5708 x^2), x = rr/dc <= 1/2
-                    const float xr = __fdividef(rr, dc);
-                    const float uc = sweep_atan2(ly, lx) * inv_dphi + u_off;
-                    const float du = (xr * fmaf(0.5708f, xr * xr, 1.f) + 1e-3f) * inv_dphi;
-                    const int klo = max(0, (int)ceilf(uc - du)), khi = min(R - 1, (int)floorf(uc + du));
-                    const int n = khi - klo + 1;
-                    if (n <= 0) keep = false;
-                    else if (n <= 3) { narrow = true; item = ci | (klo << 7) | (n << 13); }
-                }
             }
-            const unsigned m = __ballot_sync(kFull, keep && !narrow);
-            if (keep && !narrow) cv.list[count + __popc(m & lt)] = (unsigned short)ci;
+            const unsigned m = __ballot_sync(kFull, keep);
+            if (keep) cv.list[count + __popc(m & lt)] = (unsigned short)ci;
             count += __popc(m);
-            const unsigned mb = __ballot_sync(kFull, keep && narrow);
-            if (keep && narrow) list_b[count_b + __popc(mb & lt)] = (unsigned short)item;
-            count_b += __popc(mb);
         }
         __syncwarp();
-        // ---- level 2, narrow chunks: a half-warp per chunk, each of its (<= 3) rays against the 15 segments ----
-#pragma unroll 1
-        for (int it = 0; it < count_b; it += 2) {
-            const int my = it + half;
-            const bool act = my < count_b;
-            const int item = act ? (int)list_b[my] : 0;
-            const int ci = item & 127, k0 = (item >> 7) & 63, n = act ? (item >> 13) : 0;
-            const int side = ci >= nrc;
-            const int pt = (ci - side * nrc) * kRaySegs + j;
-            float px = 1e6f, py = 1e6f;
-            if (act && pt <= N) {
-                const float2 P = bpt[side * (N + 1) + pt];
-                px = P.x - ox; py = P.y - oy;
-            }
-            const float qx = __shfl_down_sync(kFull, px, 1), qy = __shfl_down_sync(kFull, py, 1);
-            const int nmax = max(n, __shfl_xor_sync(kFull, n, 16));   // both halves run the same number of rounds
-            for (int q = 0; q < nmax; ++q) {
-                const int k = min(k0 + q, R - 1);
-                const float2 d = dirs[k];
-                const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;   // signed distances to the ray's line
-                if (q < n && j < kRaySegs && pt < N) {
-                    const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) || (cp >= -kPerpSlack && cq <= kPerpSlack);
-                    const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
-                    const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
-                    if (straddle && thi >= -kFrontSlack) {
-                        const float vx = qx - px, vy = qy - py;
-                        const float den = d.x * vy - d.y * vx;
-                        float t = (fabsf(den) > 1e-12f) ? __fdividef(px * vy - py * vx, den) : tlo;
-                        t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
-                        atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(side * N + pt));
-                    }
-                }
-            }
-        }
         // ---- level 2 ----
 #pragma unroll kLevel2Unroll
         for (int it = 0; it < count; it += 2) {
