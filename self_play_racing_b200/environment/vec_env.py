@@ -11,6 +11,10 @@ Two faces:
   * device face -- `reset_device()` / `step_device(actions)` on CUDA tensors
     with no host synchronisation, used by the device-resident rollout.
 
+Auto-reset follows gymnasium 1.x NEXT_STEP (the reference's default).  `autoreset='same_step'` resets inside the
+terminal step and returns the reset observation; the terminal observation is then NOT available (`infos` carries no
+`final_obs` / `final_info`), which is why it is not the default.
+
 Environments that are `SelfPlayWrapper(MultiRacingEnv)` get the wrapper's
 semantics (environment/wrappers.py:29-55): car 0 is the learner, car 1 is driven
 by the frozen opponent snapshot (or uniform random actions when none is set),

@@ -482,6 +482,17 @@ def test_error_behaviour_through_the_abi(B):
     io.struct_size = C.sizeof(_lib.RkPpoGradIO)
     io.obs_dim, io.n = 21, 128                                                # RK_PPO_MAX_OBS_DIM = 20
     assert lib.rk_ppo_minibatch_grad(C.byref(io), None) != 0 and b'obs_dim' in lib.rk_last_error(None)
+    # the native rollout: struct sizes, missing buffers, layout and self-play preconditions are refused with a message
+    be2 = B.RacingBackend(8, kind='multi', num_agents=2, agent_major=False)
+    be2.set_tracks_from_control_points(cps, widths)
+    ro = _lib.RkRolloutIO()
+    ro.struct_size = 4
+    assert lib.rk_rollout(be2.h, C.byref(be2._io), C.byref(ro), None) != 0 and b'struct_size' in lib.rk_last_error(be2.h)
+    ro.struct_size, ro.T = C.sizeof(_lib.RkRolloutIO), 4
+    assert lib.rk_rollout(be2.h, C.byref(be2._io), C.byref(ro), None) != 0 and b'needs T > 0' in lib.rk_last_error(be2.h)
+    be2.reset(); be2.step()                                                   # the handle keeps working
+    assert lib.rk_set_seed(None, 1) != 0
+    be2.close()
     ad = _lib.RkAdamIO()
     ad.struct_size = C.sizeof(_lib.RkAdamIO)
     assert lib.rk_ppo_adam_step(C.byref(ad), None) != 0 and b'invalid arguments' in lib.rk_last_error(None)
