@@ -59,10 +59,9 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
 }
 
 constexpr int kHidden = 64;
-constexpr int kPolicyThreads = 128;           // threads per CTA (large batches); kPolicyThreadsSmall for small ones
-constexpr int kPolicyThreadsSmall = 32;       // 64 samples per CTA: four times as many CTAs when the batch is small
+constexpr int kPolicyThreads = 128;           // threads per CTA
 constexpr int kSamplesPerThread = 2;          // register tile: every weight fetched feeds 2 samples
-constexpr int kPolicyCols = kPolicyThreads * kSamplesPerThread;   // samples per CTA of the large variant = RK_POLICY_BLOCK
+constexpr int kPolicyCols = kPolicyThreads * kSamplesPerThread;
 
 // Packed parameter block (floats), produced by backend.flatten_agent(): every weight
 // matrix of a hidden layer is stored TRANSPOSED ([in][out], so one float4 broadcast
@@ -80,10 +79,8 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.
 // y[s][j] = b[j] + sum_i Wt[i][j] * x_s[i] for the thread's two samples.  x lives
 // in shared memory, one column per sample (stride kPolicyCols), so the loop over
 // inputs stays rolled with static register indexing of the 2 x 64 accumulators.
-template <int THREADS>
 __device__ __forceinline__ void dense2(const float* __restrict__ wt, const float* __restrict__ b, int nin,
                                        const float* xs, float (&y0)[kHidden], float (&y1)[kHidden]) {
-    constexpr int kCols = THREADS * kSamplesPerThread;
     // packed fp32 FMA (SASS FFMA2, activation broadcast): 64 instead of 128 FMA instructions per input,
     // bit-identical to scalar fmaf
     float2 p0[kHidden / 2], p1[kHidden / 2];
@@ -91,7 +88,7 @@ __device__ __forceinline__ void dense2(const float* __restrict__ wt, const float
     for (int j = 0; j < kHidden / 2; ++j) { p0[j] = make_float2(b[2 * j], b[2 * j + 1]); p1[j] = p0[j]; }
 #pragma unroll 2
     for (int i = 0; i < nin; ++i) {
-        const float xa = xs[i * kCols], xb = xs[i * kCols + THREADS];
+        const float xa = xs[i * kPolicyCols], xb = xs[i * kPolicyCols + kPolicyThreads];
         const float2 xa2 = make_float2(xa, xa), xb2 = make_float2(xb, xb);
         const float4* row = reinterpret_cast<const float4*>(wt + i * kHidden);
 #pragma unroll
@@ -109,13 +106,11 @@ __device__ __forceinline__ void dense2(const float* __restrict__ wt, const float
     }
 }
 
-template <int THREADS>
 __device__ __forceinline__ void stage_obs(float* xs, const float* __restrict__ obs, int64_t obs_stride, int obs_dim,
                                           int b0, int b1, int B) {
-    constexpr int kCols = THREADS * kSamplesPerThread;
     for (int i = 0; i < obs_dim; ++i) {
-        xs[i * kCols] = (b0 < B) ? obs[(size_t)b0 * obs_stride + i] : 0.f;
-        xs[i * kCols + THREADS] = (b1 < B) ? obs[(size_t)b1 * obs_stride + i] : 0.f;
+        xs[i * kPolicyCols] = (b0 < B) ? obs[(size_t)b0 * obs_stride + i] : 0.f;
+        xs[i * kPolicyCols + kPolicyThreads] = (b1 < B) ? obs[(size_t)b1 * obs_stride + i] : 0.f;
     }
 }
 
@@ -127,14 +122,12 @@ __device__ __forceinline__ void stage_obs(float* xs, const float* __restrict__ o
 // frozen opponent's (self_play: agent/ppo.py:109 and environment/wrappers.py:35-39 of the same step) as ONE grid, so
 // that the 256-sample CTAs of both fill the 148 SMs together.  A job without parameters draws the pool-empty
 // opponent's uniform Box actions (wrappers.py:30-32).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(kPolicyThreads, 2)
 policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
-    constexpr int kCols = THREADS * kSamplesPerThread;
     extern __shared__ __align__(128) float sm[];
     const PolicyJob& jb = jobs.job[blockIdx.y];
     const int B = jb.B;
-    if (blockIdx.x * kCols >= B) return;
+    if (blockIdx.x * kPolicyCols >= B) return;
     const float* __restrict__ params = jb.params;
     const float* __restrict__ obs = jb.obs;
     const int64_t obs_stride = jb.obs_stride, act_stride = jb.act_stride, pool_stride = jb.pool_stride;
@@ -146,7 +139,7 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     const int32_t* __restrict__ block_policy = jb.block_policy;
     const int block_len = jb.block_len;
     if (params == nullptr) {   // uniform Box([-1,0],[1,1]) samples, the same stream as random_act_kernel
-        for (int b = blockIdx.x * kCols + threadIdx.x; b < min(B, (int)(blockIdx.x + 1) * kCols); b += THREADS) {
+        for (int b = blockIdx.x * kPolicyCols + threadIdx.x; b < min(B, (int)(blockIdx.x + 1) * kPolicyCols); b += kPolicyThreads) {
             uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x72616e64u};
             philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
             action[(size_t)b * act_stride] = 2.f * u01(c[0]) - 1.f;
@@ -156,7 +149,7 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     }
     // a pool of stacked parameter blocks: this CTA's samples all belong to one block of `block_len` samples,
     // whose policy id selects the block it stages (self-play against several snapshots in one launch)
-    if (block_policy != nullptr) params += (int64_t)block_policy[(blockIdx.x * kCols) / block_len] * pool_stride;
+    if (block_policy != nullptr) params += (int64_t)block_policy[(blockIdx.x * kPolicyCols) / block_len] * pool_stride;
     __shared__ __align__(8) unsigned long long bar;
     const int n_packed = policy_packed_floats(obs_dim);
     const int n0 = obs_dim * kHidden;
@@ -177,8 +170,8 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"((unsigned)__cvta_generic_to_shared(sm)), "l"(params), "r"(bytes), "r"(bar_addr) : "memory");
     }
-    const int b0 = blockIdx.x * kCols + threadIdx.x, b1 = b0 + THREADS;
-    stage_obs<THREADS>(xs, obs, obs_stride, obs_dim, b0, b1, B);
+    const int b0 = blockIdx.x * kPolicyCols + threadIdx.x, b1 = b0 + kPolicyThreads;
+    stage_obs(xs, obs, obs_stride, obs_dim, b0, b1, B);
     __syncthreads();  // the barrier is initialised before anybody polls it
     {
         unsigned done = 0;
@@ -188,13 +181,13 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     }
     float y0[kHidden], y1[kHidden];
     // actor: Linear-Tanh-Linear-Tanh-Linear-Tanh (ppo.py:19-26)
-    dense2<THREADS>(aW0, ab0, obs_dim, xs, y0, y1);
+    dense2(aW0, ab0, obs_dim, xs, y0, y1);
 #pragma unroll
     for (int j = 0; j < kHidden; ++j) {
-        xs[j * kCols] = tanh_fast(y0[j]);
-        xs[j * kCols + THREADS] = tanh_fast(y1[j]);
+        xs[j * kPolicyCols] = tanh_fast(y0[j]);
+        xs[j * kPolicyCols + kPolicyThreads] = tanh_fast(y1[j]);
     }
-    dense2<THREADS>(aW2, ab2, kHidden, xs, y0, y1);
+    dense2(aW2, ab2, kHidden, xs, y0, y1);
     float m[2][2] = {{ab4[0], ab4[1]}, {ab4[0], ab4[1]}};
 #pragma unroll
     for (int j = 0; j < kHidden; ++j) {
@@ -233,14 +226,14 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     if (value != nullptr) {
         // critic: Linear-Tanh-Linear-Tanh-Linear (ppo.py:31-37); the activation columns were
         // overwritten by the actor, so the observations are staged again (L2 resident)
-        stage_obs<THREADS>(xs, obs, obs_stride, obs_dim, b0, b1, B);
-        dense2<THREADS>(cW0, cb0, obs_dim, xs, y0, y1);
+        stage_obs(xs, obs, obs_stride, obs_dim, b0, b1, B);
+        dense2(cW0, cb0, obs_dim, xs, y0, y1);
 #pragma unroll
         for (int j = 0; j < kHidden; ++j) {
-            xs[j * kCols] = tanh_fast(y0[j]);
-            xs[j * kCols + THREADS] = tanh_fast(y1[j]);
+            xs[j * kPolicyCols] = tanh_fast(y0[j]);
+            xs[j * kPolicyCols + kPolicyThreads] = tanh_fast(y1[j]);
         }
-        dense2<THREADS>(cW2, cb2, kHidden, xs, y0, y1);
+        dense2(cW2, cb2, kHidden, xs, y0, y1);
         float v0 = cW4[kHidden], v1 = cW4[kHidden];
 #pragma unroll
         for (int j = 0; j < kHidden; ++j) {
@@ -383,20 +376,10 @@ int launch_policy_jobs(const PolicyJobs& jobs, int n_jobs, int obs_dim, cudaStre
         if (j.block_policy != nullptr && (j.block_len <= 0 || j.block_len % kPolicyCols != 0 || (j.pool_stride & 3) != 0)) return 2;
     }
     if (maxB <= 0) return 0;
-    if (first_use_on_device(0)) {  // the attribute is per device, not per process
-        cudaFuncSetAttribute(policy_act_kernel<kPolicyThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(policy_act_kernel<kPolicyThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    }
-    // small batches (the strong-scaled shards: 8,192 envs per GPU) would put 32 CTAs of 256 samples on 148 SMs; CTAs of 64
-    // samples quadruple the parallelism there.  Same arithmetic per sample, same results.
-    if (maxB <= 24 * 1024) {
-        constexpr int cols = kPolicyThreadsSmall * kSamplesPerThread;
-        const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * cols) * sizeof(float);
-        policy_act_kernel<kPolicyThreadsSmall><<<dim3((maxB + cols - 1) / cols, n_jobs), kPolicyThreadsSmall, smem, stream>>>(jobs, obs_dim);
-    } else {
-        const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
-        policy_act_kernel<kPolicyThreads><<<dim3((maxB + kPolicyCols - 1) / kPolicyCols, n_jobs), kPolicyThreads, smem, stream>>>(jobs, obs_dim);
-    }
+    const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
+    if (first_use_on_device(0))  // the attribute is per device, not per process
+        cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    policy_act_kernel<<<dim3((maxB + kPolicyCols - 1) / kPolicyCols, n_jobs), kPolicyThreads, smem, stream>>>(jobs, obs_dim);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
