@@ -175,6 +175,9 @@ class BatchedRacingVecEnv:
                                       arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
                                       arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
                                       reserved0=int(os.environ.get('RK_B200_ZEROCOPY_OBS', '7')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
+        # numpy views and ctypes references of the per-step call, built once (the Gymnasium face is host-paced)
+        self._np_actions, self._np_obs = self._h_actions.numpy(), self._h_obs.numpy()
+        self._io_ref, self._host_ref = C.byref(be._io), C.byref(self._host_io)
         self.h2d_bytes_per_step = self._h_actions.numel() * 4
         self.d2h_bytes_per_step = self._h_obs.numel() * 4 + be.arena_host_bytes
 
@@ -367,10 +370,10 @@ class BatchedRacingVecEnv:
         gymnasium signature) injects the grid slots used by auto-resets this
         step; by default they come from the backend's Philox stream."""
         be = self.be
-        self._h_actions.numpy()[...] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2)
-        if self.host_chunks > 0 and getattr(self, '_opp_pool', None) is None:
+        np.copyto(self._np_actions, np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 2))
+        if self.host_chunks > 0 and self._opp_pool is None:
             self._step_host(start_slot)
-        elif self.pipeline_chunks > 1 and start_slot is None and getattr(self, '_opp_pool', None) is None:
+        elif self.pipeline_chunks > 1 and start_slot is None and self._opp_pool is None:
             self._step_pipelined()
         else:
             be.actions[0].copy_(self._h_actions, non_blocking=True)
@@ -383,7 +386,7 @@ class BatchedRacingVecEnv:
             self._h_arena.copy_(be.arena[:be.arena_host_bytes], non_blocking=True)
             torch.cuda.current_stream(be.device).synchronize()
         self._obs_cur = be.obs
-        obs, rew = self._h_obs.numpy(), self._np_reward
+        obs, rew = self._np_obs, self._np_reward
         term, trunc = self._np_terminated, self._np_truncated
         if self.selfplay:  # wrappers.py:52: the wrapper reports dones["__all__"] as `terminated`
             term = term | trunc
@@ -415,7 +418,6 @@ class BatchedRacingVecEnv:
         # The whole Gymnasium-face step as ONE C call (rk_step_host): chunked host->device copy of the
         # actions, opponent inference, step kernel and device->host copy of the observations on the
         # library's internal streams, then the small per-env results; returns when the host buffers are ready.
-        import ctypes as C
         from .. import _lib
         be = self.be
         self._opp_counter += 1
@@ -426,7 +428,9 @@ class BatchedRacingVecEnv:
         h = self._host_io
         h.counter = self._opp_counter
         h.opponent_params = self._opp_params.data_ptr() if self._opp_params is not None else None
-        _lib.check(be.lib.rk_step_host(be.h, C.byref(be._io), C.byref(h), be._stream()), be.h, 'rk_step_host')
+        rc = be.lib.rk_step_host(be.h, self._io_ref, self._host_ref, be._stream())
+        if rc:
+            _lib.check(rc, be.h, 'rk_step_host')
 
     def _step_pipelined(self):
         # One logical step as `pipeline_chunks` range launches on side streams: chunk i's
