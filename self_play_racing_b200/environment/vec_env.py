@@ -59,6 +59,45 @@ class _EnvProxy:
         return getattr(self._spec, name)
 
 
+class _EpisodeStats(dict):
+    """infos["episode"] of a vector step: {'r', 'l', 't'} arrays over all environments, valid where infos["_episode"].
+    'r' and 'l' are filled by the step kernel; 't' is computed when it is first read (an episode of length l that ends at
+    step s was reset during step s - l, whose wall time the vector env remembers), so steps whose caller never looks at
+    't' -- the reference's PPO loop reads only 'r' and 'l', agent/ppo.py:123-130 -- pay nothing for it."""
+
+    def __init__(self, r, l, mask, step_no, step_times):
+        super().__init__(r=r, l=l, t=None)
+        self._lazy = (mask, step_no, step_times, step_times[step_no % len(step_times)])
+
+    def _t(self):
+        t = dict.__getitem__(self, 't')
+        if t is None:
+            mask, step_no, times, now = self._lazy
+            idx = np.flatnonzero(mask)
+            t = np.zeros(len(mask))
+            t[idx] = np.round(now - times[(step_no - dict.__getitem__(self, 'l')[idx]) % len(times)], 6)
+            dict.__setitem__(self, 't', t)
+        return t
+
+    def __getitem__(self, key):
+        return self._t() if key == 't' else dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        self._t()
+        return dict.items(self)
+
+    def values(self):
+        self._t()
+        return dict.values(self)
+
+    def copy(self):
+        self._t()
+        return dict(self)
+
+
 class BatchedRacingVecEnv:
     def __init__(self, env_fns, device=None, query='culled', autoreset='next_step', seed=0, copy=True,
                  want_info=False, pipeline_chunks=None):
@@ -175,6 +214,7 @@ class BatchedRacingVecEnv:
                                       arena_host=self._h_arena.data_ptr(), arena_dev=be.arena.data_ptr(),
                                       arena_bytes=be.arena_host_bytes, selfplay=1 if self.selfplay else 0,
                                       reserved0=int(os.environ.get('RK_B200_ZEROCOPY_OBS', '7')), opponent_params=None, seed=self.seed ^ 0x5eed0bb, counter=0)
+        self._step_no, self._step_times = 0, np.full(4096, time.perf_counter())   # wall time of the last 4096 steps (episodes last <= 3000)
         # numpy views and ctypes references of the per-step call, built once (the Gymnasium face is host-paced)
         self._np_actions, self._np_obs = self._h_actions.numpy(), self._h_obs.numpy()
         self._io_ref, self._host_ref = C.byref(be._io), C.byref(self._host_io)
@@ -361,7 +401,8 @@ class BatchedRacingVecEnv:
         obs = self.reset_device()
         self._h_obs.copy_(obs, non_blocking=True)
         torch.cuda.current_stream(self.be.device).synchronize()
-        self._t_reset, self._ep_t0 = time.perf_counter(), None
+        self._step_no = 0
+        self._step_times[0] = time.perf_counter()
         out = self._h_obs.numpy()
         return (out.copy() if self.copy else out), {}
 
@@ -391,25 +432,17 @@ class BatchedRacingVecEnv:
         if self.selfplay:  # wrappers.py:52: the wrapper reports dones["__all__"] as `terminated`
             term = term | trunc
         infos = {}
+        self._step_no += 1
+        self._step_times[self._step_no % len(self._step_times)] = time.perf_counter()
         if self._np_ep_mask.any():
-            # RecordEpisodeStatistics' keys: return, length and elapsed wall time of the episode ('t' is measured from the
-            # environment's previous reset on the host clock, as the wrapper does).  O(episodes ended) work per step.
-            now = time.perf_counter()
-            if getattr(self, '_ep_t0', None) is None:
-                self._ep_t0 = np.full(self.num_envs, getattr(self, '_t_reset', now))
-                self._ep_t = np.zeros(self.num_envs)
-                self._ep_t_idx = np.zeros(0, dtype=np.int64)
-            self._ep_t[self._ep_t_idx] = 0.0
-            idx = np.flatnonzero(self._np_ep_mask)
-            self._ep_t[idx] = np.round(now - self._ep_t0[idx], 6)
-            self._ep_t0[idx] = now
-            self._ep_t_idx = idx
-            if self.copy:
-                infos['episode'] = {'r': self._np_ep_return.copy(), 'l': self._np_ep_length.copy(), 't': self._ep_t.copy()}
-                infos['_episode'] = self._np_ep_mask.copy()
-            else:   # views of the pinned result buffers, valid until the next step
-                infos['episode'] = {'r': self._np_ep_return, 'l': self._np_ep_length, 't': self._ep_t}
-                infos['_episode'] = self._np_ep_mask
+            # RecordEpisodeStatistics' keys: return, length and elapsed wall time of the episode.  'r' and 'l' come from
+            # the device; 't' (host clock, from the environment's previous reset, as the wrapper measures it) is derived
+            # on first access from the episode length and the wall time of the step that reset the environment.
+            mask = self._np_ep_mask.copy() if self.copy else self._np_ep_mask
+            r = self._np_ep_return.copy() if self.copy else self._np_ep_return
+            l = self._np_ep_length.copy() if self.copy else self._np_ep_length
+            infos['episode'] = _EpisodeStats(r, l, mask, self._step_no, self._step_times)
+            infos['_episode'] = mask
         if self.copy:
             return obs.copy(), rew.copy(), term.copy(), trunc.copy(), infos
         return obs, rew, term, trunc, infos
