@@ -297,3 +297,17 @@ def test_data_parallel_update_equals_single_process(tmp_path):
     assert steps == r0['steps'] == cfg['update_epochs'] * cfg['num_minibatches']
     for (k, a), b in zip(one.agent.state_dict().items(), r0['sd'].values()):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6, msg=k)
+
+
+def test_episode_stats_dict_is_lazy_and_complete():
+    """infos["episode"] of the vector env: 'r' / 'l' as given, 't' derived on first access from the episode length
+    and the step clock (an episode of length l ending at step s was reset during step s - l)."""
+    from self_play_racing_b200.environment.vec_env import _EpisodeStats
+    times = np.arange(4096) * 0.5
+    mask = np.array([False, True, False, True])
+    length = np.array([0, 3, 0, 7], np.int32)
+    d = _EpisodeStats(np.array([0.0, 2.5, 0.0, -1.0]), length, mask, 10, times)
+    assert set(d) == {'r', 'l', 't'} and dict.__getitem__(d, 't') is None          # nothing computed yet
+    np.testing.assert_allclose(d['t'], [0.0, 1.5, 0.0, 3.5])
+    np.testing.assert_allclose(dict(d.items())['t'], [0.0, 1.5, 0.0, 3.5])
+    assert d.get('t') is d['t'] and d.get('x', 5) == 5 and d.copy()['l'] is length
