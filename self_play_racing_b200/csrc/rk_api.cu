@@ -398,8 +398,6 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
-    p.row_group = 4;   // measured: profiles/r02_e2e_face.txt (RK_B200_ROW_GROUP overrides)
-    if (const char* env = getenv("RK_B200_ROW_GROUP")) p.row_group = atoi(env);
     p.lane_argmin = h->epw * h->cfg.num_agents >= 16;   // measured: profiles/r02_small_batch.txt (RK_B200_LANE_ARGMIN overrides)
     if (const char* env = getenv("RK_B200_LANE_ARGMIN")) p.lane_argmin = atoi(env) != 0;
     p.env_begin = 0;

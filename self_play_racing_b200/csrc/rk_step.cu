@@ -113,15 +113,15 @@ __device__ __forceinline__ void out_store(const StepParams& p, T* ptr, size_t i,
         if (q >= p.arena_lo && q < p.arena_hi) *reinterpret_cast<T*>(q + p.arena_delta) = v;
     }
 }
-// (the per-slot area behind CarS holds the culled mode's fp32 ray directions and candidate keys of ONE environment, 16 B
-//  per (car, ray) slot)
+// (the per-slot area behind CarS holds the culled mode's fp32 ray directions and candidate keys of ONE environment (16 B
+//  per (car, ray) slot) and, once the sweeps are done, car 0's rays of up to 32 / A environments for the zero-copy host rows)
 __host__ __device__ inline size_t slot_area_bytes(int A, int R) {
-    return ((size_t)A * R * (8 + 8) + 15) / 16 * 16;
+    const size_t per_slot = (size_t)A * R * (8 + 8), rows = (size_t)(32 / A) * R * 4;
+    return ((per_slot > rows ? per_slot : rows) + 15) / 16 * 16;
 }
-// behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode), then car 0's rays
-// of up to 32 / A environments on their way to the zero-copy host rows
+// behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode)
 __host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
-    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + (size_t)(32 / A) * R * 4 + 15) / 16 * 16;
+    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     CarS& S = *reinterpret_cast<CarS*>(wbase);
     CullView cv;
     static_assert(sizeof(CarS) % 16 == 0, "the slot area must stay 16-byte aligned");
-    cv.rows = reinterpret_cast<float*>(wbase + sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2);
+    cv.rows = reinterpret_cast<float*>(wbase + sizeof(CarS));
     cv.ray_key = reinterpret_cast<unsigned long long*>(wbase + sizeof(CarS));
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(wbase + sizeof(CarS) + slot_area_bytes(A, R));
@@ -1125,15 +1125,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     const int nslot = A * R;
     if (QUERY != RK_QUERY_EXACT_F64) {
         unsigned short* win_sh = cv.list + kListCap;   // [32][R]: fp32 winner of every ray of the warp's cars (culled mode)
-        float* row_sh = cv.rows;   // car 0's rays of every environment, for the host rows
-        // Zero-copy host rows: the warp's environments are processed in groups (sweep, finish, store the group's rows), so
-        // that the rows leave for the host all along the kernel instead of in one burst at its end.
-        const int group = (QUERY == RK_QUERY_CULLED && p.obs_host0 != nullptr && p.row_group > 0) ? p.row_group : n_env;
-      for (int g_lo = 0; g_lo < n_env; g_lo += group) {
-        const int g_hi = min(g_lo + group, n_env);
         if (QUERY == RK_QUERY_CULLED) {
             // ---- candidate search, environment by environment, all lanes cooperating (angular sweep) ------------------
-            for (int gg = g_lo; gg < g_hi; ++gg) {
+            for (int gg = 0; gg < n_env; ++gg) {
                 const int gbase = gg * A;
                 if (!((obs_envs >> gbase) & 1u)) continue;
                 const TrackMeta* tme = STAGED ? &stm : tp.meta + __shfl_sync(kFull, tid, gbase);
@@ -1162,14 +1156,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 __syncwarp();
             }
         }
+        float* row_sh = cv.rows;   // car 0's rays of every environment, for the host rows (the sweep's keys are dead by then)
         if (QUERY == RK_QUERY_CULLED) {
             // ---- float64 distances, one lane per (environment, car, ray) slot of the WHOLE warp: the re-evaluation of the
             //      fp32 winners, the other cars' edges and the stores run at full width whatever the number of cars per
             //      warp (small batches give a warp 2 environments: 44 slots are 2 passes, not 11 at 4 lanes)
-            const int total = g_hi * nslot;
+            const int total = n_env * nslot;
             const float inv_nslot = 1.f / (float)nslot, inv_R = 1.f / (float)R;
 #pragma unroll 1
-            for (int s0 = g_lo * nslot; s0 < total; s0 += 32) {
+            for (int s0 = 0; s0 < total; s0 += 32) {
                 const int slot = min(s0 + lane, total - 1);
                 const int gg = (int)(((float)slot + 0.5f) * inv_nslot);          // exact for these small integers
                 const int rem = slot - gg * nslot, ca = (int)(((float)rem + 0.5f) * inv_R), r = rem - ca * R;
@@ -1293,22 +1288,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
             }
             p.st.ray_order[c] = next;
         }
-        if (p.obs_host0 != nullptr && (QUERY == RK_QUERY_CULLED || g_lo == 0)) {
-            // car 0's complete rows of the group's consecutive environments form ONE contiguous run of D floats each in the
-            // caller's pinned buffer: full-width coalesced stores
+        if (p.obs_host0 != nullptr) {
+            // car 0's complete rows of the warp's consecutive environments form ONE contiguous run of n_env * D floats
+            // in the caller's pinned buffer: full-width coalesced stores
             __syncwarp();
-            const int r_lo = (QUERY == RK_QUERY_CULLED) ? g_lo : 0, r_hi = (QUERY == RK_QUERY_CULLED) ? g_hi : n_env;
-            const int run = (r_hi - r_lo) * D;
+            const int run = n_env * D;
             for (int f0 = 0; f0 < run; f0 += 32) {
                 const int f = f0 + lane;
                 if (f < run) {
-                    const int gq = f / D, col = f - gq * D, gg = r_lo + gq;
+                    const int gg = f / D, col = f - gg * D;
                     if ((obs_envs >> (gg * A)) & 1u)
                         p.obs_host0[(size_t)(e_base + gg) * D + col] = col < R ? row_sh[gg * R + col] : nr_sh[(col - R) * nr_stride + gg];
                 }
             }
         }
-      }   // environment groups
         return;
     }
     for (int gg = 0; gg < n_env; ++gg) {

@@ -110,7 +110,6 @@ struct StepParams {
     float* obs_host0;  // optional: car 0's observation block [E, D] in mapped pinned HOST memory; each warp then also
                        // writes the complete row there with one coalesced store, so that the rows cross PCIe
                        // while the kernel is still running (culled queries, A <= 2, A*R <= 32 only)
-    int32_t row_group;    // zero-copy host rows: environments per group of a warp's sweep / finish / store cycle (0: all at once)
     int32_t lane_argmin;  // culled / grid: 1 = every car searches its nearest waypoints on its own lane (throughput: many cars
                           // per warp), 0 = one car at a time with the whole warp (latency: small batches, few cars per warp)
     int32_t mode;  // 0 = step, 1 = reset(mask), 2 = observe only
