@@ -127,7 +127,7 @@ int rk_create(const rk_config* cfg, rk_handle* out) {
          dev_alloc(h, &h->st.fstep, C) || dev_alloc(h, &h->st.steps, (size_t)E) ||
          dev_alloc(h, &h->st.needs_reset, (size_t)E) || dev_alloc(h, &h->st.ep_return, (size_t)E) ||
          dev_alloc(h, &h->st.ep_length, (size_t)E) || dev_alloc(h, &h->st.reset_count, (size_t)E) ||
-         dev_alloc(h, &h->st.ray_order, C) ||
+         dev_alloc(h, &h->st.ray_order, C) || dev_alloc(h, &h->st.wall_cache, C * (size_t)R) ||
          dev_alloc(h, &h->sensor_angles, (size_t)3 * R);
     if (rc) {
         snprintf(g_create_err, sizeof(g_create_err), "rk_create: %s", h->err[0] ? h->err : "cudaSetDevice failed");
@@ -686,7 +686,7 @@ int rk_get_state(rk_handle h, double* car_f64, int32_t* car_i32, int32_t* env_i3
         const int32_t* src[4] = {h->st.pidx, h->st.lpidx, h->st.flags, h->st.fstep};
         for (int k = 0; k < 4; ++k) {
             H_CUDA(h, cudaMemcpy(t.data(), src[k], C * sizeof(int32_t), cudaMemcpyDeviceToHost));
-            for (size_t i = 0; i < C; ++i) car_i32[4 * i + k] = t[i];
+            for (size_t i = 0; i < C; ++i) car_i32[4 * i + k] = (k == 2) ? (t[i] & ~(int32_t)F_RAYCACHE) : t[i];   // internal bit
         }
     }
     if (env_i32) {
@@ -724,7 +724,7 @@ int rk_set_state(rk_handle h, const double* car_f64, const int32_t* car_i32, con
         std::vector<int32_t> t(C);
         int32_t* dst[4] = {h->st.pidx, h->st.lpidx, h->st.flags, h->st.fstep};
         for (int k = 0; k < 4; ++k) {
-            for (size_t i = 0; i < C; ++i) t[i] = car_i32[4 * i + k];
+            for (size_t i = 0; i < C; ++i) t[i] = (k == 2) ? (car_i32[4 * i + k] & ~(int32_t)F_RAYCACHE) : car_i32[4 * i + k];
             H_CUDA(h, cudaMemcpy(dst[k], t.data(), C * sizeof(int32_t), cudaMemcpyHostToDevice));
         }
     }

@@ -1029,6 +1029,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     }
 
     // ---- write state back ----------------------------------------------------------------
+    // a crashed car of a multi env is frozen from now on: this launch leaves its wall distances in wall_cache (below)
+    const bool cache_in = KIND == RK_ENV_MULTI && QUERY == RK_QUERY_CULLED && p.mode == 0 && !resetting &&
+                          (flags & F_RAYCACHE) && (flags & F_CRASHED);
+    if (KIND == RK_ENV_MULTI && QUERY == RK_QUERY_CULLED && p.mode == 0 && p.io.obs != nullptr && is_car && (flags & F_CRASHED))
+        flags |= F_RAYCACHE;
     if (p.mode != 2 && is_car) {
         p.st.x[c] = x; p.st.y[c] = y; p.st.ang[c] = ang; p.st.vx[c] = vx; p.st.vy[c] = vy;
         p.st.last_steer[c] = last_steer;
@@ -1144,8 +1149,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 }
                 __syncwarp();
                 for (int ca = 0; ca < A; ++ca)
-                    raycast_walls_culled<KIND>(tp, tme, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
-                                               S.s[gbase + ca], ca * R, lane, cv);
+                    if (!__shfl_sync(kFull, (int)cache_in, gbase + ca))   // (a frozen car's walls are in wall_cache)
+                        raycast_walls_culled<KIND>(tp, tme, p, S.x[gbase + ca], S.y[gbase + ca], S.c[gbase + ca],
+                                                   S.s[gbase + ca], ca * R, lane, cv);
                 for (int s0 = 0; s0 < nslot; s0 += 32) {
                     const int slot = s0 + lane;
                     if (slot < nslot) {
@@ -1175,10 +1181,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 const double ox = S.x[lc], oy = S.y[lc];
                 double v3x = 0.0, v3y = 1.0, wall = INFINITY;
                 bool redo = false;
+                const bool cached = KIND == RK_ENV_MULTI && __shfl_sync(kFull, (int)cache_in, lc);
+                const int flags_c = (KIND == RK_ENV_MULTI) ? __shfl_sync(kFull, flags, lc) : 0;
+                float* wcache = (KIND == RK_ENV_MULTI) ? p.st.wall_cache + (size_t)__shfl_sync(kFull, c, lc) * R + r : nullptr;
                 if (live) {
                     const double cc = S.c[lc], ss = S.s[lc], rc = p.sensor_cos[r], rs = p.sensor_sin[r];
                     v3x = -dadd(dmul(ss, rc), dmul(cc, rs)); v3y = dsub(dmul(cc, rc), dmul(ss, rs));  // track.py:178
-                    const unsigned w = win_sh[lc * R + r];
+                    const unsigned w = cached ? 0xffffu : win_sh[lc * R + r];
+                    if (cached) wall = (double)*wcache;
                     if (w != 0xffffu) {
                         const size_t i = 2 * (size_t)tmr->wp_off + w;
                         const double ax = tp.v2x[i], ay = tp.v2y[i];
@@ -1198,6 +1208,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
                 }
                 if (live) {
                     double t = wall;
+                    // (the float copy loses nothing: rounding is monotonic, so min and the final float cast commute)
+                    if (KIND == RK_ENV_MULTI && (flags_c & F_RAYCACHE) && !cached) *wcache = (float)wall;
                     if (KIND == RK_ENV_MULTI)
                         t = fmin(fmin(t, raycast_car_edges<true>(S, gg * A, A, ox, oy, v3x, v3y)), kMaxRange);  // multi_track.py:8,26
                     else if (t == INFINITY)

@@ -18,7 +18,8 @@ constexpr int kListMax = 480;       // chunks of one kind per track: the culled 
 constexpr int kWarpsPerCta = RK_WARPS;
 
 // flags word of a car
-enum : int { F_CRASHED = 1, F_FINISHED = 2, F_CP25 = 4, F_CP50 = 8, F_CP75 = 16, F_HAS_CRASHED = 32 };
+enum : int { F_CRASHED = 1, F_FINISHED = 2, F_CP25 = 4, F_CP50 = 8, F_CP75 = 16, F_HAS_CRASHED = 32,
+             F_RAYCACHE = 64 };  // internal: EnvState::wall_cache holds this (crashed, hence frozen) car's wall distances
 
 // One record per track.  Everything float64 is what the reference keeps in
 // Track (environment/track.py:61-98); org/chunk fields serve the culled query
@@ -77,6 +78,11 @@ struct EnvState {
     // per car (RK_QUERY_GRID, R <= 15): this car's ray indices ordered by the previous step's readings, longest first,
     // 4 bits each, bits 60..63 = 0xF when valid.  A scheduling hint only -- results do not depend on it.
     unsigned long long* ray_order;
+    // per (car, ray) (RK_QUERY_CULLED, multi): the wall distance of each ray of a CRASHED car.  Crashed cars stay frozen
+    // (car.py:51-52) but are observed until the episode ends (multi_racing_env.py:236-249): their walls do not move, so
+    // the sweep runs once, in the step of the crash, and later steps only add the other cars' edges.  Valid while the
+    // car's flags carry F_RAYCACHE (cleared by every reset and by rk_set_state).
+    float* wall_cache;
 };
 
 struct StepParams {
