@@ -373,7 +373,9 @@ class PpoMinibatchGrad:
         io.workspace, io.workspace_bytes = self.workspace.data_ptr(), nbytes
         io.flat_grad, io.kl_sum = self.flat_grad.data_ptr(), self.kl_sum.data_ptr()
         io.kl_sum_f32 = self.kl_f32.data_ptr()
-        io.tensor_cores = 1 if tensor_cores else 0
+        # 0: fp32 FMA kernel; 1 / True: per-sample products on tcgen05; 2: the weight gradients on tcgen05 as well
+        io.tensor_cores = int(tensor_cores) if not isinstance(tensor_cores, bool) else (1 if tensor_cores else 0)
+        self.tensor_cores = io.tensor_cores
         self.io = io
 
     def grad_views(self):

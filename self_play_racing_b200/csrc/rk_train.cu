@@ -42,7 +42,13 @@ struct GradArgs {
     double* kl_partial;   // [gridDim.x]
 };
 
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// tanh(x) = 1 - 2 / (exp(2x) + 1); ex2.approx.ftz directly (one MUFU): __expf adds a denormal-range fix-up (compare +
+// two multiplies per call) that only matters where the result is -1 anyway
+__device__ __forceinline__ float tanh_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -470,6 +476,13 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     hi = __float_as_uint(h);
     lo = __float_as_uint(tf32_rn(x - h));
 }
+// The same split in three instructions (variant 2): hi = x rounded to TF32's 11 significant bits (add half an ulp to the
+// bit pattern, clear the low 13 bits: round-to-nearest, ties away), lo = x - hi exactly; lo is handed to the tensor core
+// as it is -- kind::tf32 reads the upper 19 bits of each 32-bit operand, so hi + lo carries >= 21 bits of x.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
@@ -505,7 +518,8 @@ __device__ __forceinline__ void issue_product(uint32_t tmem, int colD, int colAh
             acc = 1;
         }
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if (bar != nullptr)   // (nullptr: the caller issues more products and commits them together)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded: if the tensor core never signalled completion (a wrong descriptor) the kernel finishes with wrong
 // results, which the parity tests catch, instead of hanging the GPU.
@@ -898,6 +912,459 @@ constexpr size_t kTrainTcSmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH
 static_assert(kTrainTcSmemFloats * sizeof(float) <= 226 * 1024, "one CTA per SM");
 static_assert((kH * kXK) % 4 == 0, "16-byte aligned carve-up");
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant 2 (rk_ppo_grad_io.tensor_cores = 2): the WEIGHT GRADIENTS dW2 = dZ2^T H1 (+ db2) and
+// dW1 = dZ1^T X (+ db1) run on tcgen05 as well -- every 64-wide product of the update is then a tensor-core product
+// and the CUDA cores keep the epilogues (bias, tanh, loss gradient, the TF32 hi/lo splits) and dW3.
+//   * Both operands of a weight-gradient product are needed FEATURE-major (K = the tile's 128 samples), so they can
+//     not come from tensor memory (a TMEM lane is a sample).  The thread-per-sample epilogues write them straight
+//     into shared-memory operand tiles in the K-major no-swizzle core-matrix layout, with the k-cores of a row
+//     group 144 bytes apart instead of 128: the 32 threads of a warp (32 consecutive samples) then store one feature
+//     row into 32 distinct banks (tools/umma_dw_selftest.cu verifies descriptors with LBO = 144, SBO = 4608).
+//     The plain [feature][sample] tiles of variant 1 are gone.
+//   * The hi and lo parts of an operand are STACKED along M or N so that one series of 16 instructions (K = 8 samples
+//     each) computes several terms of the split at once; the accumulators persist in TMEM across all tiles of the CTA
+//     and are read (and their parts added) once at the end.  The bias gradients ride along as one more column: H1's
+//     operand tile is preceded by a constant row of ones, X's tile holds a one in column D.
+//   * Three 36 KB operand buffers, adjacent in the order [ones | P | R | Q], are time-multiplexed within a tile (227 KB
+//     of shared memory hold the 76 KB of weight tiles, these three and X^T hi/lo, nothing more):
+//       P: h1.hi (epilogue 1)                         -> dz1.hi (after the products that read h1.hi)
+//       R: dz2.lo -> h1.lo (fetched back from the TMEM columns that fed layer 2) -> dz1.lo
+//       Q: h2 (epilogue 2) -> dz2.hi (in place)
+//     dW2|db2:  [R; Q] . [ones | P]^T   M = 128, N = 72  (dz2.lo.h1.hi and dz2.hi.h1.hi in lanes 0-63 / 64-127; issued
+//               together with dH1 and completing under the dZ1 arithmetic), then Q . R'^T  M = 64, N = 64 (dz2.hi.h1.lo)
+//               once h1.lo is in R;
+//     dW1|db1:  [P'; R''] . [Xh; Xl]^T  M = 128, N = 48  (all four terms of the split), issued at the end of the tile and
+//               completing under the next tile's layer 1.
+//   * The next tile's observation rows are loaded into registers while layer 2 runs and stored (TMEM A operand of
+//     layer 1 + X^T tile of dW1) when the previous users of those buffers have completed.
+// ---------------------------------------------------------------------------
+constexpr int kLboF = 36, kSboF = 32 * kLboF;   // floats: 144 B between the k-cores of a row group, 4608 B between 8-row groups
+__device__ __forceinline__ int poff(int r, int k) { return (r >> 3) * kSboF + (k >> 2) * kLboF + (r & 7) * 4 + (k & 3); }
+// TMEM columns: the X operand of layer 1 (written at the end of the previous tile) shares the columns of dZ2 (written
+// after layer 1 has completed, consumed by dH1 before the next X arrives)
+constexpr int kC2Acc = 0, kC2dW2 = 64, kC2dW2c = 136, kC2dW1 = 200, kC2Hh = 248, kC2Hl = 312, kC2Zh = 376, kC2Zl = 440,
+              kC2Xh = kC2Zh, kC2Xl = kC2Zl;
+static_assert(kC2Zl + kH <= kTmemCols, "TMEM columns");
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[M x N] (+)= A[M x 128] . B[N x 128]^T, both operands padded K-major tiles in shared memory (M = 64: row r in TMEM
+// lane 32 * (r / 16) + r % 16; M = 128: row r in lane r)
+__device__ __forceinline__ void issue_ss(uint32_t tmem_d, const float* A, const float* B, int M, int N, uint32_t& acc) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    uint64_t da = umma_desc(smem_u32(A), 4 * kLboF, 4 * kSboF), db = umma_desc(smem_u32(B), 4 * kLboF, 4 * kSboF);
+#pragma unroll
+    for (int kb = 0; kb < kTS / 8; ++kb) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        acc = 1;
+        da += (2 * 4 * kLboF) >> 4;   // next 8 samples: two k-cores further (the start-address field counts 16-byte units)
+        db += (2 * 4 * kLboF) >> 4;
+    }
+}
+// smem operand tiles written by this thread (generic proxy) become visible to the tensor core (async proxy)
+__device__ __forceinline__ void publish_operands_and_sync() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tmem_publish_and_sync();
+}
+
+template <int OUT>
+__device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P, float* smem) {
+    constexpr bool kActor = OUT == 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, D = g.D;
+    const int half = warp >> 2;                    // which 32 of the 64 accumulator columns this thread handles
+    const int srow = (warp & 3) * 32 + lane;       // sample of the tile = TMEM lane
+    const int cbase = half * 32;
+    float* W1h = smem;                      // [64][kXK]  B of layer 1 (K-major, rows = output j)
+    float* W1l = W1h + kH * kXK;
+    float* W2h = W1l + kH * kXK;            // [64][64]   B of layer 2: rows = output j, k = input i
+    float* W2l = W2h + kH * kH;
+    float* W2th = W2l + kH * kH;            // [64][64]   B of dH1: rows = input i, k = output j
+    float* W2tl = W2th + kH * kH;
+    float* sb1 = W2tl + kH * kH;            // [64]
+    float* sb2 = sb1 + kH;                  // [64]
+    float* sW3 = sb2 + kH;                  // [OUT][64]
+    float* Ob = sW3 + 2 * kH;               // [8 rows][128 samples]   row 0 = ones: with P the B operand of dW2|db2
+    float* Pb = Ob + kSboF;                 // [64]  h1.hi, later dz1.hi
+    float* Rb = Pb + 8 * kSboF;             // [64]  dz2.lo, h1.lo, dz1.lo    ([P; R] = A of dW1, [R; Q] = A of dW2)
+    float* Qb = Rb + 8 * kSboF;             // [64]  h2, later dz2.hi
+    float* XTh = Qb + 8 * kSboF;            // [24]  X^T hi (row D = ones)   ([Xh; Xl] = B of dW1)
+    float* XTl = XTh + 3 * kSboF;
+    float* DO = XTl + 3 * kSboF;            // [2][kLD]   d loss / d (pre-activation output)
+    float* OP = DO + 2 * kLD;               // [2 halves][2][kLD]  partial output-layer sums of the two column halves
+    float* red = OP + 4 * kLD;              // [32]
+    __shared__ __align__(8) unsigned long long bar, bar2;
+    __shared__ uint32_t tmem_slot;
+
+    for (int q = tid; q < kH * kXK; q += kNT2) {
+        const int j = q / kXK, i = q - j * kXK;
+        uint32_t hi = 0, lo = 0;
+        if (i < D) split_tf32(P.W1[j * D + i], hi, lo);
+        W1h[umma_off(j, i, kXK)] = __uint_as_float(hi);
+        W1l[umma_off(j, i, kXK)] = __uint_as_float(lo);
+    }
+    for (int q = tid; q < kH * kH; q += kNT2) {
+        const int j = q >> 6, i = q & 63;
+        uint32_t hi, lo;
+        split_tf32(P.W2[q], hi, lo);
+        W2h[umma_off(j, i, kH)] = __uint_as_float(hi); W2l[umma_off(j, i, kH)] = __uint_as_float(lo);
+        W2th[umma_off(i, j, kH)] = __uint_as_float(hi); W2tl[umma_off(i, j, kH)] = __uint_as_float(lo);
+    }
+    for (int q = tid; q < kH; q += kNT2) { sb1[q] = P.b1[q]; sb2[q] = P.b2[q]; }
+    for (int q = tid; q < OUT * kH; q += kNT2) sW3[q] = P.W3[q];
+    for (int q = tid; q < 8 * kTS; q += kNT2) Ob[poff(q >> 7, q & 127)] = (q >> 7) == 0 ? 1.f : 0.f;
+    float b3[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) b3[o] = P.b3[o];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the weight tiles are read by the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's quarter of the TMEM lanes
+    unsigned phase = 0, phase2 = 0;
+
+    float adv_mean = 0.f, adv_std = 1.f;
+    if (kActor) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int b = 0; b < kAdvBlocks; ++b) { s1 += g.adv_part[2 * b]; s2 += g.adv_part[2 * b + 1]; }
+        const double mean = s1 / g.n_global;
+        const double var = (s2 - g.n_global * mean * mean) / (g.n_global - 1.0);
+        adv_mean = (float)mean;
+        adv_std = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    const float ls0 = kActor ? g.log_std[0] : 0.f, ls1 = kActor ? g.log_std[1] : 0.f;
+
+    const int u = tid & 63, grp = tid >> 6;               // dW3: output j = u, (output o x sample half) or sample quarter
+    float gW3 = 0.f, gb3[OUT], kl = 0.f;
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) gb3[o] = 0.f;
+
+    const int ntiles = (g.n + kTS - 1) / kTS;
+    // One tile's observation rows: two threads per sample (columns 0-15 / 16-23 of the padded row), loaded into registers
+    auto gather_load = [&](int tile, float (&x)[16], bool& valid, float& a0, float& a1, float& lp, float& adv, float& ret,
+                           float& val) {
+        const int gi = tile * kTS + srow;
+        valid = gi < g.n;
+        const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
+        const float* src = g.obs + row * g.obs_stride;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int i = half * 16 + c;
+            x[c] = (valid && i < D) ? src[i] : 0.f;
+        }
+        a0 = a1 = lp = adv = ret = val = 0.f;
+        if (valid && half == 0) {
+            if (kActor) {
+                const float2 a = *reinterpret_cast<const float2*>(g.act + 2 * row);
+                a0 = a.x; a1 = a.y; lp = g.old_logp[row]; adv = g.adv[row];
+            } else {
+                ret = g.ret[row]; val = g.val[row];
+            }
+        }
+    };
+    // ... split into hi + lo: the A operand of layer 1 (TMEM columns) ...
+    auto store_x_tmem = [&](const float (&x)[16]) {
+#pragma unroll
+        for (int c8 = 0; c8 < 16; c8 += 8) {
+            if (c8 == 0 || half == 0) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) split_tf32_fast(x[c8 + c], hi[c], lo[c]);
+                tmem_st8(lane_base + kC2Xh + half * 16 + c8, hi);
+                tmem_st8(lane_base + kC2Xl + half * 16 + c8, lo);
+            }
+        }
+    };
+    // ... and the B operand of dW1 (X^T tile; column D is the constant one that yields db1)
+    auto store_x_smem = [&](const float (&x)[16]) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            if (c < 8 || half == 0) {
+                const int i = half * 16 + c;
+                uint32_t hi, lo;
+                split_tf32_fast(x[c], hi, lo);
+                if (i == D) hi = 0x3f800000u;
+                XTh[poff(i, srow)] = __uint_as_float(hi);
+                XTl[poff(i, srow)] = __uint_as_float(lo);
+            }
+        }
+    };
+
+    bool valid = false, n_valid = false;
+    float d_a0 = 0.f, d_a1 = 0.f, d_lp = 0.f, d_adv = 0.f, d_ret = 0.f, d_val = 0.f;
+    float n_a0 = 0.f, n_a1 = 0.f, n_lp = 0.f, n_adv = 0.f, n_ret = 0.f, n_val = 0.f;
+    float xr[16], xn[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { xr[c] = 0.f; xn[c] = 0.f; }
+    const bool any_tile = (int)blockIdx.x < ntiles;
+    if (any_tile) {
+        gather_load(blockIdx.x, xr, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
+        store_x_tmem(xr);
+    }
+    tmem_publish_and_sync();
+    uint32_t acc2 = 0, acc2c = 0, acc1 = 0;   // (thread 0) the gradient accumulators are overwritten by their first instruction only
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const bool more = tile + (int)gridDim.x < ntiles;
+        // ---- layer 1 on the tensor core: ACC = X W1^T (its completion also covers dW1 of the previous tile) ----
+        if (tid == 0) issue_product(tmem, kC2Acc, kC2Xh, kC2Xl, W1h, W1l, kXK, &bar);
+        wait_product(&bar, phase);
+        store_x_smem(xr);
+        {
+            uint32_t v[32];
+            tmem_ld32(lane_base + kC2Acc + cbase, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 32; c8 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = cbase + c8 + c;
+                    const float h = tanh_fast(__uint_as_float(v[c8 + c]) + sb1[j]);
+                    split_tf32_fast(h, hi[c], lo[c]);
+                    Pb[poff(j, srow)] = __uint_as_float(hi[c]);
+                }
+                tmem_st8(lane_base + kC2Hh + cbase + c8, hi);
+                tmem_st8(lane_base + kC2Hl + cbase + c8, lo);
+            }
+        }
+        tmem_publish_and_sync();
+        // ---- layer 2: ACC = H1 W2^T; meanwhile the next tile's rows are on their way into registers ----
+        if (tid == 0) issue_product(tmem, kC2Acc, kC2Hh, kC2Hl, W2h, W2l, kH, &bar);
+        if (more) gather_load(tile + gridDim.x, xn, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
+        wait_product(&bar, phase);
+        {
+            float out[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) out[o] = 0.f;
+            uint32_t v[32];
+            tmem_ld32(lane_base + kC2Acc + cbase, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = cbase + c;
+                const float h = tanh_fast(__uint_as_float(v[c]) + sb2[j]);
+                Qb[poff(j, srow)] = h;
+#pragma unroll
+                for (int o = 0; o < OUT; ++o) out[o] = fmaf(h, sW3[o * kH + j], out[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) OP[(half * 2 + o) * kLD + srow] = out[o];
+        }
+        __syncthreads();
+        // ---- output layer + loss gradient: one thread per sample (column half 0) ----
+        if (half == 0) {
+            float out[OUT], dpre[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) out[o] = b3[o] + (OP[o * kLD + srow] + OP[(2 + o) * kLD + srow]);
+            if (kActor) {
+                const float mu0 = tanh_fast(out[0]), mu1 = tanh_fast(out[OUT - 1]);  // actor_mu ends in nn.Tanh (ppo.py:19)
+                float dmu0 = 0.f, dmu1 = 0.f, klv = 0.f;
+                if (valid)
+                    ppo_policy_grad(mu0, mu1, d_a0, d_a1, d_lp, d_adv, adv_mean, adv_std, ls0, ls1, g.clip, g.n, dmu0,
+                                    dmu1, klv);
+                kl += klv;
+                dpre[0] = dmu0 * (1.f - mu0 * mu0);
+                dpre[OUT - 1] = dmu1 * (1.f - mu1 * mu1);
+            } else {
+                dpre[0] = valid ? ppo_value_grad(out[0], d_ret, d_val, g.clip, g.vf_coef, g.n) : 0.f;
+            }
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) { DO[o * kLD + srow] = dpre[o]; gb3[o] += dpre[o]; }
+        }
+        __syncthreads();
+        // ---- dW3 += H2^T dOut on the CUDA cores (2 x 64 outputs): rows of the h2 tile are read along the samples ----
+        {
+            const int o = kActor ? (grp & 1) : 0;
+            const int s0 = kActor ? (grp >> 1) * 64 : grp * 32, s1 = s0 + (kActor ? 64 : 32);
+            const float* h = Qb + (u >> 3) * kSboF + (u & 7) * 4;
+            const float* d = DO + o * kLD;
+            float a = 0.f;
+#pragma unroll 4
+            for (int s = s0; s < s1; s += 4) {
+                const float4 hv = ld4(h + (s >> 2) * kLboF), dv = ld4(d + s);
+                a = fmaf(hv.x, dv.x, a); a = fmaf(hv.y, dv.y, a); a = fmaf(hv.z, dv.z, a); a = fmaf(hv.w, dv.w, a);
+            }
+            gW3 += a;
+        }
+        __syncthreads();
+        // ---- dZ2 = (dOut W3) * (1 - H2^2): hi in place (A of dW2), lo next to it, both as the A operand of dH1 ----
+        {
+            float dpre[OUT];
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) dpre[o] = DO[o * kLD + srow];
+#pragma unroll
+            for (int c8 = 0; c8 < 32; c8 += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = cbase + c8 + c;
+                    const int q = poff(j, srow);
+                    const float h = Qb[q];
+                    float z = 0.f;
+#pragma unroll
+                    for (int o = 0; o < OUT; ++o) z = fmaf(dpre[o], sW3[o * kH + j], z);
+                    z *= 1.f - h * h;
+                    split_tf32_fast(z, hi[c], lo[c]);
+                    Qb[q] = __uint_as_float(hi[c]);
+                    Rb[q] = __uint_as_float(lo[c]);
+                }
+                tmem_st8(lane_base + kC2Zh + cbase + c8, hi);
+                tmem_st8(lane_base + kC2Zl + cbase + c8, lo);
+            }
+        }
+        publish_operands_and_sync();
+        // ---- dH1 = dZ2 W2 (ACC, own barrier) and dW2|db2 += [dz2.lo; dz2.hi]^T [1 | h1.hi] ----
+        if (tid == 0) {
+            issue_product(tmem, kC2Acc, kC2Zh, kC2Zl, W2th, W2tl, kH, &bar);
+            issue_ss(tmem + kC2dW2, Rb, Ob, 128, kH + 8, acc2);
+            mma_commit(&bar2);
+        }
+        wait_product(&bar, phase);
+        // ---- dZ1 = dH1 * (1 - H1^2) while the weight-gradient product runs; h1 = hi + lo comes back from the TMEM
+        //      columns that fed layer 2 ----
+        float zhi[32], zlo[32], h1lo[32];
+        {
+            uint32_t d[32], hh[32], hl[32];
+            tmem_ld32(lane_base + kC2Acc + cbase, d);
+            tmem_ld32(lane_base + kC2Hh + cbase, hh);
+            tmem_ld32(lane_base + kC2Hl + cbase, hl);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float h = __uint_as_float(hh[c]) + __uint_as_float(hl[c]);
+                const float z = __uint_as_float(d[c]) * (1.f - h * h);
+                uint32_t zh, zl;
+                split_tf32_fast(z, zh, zl);
+                zhi[c] = __uint_as_float(zh); zlo[c] = __uint_as_float(zl); h1lo[c] = __uint_as_float(hl[c]);
+            }
+        }
+        wait_product(&bar2, phase2);   // h1.hi (P) and dz2.lo (R) have been consumed
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int q = poff(cbase + c, srow);
+            Rb[q] = h1lo[c];   // B of the last term of dW2
+            Pb[q] = zhi[c];    // A of dW1
+        }
+        publish_operands_and_sync();
+        if (tid == 0) {
+            issue_ss(tmem + kC2dW2c, Qb, Rb, 64, kH, acc2c);   // dW2 += dz2.hi^T h1.lo
+            mma_commit(&bar);
+        }
+        if (more) store_x_tmem(xn);   // dH1 has released the dZ2 columns the X operand shares
+        wait_product(&bar, phase);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) Rb[poff(cbase + c, srow)] = zlo[c];
+        publish_operands_and_sync();
+        // ---- dW1|db1 += [dz1.hi; dz1.lo]^T [Xh | 1 | Xl]: completes under the next tile's layer 1 ----
+        if (tid == 0) issue_ss(tmem + kC2dW1, Pb, XTh, 128, 2 * kXK, acc1);
+        valid = n_valid; d_a0 = n_a0; d_a1 = n_a1; d_lp = n_lp; d_adv = n_adv; d_ret = n_ret; d_val = n_val;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xr[c] = xn[c];
+    }
+    if (any_tile) {
+        if (tid == 0) mma_commit(&bar);
+        wait_product(&bar, phase);
+    }
+
+    // ---- this CTA's partial gradient, in torch's parameter order of one Sequential: W1 [64][D], b1, W2 [64][64], b2, W3, b3
+    float* stage = Qb;
+    const int oW1 = 0, ob1 = kH * D, oW2 = ob1 + kH, ob2 = oW2 + kH * kH, oW3 = ob2 + kH, ob3 = oW3 + OUT * kH;
+    for (int q = tid; q < kNetStride; q += kNT2) stage[q] = 0.f;
+    __syncthreads();
+    // The M = 128 accumulators hold the lo-part terms in lanes 0-63 and the hi-part terms in lanes 64-127 (gradient row
+    // j = lane & 63); the M = 64 accumulator holds row j in lane 32 * (j / 16) + j % 16.  Three rounds of += through
+    // shared memory in a fixed order; the two warps of a lane quarter split the columns.
+    for (int round = 0; round < 3; ++round) {
+        if (any_tile && round < 2 && ((warp & 3) >> 1) == round) {
+            const int j = (warp & 1) * 32 + lane;
+            {
+                uint32_t v[32];
+                tmem_ld32(lane_base + kC2dW2 + 8 + cbase, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) stage[oW2 + j * kH + cbase + c] += __uint_as_float(v[c]);
+            }
+            if (half == 0) {
+                uint32_t b[8];
+                tmem_ld8(lane_base + kC2dW2, b);
+                stage[ob2 + j] += __uint_as_float(b[0]);
+            } else {
+#pragma unroll
+                for (int c8 = 0; c8 < 2 * kXK; c8 += 8) {
+                    uint32_t w[8];
+                    tmem_ld8(lane_base + kC2dW1 + c8, w);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int i = (c8 + c) % kXK;   // columns 24.. are the X.lo terms of the same element
+                        if (i < D) stage[oW1 + j * D + i] += __uint_as_float(w[c]);
+                        else if (i == D) stage[ob1 + j] += __uint_as_float(w[c]);
+                    }
+                }
+            }
+        }
+        if (any_tile && round == 2) {
+            const int j = (warp & 3) * 16 + lane;
+            uint32_t v[32];
+            tmem_ld32(lane_base + kC2dW2c + cbase, v);
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) stage[oW2 + j * kH + cbase + c] += __uint_as_float(v[c]);
+            }
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    for (int pass = 0; pass < 4; ++pass) {
+        if (grp == pass) stage[oW3 + (kActor ? (grp & 1) : 0) * kH + u] += gW3;   // dW3: four thread groups, fixed order
+        __syncthreads();
+    }
+    // db3 and the KL sum: fixed-order block reduction (only column-half-0 threads hold contributions)
+    float r[OUT + 1];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) r[o] = gb3[o];
+    r[OUT] = kl;
+#pragma unroll
+    for (int o = 0; o <= OUT; ++o) {
+        for (int m = 16; m > 0; m >>= 1) r[o] += __shfl_xor_sync(0xffffffffu, r[o], m);
+        if (lane == 0) red[o * 8 + warp] = r[o];
+    }
+    __syncthreads();
+    if (tid < OUT) stage[ob3 + tid] = (red[tid * 8] + red[tid * 8 + 1]) + (red[tid * 8 + 2] + red[tid * 8 + 3]);
+    if (kActor && tid == 0)
+        g.kl_partial[blockIdx.x] = (double)((red[OUT * 8] + red[OUT * 8 + 1]) + (red[OUT * 8 + 2] + red[OUT * 8 + 3]));
+    __syncthreads();
+    float* dst = g.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kNetStride;
+    const int np = ob3 + OUT;
+    for (int q = tid; q < np; q += kNT2) dst[q] = stage[q];
+}
+
+__global__ void __launch_bounds__(kNT2, 1) ppo_mlp_grad_tc2_kernel(const GradArgs g) {
+    extern __shared__ __align__(1024) float train_smem[];
+    if (blockIdx.y == 0) net_body_tc2<2>(g, g.net[0], train_smem);
+    else net_body_tc2<1>(g, g.net[1], train_smem);
+}
+
+constexpr size_t kTrainTc2SmemFloats = 2 * (size_t)kH * kXK + 4 * (size_t)kH * kH + 2 * kH + 2 * kH + (9 + 8 + 8 + 3 + 3) * (size_t)kSboF +
+                                       2 * kLD + 4 * kLD + 32;
+static_assert(kTrainTc2SmemFloats * sizeof(float) <= 227 * 1024, "one CTA per SM");
+static_assert(8 * (size_t)kSboF >= (size_t)kNetStride, "the staging area must hold one partial gradient");
+
 // flat_grad[q] = sum over CTAs of partial[net][cta][q'] in a fixed order; *kl_sum = sum kl_partial.
 // Block = 64 gradient elements x 4 groups of CTAs (each thread sums its quarter with 4 independent
 // chains, the quarters are combined through shared memory in a fixed order).
@@ -1127,7 +1594,12 @@ int launch_ppo_minibatch_grad(const PpoGradIO& io, cudaStream_t stream) {
     const size_t smem = kTrainSmemFloats * sizeof(float);
     if (first_use_on_device(1))  // the attribute is per device, not per process
         cudaFuncSetAttribute(ppo_mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (io.tensor_cores) {
+    if (io.tensor_cores == 2) {
+        const size_t smem_tc = kTrainTc2SmemFloats * sizeof(float);
+        if (first_use_on_device(3))
+            cudaFuncSetAttribute(ppo_mlp_grad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+        ppo_mlp_grad_tc2_kernel<<<dim3(ncta, 2), kNT2, smem_tc, stream>>>(g);
+    } else if (io.tensor_cores) {
         const size_t smem_tc = kTrainTcSmemFloats * sizeof(float);
         if (first_use_on_device(2))
             cudaFuncSetAttribute(ppo_mlp_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);

@@ -359,12 +359,14 @@ def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
     assert torch.equal(first, fused.flat_grad)
 
 
-@pytest.mark.parametrize('n,obs_dim', [(128, 19), (1000, 19), (4133, 15), (77, 7)])
-def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim):
-    """The tcgen05 variant of rk_ppo_minibatch_grad (layer 1, layer 2 and dH1 as TF32 x 3-pass
-    tensor-core products chained through TMEM) against the fp32 FMA kernel on the same inputs:
-    relative difference of the whole gradient <= 2e-5 of its largest element, same KL sum,
-    deterministic on replay."""
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('n,obs_dim', [(128, 19), (1000, 19), (4133, 15), (77, 7), (40000, 19), (3000, 20)])
+def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim, variant):
+    """The tcgen05 variants of rk_ppo_minibatch_grad (1: layer 1, layer 2 and dH1 as TF32 x 3-pass
+    tensor-core products chained through TMEM; 2: the weight gradients dW2 / dW1 and their biases as
+    M = 64 tensor-core products over shared-memory operand tiles as well) against the fp32 FMA kernel
+    on the same inputs: relative difference of the whole gradient <= 2e-5 of its largest element, same
+    KL sum, deterministic on replay.  (40000 rows: several tiles per CTA, i.e. accumulation in TMEM.)"""
     _, agent_mod, _ = pkg
     from self_play_racing_b200 import spaces
     from self_play_racing_b200.backend import PpoMinibatchGrad
@@ -390,7 +392,7 @@ def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim):
     fma.stats(idx, adv)
     g0, k0 = fma(idx, obs, act, logp, adv, ret, val)
     g0, k0 = g0.clone(), float(k0)
-    tc = PpoMinibatchGrad(params, agent.log_std, obs_dim, 0.2, 0.5, tensor_cores=True)
+    tc = PpoMinibatchGrad(params, agent.log_std, obs_dim, 0.2, 0.5, tensor_cores=variant)
     tc.stats(idx, adv)
     g1, k1 = tc(idx, obs, act, logp, adv, ret, val)
     g1, k1 = g1.clone(), float(k1)

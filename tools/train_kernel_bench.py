@@ -17,7 +17,7 @@ obs = torch.rand(B, D, device='cuda', generator=g) * 2 - 1
 act = torch.rand(B, 2, device='cuda', generator=g) * 2 - 1
 adv, val, ret, logp = (torch.randn(B, device='cuda', generator=g) for _ in range(4))
 perm = torch.randperm(B, device='cuda', generator=g)
-tc = os.environ.get('RK_TC', '0') == '1'
+tc = int(os.environ.get('RK_TC', '0'))   # 0 FMA kernel, 1 per-sample products on tcgen05, 2 weight gradients too
 fused = PpoMinibatchGrad(list(agent.parameters()), agent.log_std, D, 0.2, 0.5, tensor_cores=tc)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(16)]
@@ -34,6 +34,6 @@ for rep in range(2):
 ms = sorted(a.elapsed_time(b) for a, b in ev)
 med = ms[len(ms) // 2]
 flop = 2.0 * n * 2 * (2 * D * 64 + 3 * 64 * 64)   # per net: forward 2 products, backward dH1 + dW2 + dW1 (no dX)
-print(f'rk_ppo_minibatch_grad{" [tensor cores]" if tc else ""} n={n} D={D}: median {med * 1e3:.1f} us (min {ms[0] * 1e3:.1f}), '
+print(f'rk_ppo_minibatch_grad{" [tensor cores, variant %d]" % tc if tc else ""} n={n} D={D}: median {med * 1e3:.1f} us (min {ms[0] * 1e3:.1f}), '
       f'{flop / med / 1e9:.1f} TFLOP/s fp32 (hidden layers), {n / med / 1e3:.1f} M rows/s; launches per call '
       f'{(_lib.launch_count() - l0) // 16 - 1}')
