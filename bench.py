@@ -558,16 +558,17 @@ def time_ppo(args, wl, vec, E, dev, rank, world, with_grad_kernel=True):
                     b.record()
                 torch.cuda.synchronize(dev)
             return sorted(a.elapsed_time(b) * 1e3 for a, b in evs)[len(evs) // 2], k.flat_grad.clone()
-        us_fma, grad_fma = time_impl(False)
-        us_tc, grad_tc = time_impl(True)
-        used_tc = bool(getattr(g, 'tensor_cores', False))
-        us = us_tc if used_tc else us_fma
+        us_fma, grad_fma = time_impl(0)
+        us_tc1, _ = time_impl(1)
+        us_tc, grad_tc = time_impl(2)
+        used_tc = int(getattr(g, 'tensor_cores', 0))
+        us = {0: us_fma, 1: us_tc1, 2: us_tc}[used_tc]
         fma_per_row = 2 * (2 * D * 64 + 3 * 64 * 64)   # both networks: forward 2 products, backward dH1 + dW2 + dW1
-        grad_kernel = {'kernel': ('rk::ppo_mlp_grad_tc_kernel' if used_tc else 'rk::ppo_mlp_grad_kernel') +
+        grad_kernel = {'kernel': ('rk::ppo_mlp_grad_kernel', 'rk::ppo_mlp_grad_tc_kernel', 'rk::ppo_mlp_grad_tc2_kernel')[used_tc] +
                                  ' + rk::ppo_grad_reduce_kernel',
                        'rows_per_minibatch': mb, 'us_per_minibatch': us, 'fma_per_row': fma_per_row,
                        'tflops': 2.0 * fma_per_row * mb / (us * 1e-6) / 1e12,
-                       'fp32_fma_kernel_us': us_fma, 'tcgen05_kernel_us': us_tc,
+                       'fp32_fma_kernel_us': us_fma, 'tcgen05_per_sample_products_only_us': us_tc1, 'tcgen05_kernel_us': us_tc,
                        'max_rel_diff_between_them': float((grad_tc - grad_fma).abs().max() /
                                                           grad_fma.abs().max().clamp_min(1e-30))}
         del flush
@@ -585,8 +586,9 @@ def time_ppo(args, wl, vec, E, dev, rank, world, with_grad_kernel=True):
             'kl_early_stop': 'disabled for timing', 'opponent_pool': cfg['pool_size'],
             'update_matmul_precision': args.ppo_precision,
             'rollout_launch_mode': getattr(trainer, 'rollout_mode', 'eager'),
-            'update_products': ('tcgen05 tf32 x 3 passes (fp32 emulation, fp32 accumulate)'
-                                if getattr(getattr(trainer, '_graphed', None), 'tensor_cores', False) else 'fp32 FMA'),
+            'update_products': ('fp32 FMA', 'per-sample products on tcgen05, tf32 x 3 terms (fp32 emulation, fp32 accumulate)',
+                                'all 64-wide products incl. the weight gradients on tcgen05, tf32 x 3 terms (fp32 emulation, '
+                                'fp32 accumulate)')[int(getattr(getattr(trainer, '_graphed', None), 'tensor_cores', 0))],
             'rollout_agent_steps_per_s': world * E * 2 * T / (roll * 1e-3), 'grad_kernel': grad_kernel}
 
 

@@ -326,7 +326,9 @@ typedef struct rk_ppo_grad_io {
     float* kl_sum_f32;         /* optional out: the same as float32 -- e.g. the slot right after flat_grad, so
                                 * that ONE all-reduce carries the gradient and the KL sum across ranks */
     int32_t tensor_cores;      /* 0: fp32 FMA kernel; 1: the per-sample products on tcgen05 tensor cores (TF32 x 3
-                                * split, fp32-grade accuracy, accumulators and chained operands in TMEM) */
+                                * split, fp32-grade accuracy, accumulators and chained operands in TMEM); 2: the weight
+                                * gradients dW2 / dW1 and their biases as tcgen05 products as well (operand tiles in
+                                * shared memory, accumulators resident in TMEM across the CTA's tiles) */
     int32_t reserved1;
 } rk_ppo_grad_io;
 RK_API uint64_t rk_ppo_grad_workspace_bytes(void);

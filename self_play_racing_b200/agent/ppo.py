@@ -127,10 +127,12 @@ class _GraphedMinibatch:
         self.dmu, self.dv = z(mb, 2), z(mb)
         agent = ppo.agent
         if self.fused_mlp:
-            # 'tensor_core_update' (default on): the per-sample products run on tcgen05 tensor cores as TF32 x 3-pass
-            # fp32 emulation chained through TMEM (8 % faster than the FMA kernel and equal to it to
-            # 1e-6); False selects the pure fp32 FMA kernel
-            self.tensor_cores = bool(c.get('tensor_core_update', True))
+            # 'tensor_core_update' (default 2): every 64-wide product of the update -- the per-sample ones chained through
+            # TMEM and the weight gradients over shared-memory operand tiles -- runs on tcgen05 tensor cores as TF32 x
+            # 3-term fp32 emulation (27 % faster than the FMA kernel and equal to it to 1e-6); 1 keeps the
+            # weight gradients on the CUDA cores, False / 0 selects the pure fp32 FMA kernel
+            tc = c.get('tensor_core_update', 2)
+            self.tensor_cores = (1 if tc else 0) if isinstance(tc, bool) else int(tc)
             self.grad = PpoMinibatchGrad(params, agent.log_std, obs_dim, c['clip_coef'], c['vf_coef'],
                                          tensor_cores=self.tensor_cores)
             self.flat_grad, self.kl_sum = self.grad.flat_grad, self.grad.kl_sum

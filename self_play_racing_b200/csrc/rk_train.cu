@@ -976,6 +976,13 @@ __device__ __forceinline__ void publish_operands_and_sync() {
     tmem_publish_and_sync();
 }
 
+// one lane of a converged warp (the tensor-core instructions are issued by a single thread)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int OUT>
 __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P, float* smem) {
     constexpr bool kActor = OUT == 2;
@@ -1059,11 +1066,16 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
 
     const int ntiles = (g.n + kTS - 1) / kTS;
     // One tile's observation rows: two threads per sample (columns 0-15 / 16-23 of the padded row), loaded into registers
-    auto gather_load = [&](int tile, float (&x)[16], bool& valid, float& a0, float& a1, float& lp, float& adv, float& ret,
-                           float& val) {
+    // (the row index of a tile is fetched one tile earlier than its row: two dependent global loads would otherwise
+    //  sit in the critical path of every tile)
+    auto row_of = [&](int tile) -> int64_t {
         const int gi = tile * kTS + srow;
-        valid = gi < g.n;
-        const int64_t row = valid ? (g.idx ? g.idx[gi] : (int64_t)gi) : 0;
+        return (tile < ntiles && gi < g.n) ? (g.idx ? g.idx[gi] : (int64_t)gi) : -1;
+    };
+    auto gather_load = [&](int64_t row_or_neg, float (&x)[16], bool& valid, float& a0, float& a1, float& lp, float& adv, float& ret,
+                           float& val) {
+        valid = row_or_neg >= 0;
+        const int64_t row = valid ? row_or_neg : 0;
         const float* src = g.obs + row * g.obs_stride;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -1115,8 +1127,9 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
 #pragma unroll
     for (int c = 0; c < 16; ++c) { xr[c] = 0.f; xn[c] = 0.f; }
     const bool any_tile = (int)blockIdx.x < ntiles;
+    int64_t next_row = row_of(blockIdx.x + gridDim.x);
     if (any_tile) {
-        gather_load(blockIdx.x, xr, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
+        gather_load(row_of(blockIdx.x), xr, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
         store_x_tmem(xr);
     }
     tmem_publish_and_sync();
@@ -1124,9 +1137,8 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const bool more = tile + (int)gridDim.x < ntiles;
         // ---- layer 1 on the tensor core: ACC = X W1^T (its completion also covers dW1 of the previous tile) ----
-        if (tid == 0) issue_product(tmem, kC2Acc, kC2Xh, kC2Xl, W1h, W1l, kXK, &bar);
+        if (warp == 0 && elect_one()) issue_product(tmem, kC2Acc, kC2Xh, kC2Xl, W1h, W1l, kXK, &bar);
         wait_product(&bar, phase);
-        store_x_smem(xr);
         {
             uint32_t v[32];
             tmem_ld32(lane_base + kC2Acc + cbase, v);
@@ -1146,8 +1158,9 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
         }
         tmem_publish_and_sync();
         // ---- layer 2: ACC = H1 W2^T; meanwhile the next tile's rows are on their way into registers ----
-        if (tid == 0) issue_product(tmem, kC2Acc, kC2Hh, kC2Hl, W2h, W2l, kH, &bar);
-        if (more) gather_load(tile + gridDim.x, xn, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
+        if (warp == 0 && elect_one()) issue_product(tmem, kC2Acc, kC2Hh, kC2Hl, W2h, W2l, kH, &bar);
+        if (more) gather_load(next_row, xn, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
+        next_row = row_of(tile + 2 * gridDim.x);
         wait_product(&bar, phase);
         {
             float out[OUT];
@@ -1230,11 +1243,12 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
         }
         publish_operands_and_sync();
         // ---- dH1 = dZ2 W2 (ACC, own barrier) and dW2|db2 += [dz2.lo; dz2.hi]^T [1 | h1.hi] ----
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             issue_product(tmem, kC2Acc, kC2Zh, kC2Zl, W2th, W2tl, kH, &bar);
             issue_ss(tmem + kC2dW2, Rb, Ob, 128, kH + 8, acc2);
             mma_commit(&bar2);
         }
+        store_x_smem(xr);   // (X^T tile: free since layer 1's completion covered dW1 of the previous tile; needed by dW1 below)
         wait_product(&bar, phase);
         // ---- dZ1 = dH1 * (1 - H1^2) while the weight-gradient product runs; h1 = hi + lo comes back from the TMEM
         //      columns that fed layer 2 ----
@@ -1261,7 +1275,7 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
             Pb[q] = zhi[c];    // A of dW1
         }
         publish_operands_and_sync();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             issue_ss(tmem + kC2dW2c, Qb, Rb, 64, kH, acc2c);   // dW2 += dz2.hi^T h1.lo
             mma_commit(&bar);
         }
@@ -1271,13 +1285,13 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
         for (int c = 0; c < 32; ++c) Rb[poff(cbase + c, srow)] = zlo[c];
         publish_operands_and_sync();
         // ---- dW1|db1 += [dz1.hi; dz1.lo]^T [Xh | 1 | Xl]: completes under the next tile's layer 1 ----
-        if (tid == 0) issue_ss(tmem + kC2dW1, Pb, XTh, 128, 2 * kXK, acc1);
+        if (warp == 0 && elect_one()) issue_ss(tmem + kC2dW1, Pb, XTh, 128, 2 * kXK, acc1);
         valid = n_valid; d_a0 = n_a0; d_a1 = n_a1; d_lp = n_lp; d_adv = n_adv; d_ret = n_ret; d_val = n_val;
 #pragma unroll
         for (int c = 0; c < 16; ++c) xr[c] = xn[c];
     }
     if (any_tile) {
-        if (tid == 0) mma_commit(&bar);
+        if (warp == 0 && elect_one()) mma_commit(&bar);
         wait_product(&bar, phase);
     }
 

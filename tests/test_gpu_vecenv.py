@@ -255,7 +255,7 @@ def test_graphed_update_equals_eager_update(pkg):
     results = []
     for graphed, fused, fused_mlp, fused_adam, tc in ((False, False, False, False, False), (True, False, False, False, False),
                                                       (True, True, False, False, False), (True, True, True, False, False),
-                                                      (True, True, True, True, False), (True, True, True, True, True)):
+                                                      (True, True, True, True, False), (True, True, True, True, 1), (True, True, True, True, 2)):
         cfg = configs.base_config(num_envs=64, num_steps=64, update_epochs=2, num_minibatches=4, kl_target=1e9,
                                   cuda_graph_update=graphed, fused_update_kernels=fused,
                                   fused_mlp_update=fused_mlp, fused_adam_step=fused_adam, tensor_core_update=tc)
@@ -285,6 +285,7 @@ def test_graphed_update_equals_eager_update(pkg):
     # eager autograd == graphed autograd == graphed + fused loss-gradient kernel == one-kernel forward/loss/backward
     # == the same with clip + Adam + KL stop as one kernel (no per-minibatch host sync)
     # == the same with the per-sample products on the tensor cores (TF32 x 3 passes through TMEM)
+    # == the same with the weight gradients on the tensor cores too (the default)
     for other in results[1:]:
         for a, b in zip(results[0], other):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
