@@ -399,7 +399,9 @@ def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim, variant):
     g1, k1 = g1.clone(), float(k1)
     assert torch.isfinite(g1).all()
     assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
-    assert abs(k1 - k0) <= 1e-3 * max(1.0, abs(k0))
+    # (the KL SUM: the tensor core accumulates with truncation, which biases every output by a fraction of an fp32 ulp
+    #  -- measured 5e-7 per row on log-ratios of order 0.1; the early stop compares kl_sum / n with 0.015)
+    assert abs(k1 - k0) <= 1e-3 * max(1.0, abs(k0)) + 2e-6 * n
     tc(idx, obs, act, logp, adv, ret, val)
     assert torch.equal(g1, tc.flat_grad)
 
