@@ -1068,14 +1068,15 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
     // One tile's observation rows: two threads per sample (columns 0-15 / 16-23 of the padded row), loaded into registers
     // (the row index of a tile is fetched one tile earlier than its row: two dependent global loads would otherwise
     //  sit in the critical path of every tile)
+    //  (the load is unconditional from a clamped address and nothing depends on it until the row is gathered)
     auto row_of = [&](int tile) -> int64_t {
         const int gi = tile * kTS + srow;
-        return (tile < ntiles && gi < g.n) ? (g.idx ? g.idx[gi] : (int64_t)gi) : -1;
+        const int gc = (tile < ntiles && gi < g.n) ? gi : 0;
+        return g.idx ? g.idx[gc] : (int64_t)gc;
     };
-    auto gather_load = [&](int64_t row_or_neg, float (&x)[16], bool& valid, float& a0, float& a1, float& lp, float& adv, float& ret,
-                           float& val) {
-        valid = row_or_neg >= 0;
-        const int64_t row = valid ? row_or_neg : 0;
+    auto gather_load = [&](int tile, int64_t row, float (&x)[16], bool& valid, float& a0, float& a1, float& lp, float& adv,
+                           float& ret, float& val) {
+        valid = tile * kTS + srow < g.n;
         const float* src = g.obs + row * g.obs_stride;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -1129,7 +1130,7 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
     const bool any_tile = (int)blockIdx.x < ntiles;
     int64_t next_row = row_of(blockIdx.x + gridDim.x);
     if (any_tile) {
-        gather_load(row_of(blockIdx.x), xr, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
+        gather_load(blockIdx.x, row_of(blockIdx.x), xr, valid, d_a0, d_a1, d_lp, d_adv, d_ret, d_val);
         store_x_tmem(xr);
     }
     tmem_publish_and_sync();
@@ -1159,7 +1160,7 @@ __device__ __forceinline__ void net_body_tc2(const GradArgs& g, const NetPtrs& P
         tmem_publish_and_sync();
         // ---- layer 2: ACC = H1 W2^T; meanwhile the next tile's rows are on their way into registers ----
         if (warp == 0 && elect_one()) issue_product(tmem, kC2Acc, kC2Hh, kC2Hl, W2h, W2l, kH, &bar);
-        if (more) gather_load(next_row, xn, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
+        if (more) gather_load(tile + gridDim.x, next_row, xn, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
         next_row = row_of(tile + 2 * gridDim.x);
         wait_product(&bar, phase);
         {
