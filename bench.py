@@ -434,8 +434,11 @@ def measure_step(args, wl, vec, E, dev, rank, world, flush, sample_clocks):
 
     # ---- end to end through the Gymnasium face: host numpy in, host numpy out
     rs = np.random.RandomState(3 + rank)
-    host_actions = [rs.uniform(-1, 1, size=(E, 2)).astype(np.float32) for _ in range(4)]
+    # the step's inputs live in pinned host memory (four pre-drawn action arrays cycled through, as a host-side
+    # policy would fill them): BatchedRacingVecEnv.pinned_action_buffers(); the kernel reads them over PCIe
+    host_actions = vec.pinned_action_buffers(4) if hasattr(vec, 'pinned_action_buffers') else [np.empty((E, 2), np.float32) for _ in range(4)]
     for a in host_actions:
+        a[...] = rs.uniform(-1, 1, size=(E, 2)).astype(np.float32)
         a[:, 1] = np.abs(a[:, 1])
     e2e = None
     if wl['kind'] == 'single' or wl['selfplay']:

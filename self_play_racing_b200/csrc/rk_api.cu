@@ -540,6 +540,9 @@ static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* h
     // order the internal streams after whatever the caller has queued
     H_CUDA(h, cudaEventRecord(h->hevent[8], (cudaStream_t)caller_stream));
     float* dev_act = const_cast<float*>(io->actions);
+    // (a failure below leaves work queued on the internal streams that still reads / writes the caller's host buffers:
+    //  the wrapper drains them before the error is returned)
+    auto enqueue = [&]() -> int {
     for (int c = 0; c < n; ++c) {
         cudaStream_t st = h->hstream[c];
         const int lo = (int)((int64_t)E * c / n), hi = (int)((int64_t)E * (c + 1) / n), m = hi - lo;
@@ -574,6 +577,12 @@ static int step_host_impl(rk_handle h, const rk_step_io* io, const rk_host_io* h
         H_CUDA(h, cudaMemcpyAsync(host->arena_host, host->arena_dev, (size_t)host->arena_bytes, cudaMemcpyDeviceToHost, last));
     H_CUDA(h, cudaStreamSynchronize(last));
     return 0;
+    };
+    const int rc = enqueue();
+    if (rc)
+        for (int c = 0; c < n; ++c)
+            if (h->hstream[c]) cudaStreamSynchronize(h->hstream[c]);
+    return rc;
 }
 
 int rk_rollout(rk_handle h, const rk_step_io* base, const rk_rollout_io* r, void* stream_) {

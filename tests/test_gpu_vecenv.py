@@ -548,10 +548,18 @@ def test_gym_face_at_scale_equals_device_face(pkg, kind, E):
     np.testing.assert_array_equal(o1, o2)
     rs = np.random.RandomState(0)
     n_done = 0
+    pinned = vec.pinned_action_buffers(2)    # every other step hands over a page-locked array: read in place, no staging copy
     for k in range(90):                      # random drivers leave the track within 50-90 steps: auto-resets are covered
         a = rs.uniform(-1, 1, size=(E, 2)).astype(np.float32)
         a[:, 1] = np.abs(a[:, 1])
-        obs, rew, term, trunc, infos = vec.step(a)
+        if k % 2 == 0:
+            buf = pinned[(k // 2) % 2]
+            buf[...] = a
+            obs, rew, term, trunc, infos = vec.step(buf)
+            assert vec._host_io.actions == vec._pinned_acts[buf.ctypes.data].data_ptr()
+        else:
+            obs, rew, term, trunc, infos = vec.step(a)
+            assert vec._host_io.actions == vec._h_actions.data_ptr()
         be = vec.be
         # host rows == the device arrays the same kernel wrote
         np.testing.assert_array_equal(obs, be.obs[0].cpu().numpy())
