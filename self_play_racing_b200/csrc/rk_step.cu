@@ -90,6 +90,7 @@ __device__ __forceinline__ int warp_argmin_d(double d, int idx) {
 #endif
 constexpr int kLevel2Unroll = RK_L2_UNROLL;
 constexpr int kListCap = 512;  // chunk work items per warp batch (tracks are limited to kListMax chunks, rk_types.cuh)
+constexpr int kRing = 64;      // candidate ring of the sweep: < 32 pending before a push of <= 32, evaluated 32 at a time
 
 // Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
 // one column per lane: conflict free) and the scratch of the culled queries.
@@ -102,6 +103,7 @@ struct CullView {
     unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment) of the best wall candidate
     float2* dir32;                // [A*R]
     unsigned short* list;         // [kListCap]
+    unsigned* ring;               // [kRing] pending (segment, ray span) candidates of the sweep's level 2
 };
 // store of a per-environment result; mirrored into the caller's pinned host arena when zero-copy is on (consecutive
 // environments are consecutive lanes, so a warp's stores form one PCIe-friendly run)
@@ -121,7 +123,9 @@ __host__ __device__ inline size_t slot_area_bytes(int A, int R) {
 }
 // behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode)
 __host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
-    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + 15) / 16 * 16;
+    // (the candidate ring exists for multi envs only: one more KB per CTA would push the single env's 7 CTAs per SM past
+    //  the 196 KB shared-memory carve-out and halve its L1 -- measured 0.1705 -> 0.179 ms)
+    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + (A > 1 ? kRing * 4 : 0) + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -351,6 +355,21 @@ __device__ __forceinline__ float sweep_atan2(float y, float x) {
     return copysignf(r, y);
 }
 
+// Polar angle for BINNING boundary points between rays (level 2): atan(a) ~ a (pi/4 + 0.273 (1 - a)) on [0, 1], |error| <=
+// 3.8e-3 rad (kBinAngleErr, part of the binning slack), two FMAs instead of nine.  A coarse angle only ADDS (segment, ray)
+// candidates next to a bin edge; every candidate is verified against its ray (straddle test) before it may post a key, so
+// the extra ones cost an evaluation slot each and never become false winners.
+constexpr float kBinAngleErr = 4.0e-3f;
+__device__ __forceinline__ float sweep_angle_coarse(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, mx);
+    float r = a * fmaf(a, -0.273f, 1.0583982f);
+    if (ay > ax) r = 1.57079632679f - r;
+    if (x < 0.f) r = 3.14159265359f - r;
+    return copysignf(r, y);
+}
+
 // fp32 candidate search of the R rays of one car against the walls, as an
 // angular sweep.  The rays are uniformly spaced in angle around the heading
 // (np.linspace, racing_env.py:45 / multi_racing_env.py:50), so a boundary
@@ -386,7 +405,8 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
     const float2* dirs = cv.dir32 + slot0;
     unsigned long long* keys = cv.ray_key + slot0;
     const float inv_dphi = p.inv_dphi, u_off = p.cone_half * inv_dphi;
-    const float wrap_thr = 3.1405926f * inv_dphi;
+    constexpr bool kRingMode = KIND == RK_ENV_MULTI;   // (see level 2)
+    const float wrap_thr = (3.1405926f - (kRingMode ? 2.f * kBinAngleErr : 0.f)) * inv_dphi;   // (the ring mode bins coarse angles)
     const float range = (KIND == RK_ENV_MULTI) ? 50.01f : INFINITY;
     for (int pass = 0; pass < p.n_shells; ++pass) {
         // shell of this pass: chunks whose nearest possible point lies in (lo, hi]
@@ -426,6 +446,35 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
         }
         __syncwarp();
         // ---- level 2 ----
+        // Multi env (one pass over ~24 chunks per car): segments that can be crossed by a ray post ONE item (segment,
+        // first ray, ray count) to the warp's ring; whenever 32 items are pending they are evaluated one per lane -- the
+        // candidate loop inside the chunk loop runs at ~3 of 32 lanes -- and the binning angle is the coarse one, since
+        // every candidate is verified against its ray anyway.  Measured 0.277 -> 0.268 ms at 65,536 two-car envs.  The
+        // single env (two short shells per car, whose candidates the second shell's pruning needs at once) keeps the
+        // in-loop evaluation and the accurate angle: the ring's per-chunk push and per-shell flush cost it 13 %.
+        unsigned head = 0, tail = 0;
+        auto evaluate = [&](unsigned n_items) {
+            if (lane < n_items) {
+                const unsigned it = cv.ring[(head + lane) & (kRing - 1)];
+                const int seg = (int)(it & 0xffffu), k0 = (int)((it >> 16) & 0x7fu), kn = (int)((it >> 23) & 0xffu);
+                const int side = seg >= N, pt = seg - side * N;
+                const float2 P = bpt[side * (N + 1) + pt], Q = bpt[side * (N + 1) + pt + 1];
+                const float px = P.x - ox, py = P.y - oy, qx = Q.x - ox, qy = Q.y - oy;
+                const float vx = qx - px, vy = qy - py, num = px * vy - py * vx;
+                for (int k = k0; k < k0 + kn; ++k) {
+                    const float2 d = dirs[k];
+                    const float cp = d.x * py - d.y * px, cq = d.x * qy - d.y * qx;  // signed distances to the ray's line
+                    const bool straddle = (cp <= kPerpSlack && cq >= -kPerpSlack) || (cp >= -kPerpSlack && cq <= kPerpSlack);
+                    const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
+                    const float tlo = fminf(tp_, tq_), thi = fmaxf(tp_, tq_);
+                    if (!straddle || thi < -kFrontSlack) continue;
+                    const float den = d.x * vy - d.y * vx;
+                    float t = (fabsf(den) > 1e-12f) ? __fdividef(num, den) : tlo;
+                    t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
+                    atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)seg);
+                }
+            }
+        };
 #pragma unroll kLevel2Unroll
         for (int it = 0; it < count; it += 2) {
             const int my = it + half;
@@ -438,19 +487,21 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                 const float2 P = bpt[side * (N + 1) + pt];
                 px = P.x - ox; py = P.y - oy;
             }
-            const float u = sweep_atan2(py * hc - px * hs, px * hc + py * hs) * inv_dphi + u_off;
+            const float ly_ = py * hc - px * hs, lx_ = px * hc + py * hs;
+            const float u = (kRingMode ? sweep_angle_coarse(ly_, lx_) : sweep_atan2(ly_, lx_)) * inv_dphi + u_off;
             const float qx = __shfl_down_sync(kFull, px, 1), qy = __shfl_down_sync(kFull, py, 1);
             const float un = __shfl_down_sync(kFull, u, 1);
+            int klo = 1, khi = 0;
+            bool slow = false;
             if (act && j < kRaySegs && pt < N) {
                 const float m2 = fminf(px * px + py * py, qx * qx + qy * qy);
-                const bool slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
-                // angular error budget: table/origin rounding (<= 1.6e-5 / distance) + atan2 + heading rounding
-                const float slack = (3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
-                int klo = 0, khi = R - 1;
-                if (!slow) {
-                    klo = max(0, (int)ceilf(fminf(u, un) - slack));
-                    khi = min(R - 1, (int)floorf(fmaxf(u, un) + slack));
-                }
+                slow = fabsf(un - u) > wrap_thr || m2 < 0.25f;
+                // angular error budget: the coarse angle + table/origin rounding (<= 1.6e-5 / distance) + heading rounding
+                const float slack = ((kRingMode ? kBinAngleErr : 0.f) + 3e-6f + 1.6e-5f * rsqrtf(m2)) * inv_dphi;
+                klo = slow ? 0 : max(0, (int)ceilf(fminf(u, un) - slack));
+                khi = slow ? R - 1 : min(R - 1, (int)floorf(fmaxf(u, un) + slack));
+            }
+            if (!kRingMode) {
                 for (int k = klo; k <= khi; ++k) {
                     const float2 d = dirs[k];
                     const float tp_ = px * d.x + py * d.y, tq_ = qx * d.x + qy * d.y;
@@ -467,8 +518,25 @@ __device__ __forceinline__ void raycast_walls_culled(const TrackPool& tp, const 
                     t = fmaxf(fminf(fmaxf(t, tlo), thi), 0.f);  // the crossing lies between the end points
                     atomicMin(&keys[k], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(side * N + pt));
                 }
+                continue;
+            }
+            const bool has = klo <= khi;
+            const unsigned m = __ballot_sync(kFull, has);
+            if (m) {
+                if (has)
+                    cv.ring[(tail + __popc(m & lt)) & (kRing - 1)] =
+                        (unsigned)(side * N + pt) | ((unsigned)klo << 16) | ((unsigned)(khi - klo + 1) << 23);
+                tail += __popc(m);
+                if (tail - head >= 32u) {
+                    __syncwarp();
+                    evaluate(32u);
+                    head += 32u;
+                    __syncwarp();
+                }
             }
         }
+        __syncwarp();
+        if (kRingMode && tail != head) evaluate(tail - head);
         __syncwarp();
     }
 }
@@ -708,6 +776,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     cv.ray_key = reinterpret_cast<unsigned long long*>(wbase + sizeof(CarS));
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(wbase + sizeof(CarS) + slot_area_bytes(A, R));
+    cv.ring = reinterpret_cast<unsigned*>(wbase + sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2);
 
     // ---- lane = one car -------------------------------------------------------
     const int g = lane / A, a = lane - g * A;     // environment within the warp, car within the environment
