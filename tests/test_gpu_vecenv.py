@@ -386,7 +386,15 @@ def test_tensor_core_gradient_matches_fma_kernel(pkg, n, obs_dim, variant):
     ret = val + 0.3 * torch.randn(B, device='cuda', generator=g)
     with torch.no_grad():
         _, logp, _, _ = agent.get_action_and_value(obs, act)
+    logp_new = logp
     logp = logp + 0.15 * torch.randn(B, device='cuda', generator=g)
+    # The clipped surrogate is discontinuous in the probability ratio at 1 -+ clip: a row within rounding distance of a
+    # clip edge contributes its whole gradient or nothing depending on the last bit of logp (seen at 40,000 rows: ONE row
+    # flips between the kernels and moves the actor gradient by 6e-4 of its largest element, identically in both
+    # tensor-core variants).  Rows that close to an edge are moved off it; the comparison is about the arithmetic.
+    ratio = (logp_new - logp).exp()
+    near = ((ratio - 0.8).abs() < 2e-3) | ((ratio - 1.2).abs() < 2e-3)
+    logp = torch.where(near, logp + 0.02, logp)
     idx = torch.randperm(B, device='cuda', generator=g)[:n]
     params = list(agent.parameters())
     fma = PpoMinibatchGrad(params, agent.log_std, obs_dim, 0.2, 0.5)
