@@ -26,7 +26,10 @@ constexpr int kNT = 128;        // threads per CTA
 constexpr int kLD = kTS + 4;    // activation row stride: rows 4 banks apart, 16-byte aligned
 constexpr int kWLD = kH + 4;    // W2^T row stride (column reads in the backward product stay conflict-free)
 constexpr int kMaxD = 20;       // observation width supported by the register tile of dW1
-constexpr int kNetStride = 5632;  // floats per CTA partial (>= 64*20 + 64 + 4096 + 64 + 128 + 2)
+constexpr int kNetStride = 5648;  // floats per CTA partial (a multiple of 16)
+static_assert(kNetStride >= kH * kMaxD + kH + kH * kH + kH + 2 * kH + 2,
+              "one partial = W1 [64][D], b1, W2, b2, W3 [2][64], b3 (5,632 was 2 floats short at D = 20: the actor's db3 of "
+              "one CTA overlapped dW1[0][0..1] of the next)");
 
 struct NetPtrs { const float *W1, *b1, *W2, *b2, *W3, *b3; };
 struct GradArgs {

@@ -291,7 +291,7 @@ def test_graphed_update_equals_eager_update(pkg):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6)
 
 
-@pytest.mark.parametrize('n,obs_dim,use_idx', [(1000, 19, True), (128, 15, False), (5000, 19, True), (77, 7, True)])
+@pytest.mark.parametrize('n,obs_dim,use_idx', [(1000, 19, True), (128, 15, False), (5000, 19, True), (77, 7, True), (3000, 20, True)])
 def test_fused_minibatch_gradient_matches_autograd(pkg, n, obs_dim, use_idx):
     """rk_ppo_minibatch_grad (forward + PPO loss + backward of both MLPs in one
     kernel, rows gathered through the minibatch indices) against torch autograd of
