@@ -29,12 +29,12 @@ const double* pool_ctrl(const PoolBuffers* p);
 static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static std::atomic<uint64_t> g_attr_done[4];   // bit d of slot s: attribute set on device d
+static std::atomic<uint64_t> g_attr_done[8];   // bit d of slot s: attribute set on device d
 bool first_use_on_device(int slot) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
     const uint64_t bit = 1ull << dev;
-    return (g_attr_done[slot & 3].fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+    return (g_attr_done[slot & 7].fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
 }
 
 }  // namespace rk

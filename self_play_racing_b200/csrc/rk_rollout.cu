@@ -6,9 +6,11 @@
 //                        (environment/wrappers.py:29-39)
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rk_types.cuh"
 #include "rk_ppo_loss.cuh"
+#include "rk_umma.cuh"
 
 namespace rk {
 
@@ -73,8 +75,7 @@ __host__ __device__ inline int policy_packed_floats(int obs_dim) {
     return (n + 3) / 4 * 4;
 }
 
-// tanh through ex2.approx + rcp.approx: |error| < 2e-7 absolute, 6 instructions
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// tanh_fast (rk_umma.cuh): ex2.approx + rcp.approx, |error| < 2e-7 absolute
 
 // y[s][j] = b[j] + sum_i Wt[i][j] * x_s[i] for the thread's two samples.  x lives
 // in shared memory, one column per sample (stride kPolicyCols), so the loop over
@@ -245,6 +246,203 @@ policy_act_kernel(const PolicyJobs jobs, int obs_dim) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// policy_act_tc_kernel -- the same entry point on the 5th-generation tensor cores (default; RK_B200_POLICY_TC=0 selects
+// the FFMA kernel above).  The two 64-wide layers of each MLP run as tcgen05.mma kind::tf32 products with the 3-term
+// hi/lo split (fp32-grade accuracy, rk_umma.cuh) chained through tensor memory exactly like the forward half of the
+// gradient kernel (rk_train.cu): a thread pair owns a sample = a TMEM lane, reads its accumulator row with tcgen05.ld,
+// applies bias / tanh and writes the row back as the A operand of the next layer; the weights sit in shared memory as
+// K-major hi / lo tiles (staged once per CTA, re-staged only when a pool launch crosses into a block that plays another
+// snapshot).  A CTA walks a contiguous range of 128-sample tiles; two CTAs per SM (256 TMEM columns each) overlap
+// one's tensor-core waits with the other's epilogues.  The critic re-uses the observation operand already in TMEM.
+// Sampling (Philox Box-Muller, clamp, log-prob) is the code of the FFMA kernel: same counters, same noise.
+// ---------------------------------------------------------------------------
+constexpr int kPT = 256;      // threads: warps w and w + 4 share TMEM lane quarter w & 3 and split the 64 columns
+constexpr int kPXK = 24;      // layer-1 reduction length padded to a multiple of the MMA K
+constexpr int kPcAcc = 0, kPcXh = 64, kPcXl = 96, kPcHh = 128, kPcHl = 192, kPcCols = 256;
+// per network: W1h W1l [64][24], W2h W2l [64][64], b1 [64], b2 [64], W3 [2][64], b3 [4]
+constexpr int kPoW1l = kHidden * kPXK, kPoW2h = 2 * kHidden * kPXK, kPoW2l = kPoW2h + kHidden * kHidden,
+              kPob1 = kPoW2l + kHidden * kHidden, kPob2 = kPob1 + kHidden, kPoW3 = kPob2 + kHidden, kPob3 = kPoW3 + 2 * kHidden,
+              kPNetFloats = kPob3 + 4;
+constexpr size_t kPolicyTcSmemFloats = 2 * (size_t)kPNetFloats + 4 * kUmmaTS;
+
+__global__ void __launch_bounds__(kPT, 2) policy_act_tc_kernel(const PolicyJobs jobs, int obs_dim) {
+    extern __shared__ __align__(1024) float sm[];
+    const PolicyJob& jb = jobs.job[blockIdx.y];
+    const int B = jb.B;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* __restrict__ action = jb.action;
+    const int64_t act_stride = jb.act_stride;
+    const uint64_t seed = jb.seed, counter = jb.counter;
+    if (jb.params == nullptr) {   // uniform Box([-1,0],[1,1]) samples, the same stream as random_act_kernel
+        for (int b = blockIdx.x * kPT + tid; b < B; b += gridDim.x * kPT) {
+            uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x72616e64u};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            action[(size_t)b * act_stride] = 2.f * u01(c[0]) - 1.f;
+            action[(size_t)b * act_stride + 1] = u01(c[1]);
+        }
+        return;
+    }
+    const int ntiles = (B + kUmmaTS - 1) / kUmmaTS;
+    const int per_cta = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = blockIdx.x * per_cta, t_end = min(ntiles, t_begin + per_cta);
+    if (t_begin >= t_end) return;   // (the whole CTA: nothing has been allocated yet)
+    const bool want_v = jb.value != nullptr;
+    const int nnet = want_v ? 2 : 1;
+    const int half = warp >> 2, srow = (warp & 3) * 32 + lane, cbase = half * 32;
+    float* OP = sm + 2 * kPNetFloats;   // [2 halves][2 outputs][128] partial output-layer sums
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kPcCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    unsigned phase = 0;
+    const int n0 = obs_dim * kHidden;
+    float s0 = 1.f, s1 = 1.f, ls0 = 0.f, ls1 = 0.f;
+    int cur_pid = -2;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        // ---- the parameter block of this tile's samples (a pool launch: the block's snapshot) ----
+        const int pid = jb.block_policy != nullptr ? (int)jb.block_policy[(tile * kUmmaTS) / jb.block_len] : -1;
+        if (pid != cur_pid) {
+            cur_pid = pid;
+            const float* __restrict__ pp = jb.params + (pid >= 0 ? (int64_t)pid * jb.pool_stride : 0);
+            __syncthreads();   // (every thread has finished with the previous block's biases / output weights)
+            for (int net = 0; net < nnet; ++net) {
+                // packed block: actor W0t[obs][64] b0 W2t[64][64] b2 W4[2][64] b4[2] log_std[2]; critic W0t b0 W2t b2 W4[64] b4[1]
+                const float* __restrict__ src = pp + (net == 0 ? 0 : n0 + kHidden + kHidden * kHidden + kHidden + 2 * kHidden + 4);
+                float* dst = sm + net * kPNetFloats;
+                for (int q = tid; q < kPXK * kHidden; q += kPT) {
+                    const int i = q >> 6, j = q & 63;
+                    uint32_t hi = 0, lo = 0;
+                    if (i < obs_dim) split_tf32(src[i * kHidden + j], hi, lo);
+                    dst[umma_off(j, i, kPXK)] = __uint_as_float(hi);
+                    dst[kPoW1l + umma_off(j, i, kPXK)] = __uint_as_float(lo);
+                }
+                const float* __restrict__ w2 = src + n0 + kHidden;
+                for (int q = tid; q < kHidden * kHidden; q += kPT) {
+                    const int i = q >> 6, j = q & 63;
+                    uint32_t hi, lo;
+                    split_tf32(w2[q], hi, lo);
+                    dst[kPoW2h + umma_off(j, i, kHidden)] = __uint_as_float(hi);
+                    dst[kPoW2l + umma_off(j, i, kHidden)] = __uint_as_float(lo);
+                }
+                const int nout = net == 0 ? 2 : 1;
+                for (int q = tid; q < kHidden; q += kPT) { dst[kPob1 + q] = src[n0 + q]; dst[kPob2 + q] = w2[kHidden * kHidden + q]; }
+                const float* __restrict__ w4 = w2 + kHidden * kHidden + kHidden;
+                for (int q = tid; q < nout * kHidden + nout; q += kPT) dst[kPoW3 + (q < nout * kHidden ? q : 2 * kHidden + q - nout * kHidden)] = w4[q];
+            }
+            const float* __restrict__ lstd = pp + n0 + kHidden + kHidden * kHidden + kHidden + 2 * kHidden + 2;
+            ls0 = lstd[0]; ls1 = lstd[1];
+            s0 = __expf(ls0); s1 = __expf(ls1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the weight tiles are read by the tensor core
+            __syncthreads();
+        }
+        // ---- this tile's observation rows: two threads per sample (columns 0-15 / 16-23), hi + lo into TMEM ----
+        const int b = tile * kUmmaTS + srow;
+        const bool valid = b < B;
+        {
+            const float* __restrict__ src = jb.obs + (size_t)(valid ? b : 0) * jb.obs_stride;
+#pragma unroll
+            for (int c8 = 0; c8 < 16; c8 += 8) {
+                if (c8 == 0 || half == 0) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int i = half * 16 + c8 + c;
+                        split_tf32_fast((valid && i < obs_dim) ? src[i] : 0.f, hi[c], lo[c]);
+                    }
+                    tmem_st8(lane_base + kPcXh + half * 16 + c8, hi);
+                    tmem_st8(lane_base + kPcXl + half * 16 + c8, lo);
+                }
+            }
+        }
+        tmem_publish_and_sync();
+        for (int net = 0; net < nnet; ++net) {
+            const float* W = sm + net * kPNetFloats;
+            const int nout = net == 0 ? 2 : 1;
+            if (warp == 0 && elect_one()) issue_product(tmem, kPcAcc, kPcXh, kPcXl, W, W + kPoW1l, kPXK, &bar);
+            wait_product(&bar, phase);
+            {
+                uint32_t v[32];
+                tmem_ld32(lane_base + kPcAcc + cbase, v);
+#pragma unroll
+                for (int c8 = 0; c8 < 32; c8 += 8) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        split_tf32_fast(tanh_fast(__uint_as_float(v[c8 + c]) + W[kPob1 + cbase + c8 + c]), hi[c], lo[c]);
+                    tmem_st8(lane_base + kPcHh + cbase + c8, hi);
+                    tmem_st8(lane_base + kPcHl + cbase + c8, lo);
+                }
+            }
+            tmem_publish_and_sync();
+            if (warp == 0 && elect_one()) issue_product(tmem, kPcAcc, kPcHh, kPcHl, W + kPoW2h, W + kPoW2l, kHidden, &bar);
+            wait_product(&bar, phase);
+            {
+                float out[2] = {0.f, 0.f};
+                uint32_t v[32];
+                tmem_ld32(lane_base + kPcAcc + cbase, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int j = cbase + c;
+                    const float h = tanh_fast(__uint_as_float(v[c]) + W[kPob2 + j]);
+                    out[0] = fmaf(W[kPoW3 + j], h, out[0]);
+                    if (nout == 2) out[1] = fmaf(W[kPoW3 + kHidden + j], h, out[1]);
+                }
+                OP[(half * 2 + 0) * kUmmaTS + srow] = out[0];
+                OP[(half * 2 + 1) * kUmmaTS + srow] = out[1];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (half == 0 && valid) {
+                const float o0 = W[kPob3] + (OP[srow] + OP[2 * kUmmaTS + srow]);
+                if (net == 0) {
+                    const float o1 = W[kPob3 + 1] + (OP[kUmmaTS + srow] + OP[3 * kUmmaTS + srow]);
+                    const float m0 = tanh_fast(o0), m1 = tanh_fast(o1);
+                    if (jb.mean != nullptr) {
+                        jb.mean[2 * (size_t)b] = m0;
+                        jb.mean[2 * (size_t)b + 1] = m1;
+                    }
+                    // a ~ N(mu, exp(log_std)) clamped to [-1, 1] (ppo.py:47-54); Box-Muller on Philox
+                    uint32_t c[4] = {(uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32), 0x706f6c79u};
+                    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+                    const float rad = sqrtf(-2.f * logf(u01(c[0])));
+                    float sn, cs;
+                    sincosf(6.2831853071795865f * u01(c[1]), &sn, &cs);
+                    const float a0 = fminf(fmaxf(fmaf(s0, rad * cs, m0), -1.f), 1.f);
+                    const float a1 = fminf(fmaxf(fmaf(s1, rad * sn, m1), -1.f), 1.f);
+                    action[(size_t)b * act_stride] = a0;
+                    action[(size_t)b * act_stride + 1] = a1;
+                    if (jb.logprob != nullptr) {
+                        // torch Normal.log_prob: -(a-mu)^2 / (2 var) - log_std - log(sqrt(2 pi)), summed (ppo.py:56)
+                        const float kLogSqrt2Pi = 0.9189385332046727f;
+                        const float l0 = -((a0 - m0) * (a0 - m0)) / (2.f * s0 * s0) - ls0 - kLogSqrt2Pi;
+                        const float l1 = -((a1 - m1) * (a1 - m1)) / (2.f * s1 * s1) - ls1 - kLogSqrt2Pi;
+                        jb.logprob[b] = l0 + l1;
+                    }
+                } else {
+                    jb.value[b] = o0;
+                }
+            }
+            __syncthreads();   // OP is rewritten by the next network / tile
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kPcCols));
+}
+
 // ---------------------------------------------------------------------------
 // PPO update helpers (reference agent/ppo.py:156-209): one launch gathers a
 // minibatch, one launch turns the network outputs into the loss gradients.
@@ -376,8 +574,21 @@ int launch_policy_jobs(const PolicyJobs& jobs, int n_jobs, int obs_dim, cudaStre
         if (j.block_policy != nullptr && (j.block_len <= 0 || j.block_len % kPolicyCols != 0 || (j.pool_stride & 3) != 0)) return 2;
     }
     if (maxB <= 0) return 0;
+    static const bool use_tc = [] { const char* e = getenv("RK_B200_POLICY_TC"); return !(e && e[0] == '0'); }();
+    if (use_tc && obs_dim <= kPXK) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t smem_tc = kPolicyTcSmemFloats * sizeof(float);
+        if (first_use_on_device(0))  // the attribute is per device, not per process
+            cudaFuncSetAttribute(policy_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+        const int ntiles = (maxB + kUmmaTS - 1) / kUmmaTS, ctas = 2 * sms / n_jobs;   // two CTAs per SM over all jobs
+        policy_act_tc_kernel<<<dim3(ntiles < ctas ? ntiles : ctas, n_jobs), kPT, smem_tc, stream>>>(jobs, obs_dim);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     const size_t smem = ((size_t)policy_packed_floats(obs_dim) + (size_t)kHidden * kPolicyCols) * sizeof(float);
-    if (first_use_on_device(0))  // the attribute is per device, not per process
+    if (first_use_on_device(4))  // the attribute is per device, not per process
         cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     policy_act_kernel<<<dim3((maxB + kPolicyCols - 1) / kPolicyCols, n_jobs), kPolicyThreads, smem, stream>>>(jobs, obs_dim);
     count_launch();

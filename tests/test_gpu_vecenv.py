@@ -468,7 +468,9 @@ def test_opponent_pool_one_launch_equals_per_opponent_launches(pkg):
         sel = torch.cat([torch.arange(b * block, min((b + 1) * block, B)) for b in range(4) if int(ids[b]) == k]).cuda()
         with torch.no_grad():
             mu = agents[k].actor_mu(obs[sel])
-        torch.testing.assert_close(mean[sel], mu, rtol=0, atol=2e-6)
+        # (tcgen05 inference: 3-term TF32 products, >= 21 bits per factor, and the tensor core's truncating fp32
+        #  accumulation; these agents carry 0.3-sigma weight noise, i.e. pre-activations of several units)
+        torch.testing.assert_close(mean[sel], mu, rtol=0, atol=4e-6)
     # through the vector env: the opponent's actions differ between blocks with different members
     vec = env_mod.BatchedRacingVecEnv.synthetic('multi', 1024, n_tracks=4, num_agents=2, selfplay=True, seed=0)
     vec.set_opponents(agents, block_policy=[0, 1, 2, 0], block_len=256)
