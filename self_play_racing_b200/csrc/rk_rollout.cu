@@ -322,20 +322,36 @@ __global__ void __launch_bounds__(kPT, 2) policy_act_tc_kernel(const PolicyJobs 
                 // packed block: actor W0t[obs][64] b0 W2t[64][64] b2 W4[2][64] b4[2] log_std[2]; critic W0t b0 W2t b2 W4[64] b4[1]
                 const float* __restrict__ src = pp + (net == 0 ? 0 : n0 + kHidden + kHidden * kHidden + kHidden + 2 * kHidden + 4);
                 float* dst = sm + net * kPNetFloats;
-                for (int q = tid; q < kPXK * kHidden; q += kPT) {
-                    const int i = q >> 6, j = q & 63;
-                    uint32_t hi = 0, lo = 0;
-                    if (i < obs_dim) split_tf32(src[i * kHidden + j], hi, lo);
-                    dst[umma_off(j, i, kPXK)] = __uint_as_float(hi);
-                    dst[kPoW1l + umma_off(j, i, kPXK)] = __uint_as_float(lo);
+                // (all of a thread's loads are issued before the first split: the block comes from L2)
+                {
+                    float w[kPXK * kHidden / kPT];
+#pragma unroll
+                    for (int k = 0; k < kPXK * kHidden / kPT; ++k) {
+                        const int q = tid + k * kPT, i = q >> 6;
+                        w[k] = i < obs_dim ? src[q] : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < kPXK * kHidden / kPT; ++k) {
+                        const int q = tid + k * kPT, i = q >> 6, j = q & 63;
+                        uint32_t hi, lo;
+                        split_tf32_fast(w[k], hi, lo);
+                        dst[umma_off(j, i, kPXK)] = __uint_as_float(hi);
+                        dst[kPoW1l + umma_off(j, i, kPXK)] = __uint_as_float(lo);
+                    }
                 }
                 const float* __restrict__ w2 = src + n0 + kHidden;
-                for (int q = tid; q < kHidden * kHidden; q += kPT) {
-                    const int i = q >> 6, j = q & 63;
-                    uint32_t hi, lo;
-                    split_tf32(w2[q], hi, lo);
-                    dst[kPoW2h + umma_off(j, i, kHidden)] = __uint_as_float(hi);
-                    dst[kPoW2l + umma_off(j, i, kHidden)] = __uint_as_float(lo);
+                {
+                    float w[kHidden * kHidden / kPT];
+#pragma unroll
+                    for (int k = 0; k < kHidden * kHidden / kPT; ++k) w[k] = w2[tid + k * kPT];
+#pragma unroll
+                    for (int k = 0; k < kHidden * kHidden / kPT; ++k) {
+                        const int q = tid + k * kPT, i = q >> 6, j = q & 63;
+                        uint32_t hi, lo;
+                        split_tf32_fast(w[k], hi, lo);
+                        dst[kPoW2h + umma_off(j, i, kHidden)] = __uint_as_float(hi);
+                        dst[kPoW2l + umma_off(j, i, kHidden)] = __uint_as_float(lo);
+                    }
                 }
                 const int nout = net == 0 ? 2 : 1;
                 for (int q = tid; q < kHidden; q += kPT) { dst[kPob1 + q] = src[n0 + q]; dst[kPob2 + q] = w2[kHidden * kHidden + q]; }
