@@ -642,3 +642,30 @@ def gae(rewards, dones, values, next_value, next_done, gamma, lam):
         running = delta + gl * nnt * running
         adv[t] = running
     return adv, adv + values
+
+
+# --------------------------------------------------------------------------
+# P: Agent forward pass (agent/ppo.py:11-62), float64
+# --------------------------------------------------------------------------
+def agent_forward(state_dict, obs, action=None):
+    """Agent.get_action_and_value's deterministic part for a state_dict of numpy arrays (torch's key names):
+    mu = actor_mu(obs) -- Linear-Tanh-Linear-Tanh-Linear-Tanh (agent/ppo.py:18-26), value = critic(obs) --
+    Linear-Tanh-Linear-Tanh-Linear (ppo.py:31-37); with `action` also Normal(mu, exp(log_std)).log_prob(action)
+    summed over the two action dimensions (ppo.py:45-56).  Returns (mu [n, 2], value [n], logp [n] or None)."""
+    sd = {k: np.asarray(v, dtype=np.float64) for k, v in state_dict.items()}
+    x = np.asarray(obs, dtype=np.float64)
+
+    def mlp(prefix, last_tanh):
+        h = np.tanh(x @ sd[prefix + '.0.weight'].T + sd[prefix + '.0.bias'])
+        h = np.tanh(h @ sd[prefix + '.2.weight'].T + sd[prefix + '.2.bias'])
+        o = h @ sd[prefix + '.4.weight'].T + sd[prefix + '.4.bias']
+        return np.tanh(o) if last_tanh else o
+
+    mu = mlp('actor_mu', True)
+    value = mlp('critic', False)[:, 0]
+    logp = None
+    if action is not None:
+        ls = sd['log_std']
+        a = np.asarray(action, dtype=np.float64)
+        logp = (-((a - mu) ** 2) / (2.0 * np.exp(ls) ** 2) - ls - 0.5 * np.log(2.0 * np.pi)).sum(1)
+    return mu, value, logp

@@ -262,3 +262,14 @@ def test_rollout_buffers_of_the_reference_loop(golden):
             ep_r += list(info['episode_r'][info['_episode']]); ep_l += list(info['episode_l'][info['_episode']])
         np.testing.assert_allclose(ep_r, g[f'ep_r{it}'], rtol=0, atol=1e-9)
         np.testing.assert_array_equal(ep_l, g[f'ep_l{it}'])
+
+
+def test_agent_forward_matches_reference_agent(golden):
+    """oracle.agent_forward (float64 restatement of agent/ppo.py:11-62) against the outputs the reference's torch Agent
+    recorded for the same parameters and observations: mean, value and the log-probability of the recorded action."""
+    g = golden('agent')
+    sd = {k[3:]: v for k, v in g.items() if k.startswith('sd.')}
+    mu, value, logp = O.agent_forward(sd, g['obs'], action=g['act'])
+    np.testing.assert_allclose(mu, g['mu'], rtol=0, atol=5e-7)          # float32 torch vs float64 numpy
+    np.testing.assert_allclose(value, g['value'][:, 0], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(logp, g['logp'], rtol=0, atol=2e-5)
