@@ -615,7 +615,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         float* Xcur = X + buf * kMaxD * kLD;
         float* Xoth = X + (buf ^ 1) * kMaxD * kLD;
         // ---- layer 1 on the tensor core: ACC0 = X W1^T; meanwhile dW1 of the previous tile ----
-        if (tid == 0) issue_product(tmem, kColAcc0, kColXh, kColXl, W1h, W1l, kXK, &bar);
+        if (warp == 0 && elect_one()) issue_product(tmem, kColAcc0, kColXh, kColXl, W1h, W1l, kXK, &bar);
         if (have_prev) dw1(Xoth);
         __syncthreads();   // dW1 has finished reading H1 (dZ1 of the previous tile) before the epilogue overwrites it
         wait_product(&bar, phase);
@@ -638,7 +638,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         }
         tmem_publish_and_sync();
         // ---- layer 2: ACC1 = H1 W2^T; meanwhile the next tile's rows are gathered (layer 1 has released the X columns) ----
-        if (tid == 0) issue_product(tmem, kColAcc1, kColHh, kColHl, W2h, W2l, kH, &bar);
+        if (warp == 0 && elect_one()) issue_product(tmem, kColAcc1, kColHh, kColHl, W2h, W2l, kH, &bar);
         if (tile + (int)gridDim.x < ntiles) gather(tile + gridDim.x, Xoth, n_valid, n_a0, n_a1, n_lp, n_adv, n_ret, n_val);
         wait_product(&bar, phase);
         {
@@ -720,7 +720,7 @@ __device__ __forceinline__ void net_body_tc(const GradArgs& g, const NetPtrs& P,
         }
         tmem_publish_and_sync();
         // ---- dH1 = dZ2 W2 on the tensor core (ACC0) while the CUDA cores accumulate dW2 += H1^T dZ2 ----
-        if (tid == 0) issue_product(tmem, kColAcc0, kColZh, kColZl, W2th, W2tl, kH, &bar);
+        if (warp == 0 && elect_one()) issue_product(tmem, kColAcc0, kColZh, kColZl, W2th, W2tl, kH, &bar);
         {
             const float* ha = H1 + ti * kLD + kg * 64;
             const float* zb = H2 + tj * kLD + kg * 64;
