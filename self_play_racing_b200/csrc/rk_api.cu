@@ -51,6 +51,7 @@ struct rk_env_s {
     // staged launch plan (environments grouped by track); null when not applicable
     int32_t *group_env = nullptr, *group_count = nullptr, *cta_track = nullptr;
     int n_ctas = 0, stage_bytes = 0;
+    int list_cap = 512;                // per-warp chunk-list entries the step kernel reserves (sized by set_tracks)
     // internal streams / events of rk_step_host
     cudaStream_t hstream[8] = {nullptr};
     cudaEvent_t hevent[9] = {nullptr};
@@ -276,6 +277,22 @@ static int set_tracks_common(rk_handle h, const double* ctrl, const int32_t* n_c
                 return 1;
             }
         }
+    h->list_cap = 512;
+    if (const char* env = getenv("RK_B200_LIST_CAP")) {
+        // Opt-in: size the step kernel's per-warp chunk list for the pool's largest track (+ 16 entries of scratch).  At
+        // 65,536 two-car envs that takes 7 CTAs x 26 KB of shared memory below the 164 KB carve-out (L1 60 -> 92 KB):
+        // step kernel 0.2685 -> 0.2644 ms device-resident, but the Gymnasium face gets SLOWER (0.333 -> 0.344 ms; the
+        // inference kernel needs the 196 KB carve-out, and alternating configurations cost more than the larger L1
+        // wins when the two kernels are launched per step from the host) -- hence off by default.
+        if (strcmp(env, "auto") == 0) {
+            int most = 0;
+            for (int t = 0; t < n_tracks; ++t) {
+                const TrackMeta& m = *pool_host_meta(h->pool, t);
+                most = std::max(most, std::max((int)m.n_bchunk, (int)m.n_wchunk));
+            }
+            h->list_cap = std::min(512, (most + 16 + 31) / 32 * 32);
+        }
+    }
     return plan_staged_launch(h, e2t);
 }
 
@@ -398,6 +415,7 @@ static int fill_params(rk_handle h, StepParams& p, const char* who) {
         for (int i = 0; i < 4; ++i) p.shell[i] = (i < ns - 1) ? sh[i] : INFINITY;
     }
     p.E = h->cfg.num_envs; p.A = h->cfg.num_agents; p.R = h->cfg.num_sensors; p.D = h->D;
+    p.list_cap = h->list_cap;
     p.lane_argmin = h->epw * h->cfg.num_agents >= 16;   // measured: profiles/r02_small_batch.txt (RK_B200_LANE_ARGMIN overrides)
     if (const char* env = getenv("RK_B200_LANE_ARGMIN")) p.lane_argmin = atoi(env) != 0;
     p.env_begin = 0;

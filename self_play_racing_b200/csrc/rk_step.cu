@@ -89,7 +89,8 @@ __device__ __forceinline__ int warp_argmin_d(double d, int idx) {
 #define RK_L2_UNROLL 1
 #endif
 constexpr int kLevel2Unroll = RK_L2_UNROLL;
-constexpr int kListCap = 512;  // chunk work items per warp batch (tracks are limited to kListMax chunks, rk_types.cuh)
+// chunk work items per warp: StepParams::list_cap entries (set_tracks sizes it for the largest track of the pool, <= 512;
+// every KB of shared memory per CTA that is not needed stays L1: 7 CTAs x 26 KB sit above the 164 KB carve-out, 7 x 22.5 KB below)
 constexpr int kRing = 64;      // candidate ring of the sweep: < 32 pending before a push of <= 32, evaluated 32 at a time
 
 // Per-warp shared memory: the pose of the warp's 32 cars (structure of arrays,
@@ -102,7 +103,7 @@ struct CullView {
     float* rows;                  // the slot area seen as floats: car 0's rays of every environment (zero-copy host rows)
     unsigned long long* ray_key;  // [A*R] (fp32 t bits << 32 | segment) of the best wall candidate
     float2* dir32;                // [A*R]
-    unsigned short* list;         // [kListCap]
+    unsigned short* list;         // [list_cap]
     unsigned* ring;               // [kRing] pending (segment, ray span) candidates of the sweep's level 2
 };
 // store of a per-environment result; mirrored into the caller's pinned host arena when zero-copy is on (consecutive
@@ -122,10 +123,10 @@ __host__ __device__ inline size_t slot_area_bytes(int A, int R) {
     return ((per_slot > rows ? per_slot : rows) + 15) / 16 * 16;
 }
 // behind the chunk list: the winning segment id of each of the warp's 32 cars' R rays (culled mode)
-__host__ __device__ inline size_t warp_smem_bytes(int A, int R) {
+__host__ __device__ inline size_t warp_smem_bytes(int A, int R, int list_cap) {
     // (the candidate ring exists for multi envs only: one more KB per CTA would push the single env's 7 CTAs per SM past
     //  the 196 KB shared-memory carve-out and halve its L1 -- measured 0.1705 -> 0.179 ms)
-    return (sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2 + (A > 1 ? kRing * 4 : 0) + 15) / 16 * 16;
+    return (sizeof(CarS) + slot_area_bytes(A, R) + (size_t)list_cap * 2 + (size_t)32 * R * 2 + (A > 1 ? kRing * 4 : 0) + 15) / 16 * 16;
 }
 
 // ---------------------------------------------------------------------------
@@ -737,7 +738,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     TrackMeta stm;                                                // STAGED: the CTA's track, offsets re-based to shared memory
     if (STAGED) {
         stm = tp.meta[p.cta_track[blockIdx.x]];
-        unsigned char* stage = smem_raw + (size_t)kWarpsPerCta * warp_smem_bytes(A, R);
+        unsigned char* stage = smem_raw + (size_t)kWarpsPerCta * warp_smem_bytes(A, R, p.list_cap);
         const unsigned b_bpt = 16u * (unsigned)(stm.n_wp + 1), b_bch = 16u * (unsigned)stm.n_bchunk,
                        b_wch = 16u * (unsigned)stm.n_wchunk;
         const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
         n_env = min(epw, p.env_end - e_base);
     }
     const int* genv = STAGED ? p.group_env + (size_t)gwarp * epw : nullptr;
-    unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R);
+    unsigned char* wbase = smem_raw + (size_t)warp * warp_smem_bytes(A, R, p.list_cap);
     CarS& S = *reinterpret_cast<CarS*>(wbase);
     CullView cv;
     static_assert(sizeof(CarS) % 16 == 0, "the slot area must stay 16-byte aligned");
@@ -776,7 +777,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     cv.ray_key = reinterpret_cast<unsigned long long*>(wbase + sizeof(CarS));
     cv.dir32 = reinterpret_cast<float2*>(cv.ray_key + A * R);
     cv.list = reinterpret_cast<unsigned short*>(wbase + sizeof(CarS) + slot_area_bytes(A, R));
-    cv.ring = reinterpret_cast<unsigned*>(wbase + sizeof(CarS) + slot_area_bytes(A, R) + kListCap * 2 + (size_t)32 * R * 2);
+    cv.ring = reinterpret_cast<unsigned*>(wbase + sizeof(CarS) + slot_area_bytes(A, R) + (size_t)p.list_cap * 2 + (size_t)32 * R * 2);
 
     // ---- lane = one car -------------------------------------------------------
     const int g = lane / A, a = lane - g * A;     // environment within the warp, car within the environment
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
             for (int k = 0; k < 4; ++k) { qx[k + 1] = S.cx[k][l]; qy[k + 1] = S.cy[k][l]; }
             int idx[5];
             if (QUERY != RK_QUERY_EXACT_F64) {
-                int* res = reinterpret_cast<int*>(cv.list + kListCap - 16);   // past any chunk list (lists hold <= kListMax)
+                int* res = reinterpret_cast<int*>(cv.list + p.list_cap - 16);   // past any chunk list (list_cap = largest list + 16, rounded up)
                 argmin_culled5_f64(tp, tm, S, l, lane, cv.list, res);
 #pragma unroll
                 for (int q = 0; q < 5; ++q) idx[q] = res[q];
@@ -1198,7 +1199,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, RK_STEP_MIN_BLOCKS) step_ke
     const unsigned obs_envs = __ballot_sync(kFull, want_obs && a == 0);
     const int nslot = A * R;
     if (QUERY != RK_QUERY_EXACT_F64) {
-        unsigned short* win_sh = cv.list + kListCap;   // [32][R]: fp32 winner of every ray of the warp's cars (culled mode)
+        unsigned short* win_sh = cv.list + p.list_cap;   // [32][R]: fp32 winner of every ray of the warp's cars (culled mode)
         if (QUERY == RK_QUERY_CULLED) {
             // ---- candidate search, environment by environment, all lanes cooperating (angular sweep) ------------------
             for (int gg = 0; gg < n_env; ++gg) {
@@ -1434,7 +1435,7 @@ int launch_step(const StepParams& p, int query_mode, int env_kind, cudaStream_t 
     const int warps = (p.env_end - p.env_begin + epw - 1) / epw;
     const int grid = staged ? p.n_ctas : (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid <= 0) return 0;
-    const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R) + (staged ? (size_t)p.stage_bytes : 0);
+    const size_t smem = kWarpsPerCta * warp_smem_bytes(p.A, p.R, p.list_cap) + (staged ? (size_t)p.stage_bytes : 0);
     using Kern = void (*)(const StepParams);
     const bool single = env_kind == RK_ENV_SINGLE, culled = query_mode == RK_QUERY_CULLED;
     Kern k;

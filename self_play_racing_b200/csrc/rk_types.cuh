@@ -99,6 +99,7 @@ struct StepParams {
     const int32_t* cta_track;    // [n_ctas]
     int32_t n_ctas, stage_bytes;
     int32_t epw;       // environments per warp (<= 32 / A): fewer means more warps for the cooperative queries
+    int32_t list_cap;  // entries of the per-warp chunk list (largest chunk list of the pool + 16, a multiple of 32; <= 512)
     int32_t n_shells;  // distance shells of the ray sweep: (-inf, shell[0]], (shell[0], shell[1]], ...
     float shell[4];
     int32_t E, A, R, D;
